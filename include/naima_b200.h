@@ -1,0 +1,199 @@
+/* naima_b200.h -- C ABI of the B200-native naima likelihood hot path.
+ *
+ * The reference (zblz/naima, pure Python) has no FFI; the functions below are
+ * the entry points a ctypes/cffi binding in the reference would bind to replace
+ * its NumPy hot path.  Each entry cites the reference code it replaces (paths
+ * relative to src/naima/ of zblz/naima @ ba20a64).
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every array pointer is a DEVICE pointer to
+ *    contiguous float64 unless the name ends in `_host`;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *    calls only enqueue work and return immediately;
+ *  - return value: 0 ok, <0 argument error (NB_E*), >0 a cudaError_t;
+ *  - no global state; the library never allocates device memory for the
+ *    caller except inside nb_plan objects (nb_plan.h section below).
+ *
+ * Units (fixed, stripped on the host): energies eV, B in G, T in K, lengths cm,
+ * densities cm^-3, angles rad; differential spectra 1/(s eV).
+ *
+ * Particle distributions (models.py): `kind` is NB_PD_*, `pd_params` is
+ * [W][NB_PD_MAXPAR] with the reference eval() argument order after `e`:
+ *   NB_PD_PL      amplitude[1/eV], e_0, alpha                      models.py:87-92
+ *   NB_PD_ECPL    amplitude, e_0, alpha, e_cutoff, beta            models.py:156-161
+ *   NB_PD_BPL     amplitude, e_0, e_break, alpha_1, alpha_2        models.py:233-238
+ *   NB_PD_ECBPL   amplitude, e_0, e_break, alpha_1, alpha_2, e_cutoff, beta  :329-335
+ *   NB_PD_LOGPAR  amplitude, e_0, alpha, beta                      models.py:401-407
+ *
+ * Integration layout ("rows"): every process reduces to log-log trapezoids
+ * (utils.py:285-355) of n[w,j] * K[r,j] over the particle grid x[j], where the
+ * emissivity table K is walker independent.  Row r = c * N_E + e for
+ * component c (seed photon field, ee/ep, ...) and photon energy e.  Tables are
+ * [R][pitch] with pitch >= N, pitch even.
+ */
+#ifndef NAIMA_B200_H
+#define NAIMA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_PD_PL 0
+#define NB_PD_ECPL 1
+#define NB_PD_BPL 2
+#define NB_PD_ECBPL 3
+#define NB_PD_LOGPAR 4
+#define NB_PD_MAXPAR 8
+
+#define NB_PP_GEANT4 0
+#define NB_PP_PYTHIA8 1
+#define NB_PP_SIBYLL 2
+#define NB_PP_QGSJET 3
+
+#define NB_EINVAL (-1)    /* bad argument (null pointer, negative size, bad kind) */
+#define NB_ETOOLARGE (-2) /* grid does not fit the kernel's shared-memory tiling */
+#define NB_EALIGN (-3)    /* pointer / pitch alignment requirement violated */
+
+#define NB_MAX_TERMS 16
+
+/* library version (major*10000 + minor*100 + patch) */
+int nb_version(void);
+/* human readable text for a return code of this library */
+const char* nb_strerror(int code);
+/* shared-memory bytes nb_contract needs for a grid of N nodes (0 if too large) */
+int nb_contract_smem_bytes(int N, int rows_per_tile);
+
+/* --- particle distribution ------------------------------------------------
+ * out[w][i] = PD.eval(e[i], params[w])                     models.py:87-335 */
+int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
+                  double* out, void* stream);
+
+/* Per-walker integration operands on a particle grid x[N]
+ * (BaseElectron._gam/_nelec radiative.py:147-160, BaseProton._Ep/_J :1002-1015):
+ *   e_j   = (x[j] * e_mul1) * e_mul2        [eV]
+ *   n_j   = PD.eval(e_j) * n_scale
+ *   xn    [w][j] = x[j] * n_j                              j < N
+ *   ds1   [w][j] = ln(n_{j+1}/n_j) * invdlx[j] + 1         j < N-1
+ * invdlx[j] = 1/ln(x[j+1]/x[j]).  wpitch >= N. */
+int nb_pd_prep(int kind, const double* pd_params, int W, const double* x, int N,
+               double e_mul1, double e_mul2, double n_scale, const double* invdlx,
+               double* xn, double* ds1, int wpitch, void* stream);
+
+/* nb_pd_prep that also stores n[w][j] itself in nraw (may be NULL); the
+ * exact contraction (nb_contract exact != 0) consumes nraw. */
+int nb_pd_prep_ex(int kind, const double* pd_params, int W, const double* x, int N,
+                  double e_mul1, double e_mul2, double n_scale, const double* invdlx,
+                  double* xn, double* ds1, double* nraw, int wpitch, void* stream);
+
+/* Total particle energy  W = trapz_loglog(x*n, x*x_to_energy)  in the unit of
+ * x_to_energy (We radiative.py:162-195, Wp :1017-1055), reference operation
+ * order.  out[W]. */
+int nb_particle_energy(int kind, const double* pd_params, int W, const double* x, int N,
+                       double e_mul1, double e_mul2, double n_scale, double x_to_energy,
+                       double* out, void* stream);
+
+/* --- emissivity tables (walker independent) --------------------------------
+ * IC on grey-body seeds: Khangulyan+14 Eq.14 (theta[s] NaN) or Eq.11
+ * (radiative.py:547-607).  Eph = photon energy / mec2.  Writes rows
+ * [row0 + s*N_E + e]. */
+int nb_ic_planck_table(const double* gam, int N, const double* Eph, int N_E,
+                       const double* seed_T, const double* seed_theta, int S, double* K,
+                       int pitch, int row0, void* stream);
+
+/* IC on a monochromatic (Ns == 1, phn = energy density in mec2/cm3) or tabulated
+ * (Ns > 1, phn = dn/dE in 1/(mec2 cm3)) isotropic seed: Aharonian & Atoyan 81
+ * Eq.22 incl. the inner log-log trapezoid over seed energy
+ * (radiative.py:609-655).  eps0 = seed energies / mec2.  Writes rows
+ * [row0 + e]. */
+int nb_ic_seed_table(const double* gam, int N, const double* Eph, int N_E,
+                     const double* eps0, const double* phn, int Ns, double* K, int pitch,
+                     int row0, void* stream);
+
+/* Same with a per-walker seed density phn[W][Ns] (synchrotron self-Compton):
+ * K is [W][N_E][pitch]. */
+int nb_ic_seed_table_batched(const double* gam, int N, const double* Eph, int N_E,
+                             const double* eps0, const double* phn, int Ns, int W,
+                             double* K, int pitch, void* stream);
+
+/* Bremsstrahlung, Baring+99 (radiative.py:838-938): rows [row0 + e] get
+ * sigma_ee / mec2_eV (cm2/eV), rows [row0 + N_E + e] get sigma_1 (cm2/mec2). */
+int nb_brems_table(const double* gam, int N, const double* eps, int N_E, double* K,
+                   int pitch, int row0, void* stream);
+
+/* Pion decay dsigma/dEgamma [cm2/GeV], Kafexhiu+14 analytic (radiative.py:1215-1482). */
+int nb_pp_analytic_table(int hiEmodel, int nuclear_enhancement, const double* Ep_GeV, int N,
+                         const double* Eg_GeV, int N_E, double* K, int pitch, int row0,
+                         void* stream);
+
+/* Same from the bicubic B-spline of the packaged lookup table
+ * (LookupTable radiative.py:1770-1797 = FITPACK bispev with clamping):
+ * tx[nx], ty[ny] knots, c[(nx-4)*(ny-4)] coefficients. */
+int nb_pp_lut_table(const double* tx, int nx, const double* ty, int ny, const double* c,
+                    const double* Ep_GeV, int N, const double* Eg_GeV, int N_E, double* K,
+                    int pitch, int row0, void* stream);
+
+/* lrs[r][j] = ln(K[r][j+1]/K[r][j]) * invdlx[j]   (j < N-1; NaN for sign changes,
+ * which selects trapz_loglog's log branch, utils.py:341-345). */
+int nb_table_finalize(const double* K, int R, int N, int pitch, const double* invdlx,
+                      double* lrs, void* stream);
+
+/* --- the hot contraction ---------------------------------------------------
+ * out[w][r] = coef[r] * trapz_loglog(n[w,:] * K[r,:], x)     utils.py:285-355
+ * for all W walkers and R rows in one launch.  dlx[j] = ln(x[j+1]/x[j]).
+ * coef may be NULL (=1).  `exact` != 0 evaluates every interval in the
+ * reference's own operation order (log10/pow per interval): then `xn` must
+ * hold n[w][j] itself (nraw of nb_pd_prep_ex), `xgrid` the grid x[N], and
+ * lrs/ds1/dlx are ignored (may be NULL).
+ * K_wstride: 0 for a shared table, else the per-walker table stride in
+ * doubles (self-Compton). */
+int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
+                long long K_wstride, const double* xn, const double* ds1, int wpitch, int W,
+                const double* dlx, const double* xgrid, const double* coef, double* out,
+                int exact, void* stream);
+
+/* --- synchrotron, fused (Synchrotron._spectrum radiative.py:282-342) -------
+ * out[w][e] = spectrum in 1/(s eV) for B[w] (Gauss) on grid gam[N] with
+ * operands xn/ds1 from nb_pd_prep; E_erg[N_E] photon energies in erg. */
+int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1, int wpitch,
+                   const double* invdlx, const double* dlx, const double* B, int W,
+                   const double* E_erg, int N_E, double* out, void* stream);
+
+/* --- combine + likelihood (BaseRadiative.flux radiative.py:102-111,
+ * lnprobmodel/lnprob core.py:64-121) ------------------------------------------
+ * model[w][e] = unit_fac[e] * sum_groups ( (sum_{terms in group} coef * src[w][off+e]) / div_g )
+ * A term with coef == NULL uses 1.  Terms are summed in the order given.  */
+typedef struct nb_term {
+  const double* src;  /* [W][ld] rows produced by nb_contract / nb_synchrotron */
+  int ld;             /* row length of src */
+  int off;            /* first row of this component */
+  int group_end;      /* != 0: close the group after this term, dividing by div */
+  double div;         /* 4 pi d^2, or 1 */
+} nb_term;
+
+/* flux_model[W][N_E] (may be NULL) receives the model in data units;
+ * lnp[W] (may be NULL) receives lnprob:
+ *   sum_{!ul} -(m-f)^2 / (2 s^2), s = err_hi if m > f else err_lo,
+ *   + n_viol * ln(1 - cl[n_viol]) when the table has upper limits,
+ *   + prior[w] (prior == NULL: 0); if prior[w] is +-inf the result is prior[w].
+ * ul is int32[N_E]. */
+int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
+                      const double* unit_fac, const double* data_flux, const double* err_lo,
+                      const double* err_hi, const int* ul, const double* cl,
+                      const double* prior, double* flux_model, double* lnp, void* stream);
+
+/* --- ensemble stretch move (emcee StretchMove, driven from core.py:127-160) --
+ * q[i][:] = c[i][:] - (c[i][:] - s[i][:]) * zz[i]  for Ns walkers of the active
+ * half; s/c are gathered rows (device), zz[Ns]. */
+int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
+                       const double* zz, int Ns, double* q, void* stream);
+
+/* accept/reject: for i < Ns with lnpdiff = (P-1) ln zz + new_lp - lp[s_idx] > ln u:
+ * coords/lp rows s_idx[i] are overwritten by q/new_lp; accepted[i] = 1. */
+int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const double* q,
+                      const double* new_lp, const double* zz, const double* lnu, int Ns,
+                      int* accepted, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAIMA_B200_H */

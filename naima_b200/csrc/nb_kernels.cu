@@ -1,0 +1,686 @@
+// nb_kernels.cu -- sm_100a kernels and C ABI of the naima likelihood hot path.
+//
+// Design: every radiative process is  spec[w,e] = sum_c coef *
+// trapz_loglog(n[w,:] * K_c[e,:], x).  The emissivity tables K are walker
+// independent, so they are built once per (grid, photon energies, seeds) by the
+// *_table kernels in the reference's operation order; per ensemble half-step
+// only nb_pd_prep (particle distribution on the grid) and nb_contract (the
+// log-log trapezoid contraction, table tile staged into shared memory by TMA
+// bulk copies, warp-shuffle reduction along the integration axis) run.
+// Synchrotron depends on the walker through B and is one fused kernel.
+// All arithmetic is IEEE fp64; no tensor cores (there is no dense contraction).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cuda/ptx>
+
+#include "../../include/naima_b200.h"
+#include "nb_math.cuh"
+
+namespace ptx = cuda::ptx;
+using namespace nb;
+
+#define NB_CHECK_LAUNCH()                         \
+  do {                                            \
+    cudaError_t e__ = cudaGetLastError();         \
+    if (e__ != cudaSuccess) return (int)e__;      \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// particle distribution kernels
+// ---------------------------------------------------------------------------
+__global__ void pdist_eval_kernel(int kind, const double* __restrict__ params, int W,
+                                  const double* __restrict__ e, int N, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int w = blockIdx.y;
+  if (i >= N || w >= W) return;
+  double p[PD_MAXPAR];
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
+  out[(size_t)w * N + i] = pd_eval(kind, p, e[i]);
+}
+
+__global__ void pd_prep_kernel(int kind, const double* __restrict__ params, int W,
+                               const double* __restrict__ x, int N, double e_mul1, double e_mul2,
+                               double n_scale, const double* __restrict__ invdlx,
+                               double* __restrict__ xn, double* __restrict__ ds1,
+                               double* __restrict__ nraw, int wpitch) {
+  __shared__ double s_n[257];
+  int j0 = blockIdx.x * 256;
+  int j = j0 + threadIdx.x;
+  int w = blockIdx.y;
+  double p[PD_MAXPAR];
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
+  double xj = 0.0, nj = 0.0;
+  if (j < N) {
+    xj = x[j];
+    nj = pd_eval(kind, p, (xj * e_mul1) * e_mul2) * n_scale;
+    s_n[threadIdx.x] = nj;
+  }
+  if (threadIdx.x == 0) {
+    int jl = j0 + 256;
+    if (jl < N) s_n[256] = pd_eval(kind, p, (x[jl] * e_mul1) * e_mul2) * n_scale;
+  }
+  __syncthreads();
+  if (j < N) {
+    size_t o = (size_t)w * wpitch + j;
+    xn[o] = xj * nj;
+    if (nraw) nraw[o] = nj;
+    if (j < N - 1) ds1[o] = log(s_n[threadIdx.x + 1] / nj) * invdlx[j] + 1.0;
+    else ds1[o] = 0.0;
+  }
+}
+
+// W = trapz_loglog(x*n, x*x_to_energy) in reference operation order; one CTA
+// (128 threads) per walker, fixed-order tree reduction.
+__global__ void particle_energy_kernel(int kind, const double* __restrict__ params,
+                                       const double* __restrict__ x, int N, double e_mul1,
+                                       double e_mul2, double n_scale, double x_to_energy,
+                                       double* __restrict__ out) {
+  __shared__ double s_part[128];
+  int w = blockIdx.x;
+  double p[PD_MAXPAR];
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N - 1; i += 128) {
+    double x1 = x[i], x2 = x[i + 1];
+    double n1 = pd_eval(kind, p, (x1 * e_mul1) * e_mul2) * n_scale;
+    double n2 = pd_eval(kind, p, (x2 * e_mul1) * e_mul2) * n_scale;
+    acc += interval_exact(x1 * x_to_energy, x2 * x_to_energy, x1 * n1, x2 * n2);
+  }
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 64; s > 0; s >>= 1) {
+    if (threadIdx.x < s) s_part[threadIdx.x] += s_part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[w] = s_part[0];
+}
+
+// ---------------------------------------------------------------------------
+// emissivity table builders (walker independent, reference operation order)
+// ---------------------------------------------------------------------------
+__global__ void ic_planck_table_kernel(const double* __restrict__ gam, int N,
+                                       const double* __restrict__ Eph, int N_E,
+                                       const double* __restrict__ seed_T,
+                                       const double* __restrict__ seed_theta, int S,
+                                       double* __restrict__ K, int pitch, int row0) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y;  // s*N_E + e
+  if (j >= pitch) return;
+  int s = r / N_E, e = r - s * N_E;
+  double v = 0.0;
+  if (j < N) {
+    double th = seed_theta[s];
+    if (th != th) v = ic_iso_planck(gam[j], seed_T[s], Eph[e]);
+    else v = ic_ani_planck(gam[j], seed_T[s], Eph[e], th);
+  }
+  K[(size_t)(row0 + r) * pitch + j] = v;
+}
+
+// phn_wstride == 0: shared seed density; else per-walker density / table
+__global__ void ic_seed_table_kernel(const double* __restrict__ gam, int N,
+                                     const double* __restrict__ Eph, int N_E,
+                                     const double* __restrict__ eps0,
+                                     const double* __restrict__ phn, int Ns, int phn_wstride,
+                                     double* __restrict__ K, int pitch, int row0,
+                                     long long K_wstride) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = blockIdx.y;
+  int w = blockIdx.z;
+  if (j >= pitch) return;
+  const double* ph = phn + (size_t)w * phn_wstride;
+  double v = 0.0;
+  if (j < N) {
+    double g = gam[j], ep = Eph[e];
+    if (Ns == 1) {
+      double e0 = eps0[0];
+      v = ic_mono_f(g, e0, ep);
+      v *= ph[0] / (e0 * e0);
+    } else {
+      double x1 = eps0[0];
+      double y1 = ic_mono_f(g, x1, ep) * ph[0] / x1;
+      double acc = 0.0;
+      for (int s = 1; s < Ns; ++s) {
+        double x2 = eps0[s];
+        double y2 = ic_mono_f(g, x2, ep) * ph[s] / x2;
+        acc += interval_exact(x1, x2, y1, y2);
+        x1 = x2;
+        y1 = y2;
+      }
+      v = acc;
+    }
+    v *= (3.0 / 4.0) * SIGT * 29979245800.0 / (g * g);
+  }
+  K[(size_t)w * K_wstride + (size_t)(row0 + e) * pitch + j] = v;
+}
+
+__global__ void brems_table_kernel(const double* __restrict__ gam, int N,
+                                   const double* __restrict__ eps, int N_E,
+                                   double* __restrict__ K, int pitch, int row0) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = blockIdx.y;
+  if (j >= pitch) return;
+  double vee = 0.0, vep = 0.0;
+  if (j < N) {
+    vee = brems_sigma_ee(gam[j], eps[e]) / MEC2_EV;
+    vep = brems_sigma_1(gam[j], eps[e]);
+  }
+  K[(size_t)(row0 + e) * pitch + j] = vee;
+  K[(size_t)(row0 + N_E + e) * pitch + j] = vep;
+}
+
+__global__ void pp_analytic_table_kernel(int model, int nuc, const double* __restrict__ Ep,
+                                         int N, const double* __restrict__ Eg, int N_E,
+                                         double* __restrict__ K, int pitch, int row0) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = blockIdx.y;
+  if (j >= pitch) return;
+  double v = 0.0;
+  if (j < N) v = pp_diffsigma(Ep[j], Eg[e], model, nuc);
+  K[(size_t)(row0 + e) * pitch + j] = v;
+}
+
+// FITPACK bispev (fpbisp) with clamping to the knot range
+__global__ void pp_lut_table_kernel(const double* __restrict__ tx, int nx,
+                                    const double* __restrict__ ty, int ny,
+                                    const double* __restrict__ c, const double* __restrict__ Ep,
+                                    int N, const double* __restrict__ Eg, int N_E,
+                                    double* __restrict__ K, int pitch, int row0) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int e = blockIdx.y;
+  if (j >= pitch) return;
+  double v = 0.0;
+  if (j < N) v = bspl_eval2d(tx, nx, ty, ny, c, log10(Ep[j]), log10(Eg[e]));
+  K[(size_t)(row0 + e) * pitch + j] = v;
+}
+
+__global__ void table_finalize_kernel(const double* __restrict__ K, int N, int pitch,
+                                      const double* __restrict__ invdlx,
+                                      double* __restrict__ lrs) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  size_t r = blockIdx.y;
+  if (j >= pitch) return;
+  double v = 0.0;
+  if (j < N - 1) v = log(K[r * pitch + j + 1] / K[r * pitch + j]) * invdlx[j];
+  lrs[r * pitch + j] = v;
+}
+
+// ---------------------------------------------------------------------------
+// the hot contraction
+// ---------------------------------------------------------------------------
+// CTA = 8 warps.  blockIdx.x selects a tile of RT table rows, staged in shared
+// memory with two TMA bulk copies (K and lrs); blockIdx.y selects a group of
+// walkers, one walker per warp at a time.  Lane l integrates the contiguous
+// interval range [l*m, (l+1)*m) (m odd => conflict-free 64-bit smem reads),
+// carrying x*y of the previous node in a register; the 32 partial sums are
+// combined with a shuffle tree.
+struct ContractArgs {
+  const double* K;
+  const double* lrs;
+  int R, N, pitch;
+  const double* xn;   // fast: x*n ; exact: n
+  const double* ds1;
+  int wpitch, W;
+  const double* dlx;
+  const double* xgrid;
+  const double* coef;
+  double* out;
+  int m;
+  int w_per_cta;
+};
+
+template <int RT, bool EXACT>
+__global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sK = reinterpret_cast<double*>(smem_raw);
+  double* sL = sK + (size_t)RT * a.pitch;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sL + (EXACT ? 0 : (size_t)RT * a.pitch));
+
+  const int row0 = blockIdx.x * RT;
+  const int nrows = min(RT, a.R - row0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::mbarrier_init(bar, 1);
+    ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = (uint32_t)nrows * (uint32_t)a.pitch * 8u;
+    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar,
+                                   EXACT ? bytes : 2u * bytes);
+    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK,
+                       a.K + (size_t)row0 * a.pitch, bytes, bar);
+    if (!EXACT)
+      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL,
+                         a.lrs + (size_t)row0 * a.pitch, bytes, bar);
+  }
+  while (!ptx::mbarrier_try_wait_parity(bar, 0)) {
+  }
+
+  const int nint = a.N - 1;
+  const int i0 = lane * a.m;
+  const int i1 = min(i0 + a.m, nint);
+  const int wbeg = blockIdx.y * a.w_per_cta;
+  const int wend = min(wbeg + a.w_per_cta, a.W);
+
+  for (int w = wbeg + warp; w < wend; w += 8) {
+    double acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    if (i0 < nint) {
+      const double* xnw = a.xn + (size_t)w * a.wpitch;
+      if (EXACT)
+        contract_lane_exact<RT>(xnw, a.xgrid, sK, a.pitch, i0, i1, acc);
+      else
+        contract_lane_fast<RT>(xnw, a.ds1 + (size_t)w * a.wpitch, a.dlx, sK, sL, a.pitch, i0, i1,
+                               acc);
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      double v = warp_sum(acc[r]);
+      if (lane == 0 && r < nrows) {
+        int row = row0 + r;
+        if (a.coef) v *= a.coef[row];
+        a.out[(size_t)w * a.R + row] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// synchrotron (fused): CTA = (walker, photon-energy slice)
+// ---------------------------------------------------------------------------
+struct SynArgs {
+  const double* gam;
+  int N;
+  const double* xn;
+  const double* ds1;
+  int wpitch;
+  const double* invdlx;
+  const double* dlx;
+  const double* B;
+  int W;
+  const double* E_erg;
+  int N_E;
+  double* out;
+  int m;        // odd chunk per lane
+  int e_per_cta;
+};
+
+__global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx
+  double* s_iec = reinterpret_cast<double*>(smem_raw);
+  double* s_cb = s_iec + a.N;
+  double* s_xn = s_cb + a.N;
+  double* s_ds = s_xn + a.N;
+  double* s_idl = s_ds + a.N;
+  double* s_dl = s_idl + a.N;
+
+  const int w = blockIdx.x;
+  const double Bw = a.B[w];
+  for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+    syn_node(a.gam[j], Bw, &s_iec[j], &s_cb[j]);
+    s_xn[j] = a.xn[(size_t)w * a.wpitch + j];
+    s_ds[j] = a.ds1[(size_t)w * a.wpitch + j];
+    if (j < a.N - 1) {
+      s_idl[j] = a.invdlx[j];
+      s_dl[j] = a.dlx[j];
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nint = a.N - 1;
+  const int i0 = lane * a.m;
+  const int i1 = min(i0 + a.m, nint);
+  const int ebeg = blockIdx.y * a.e_per_cta;
+  const int eend = min(ebeg + a.e_per_cta, a.N_E);
+
+  for (int e = ebeg + warp; e < eend; e += 8) {
+    double E = a.E_erg[e];
+    double acc = 0.0;
+    if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
+    acc = warp_sum(acc);
+    if (lane == 0) a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, E, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// combine + likelihood: one thread per walker (N_E is O(100))
+// ---------------------------------------------------------------------------
+__global__ void combine_lnprob_kernel(CombineArgs a) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.W) return;
+  combine_lnprob_walker(a, w);
+}
+
+// ---------------------------------------------------------------------------
+// stretch move helpers
+// ---------------------------------------------------------------------------
+__global__ void stretch_propose_kernel(const double* __restrict__ coords, int P,
+                                       const int* __restrict__ s_idx,
+                                       const int* __restrict__ c_idx,
+                                       const double* __restrict__ zz, int Ns,
+                                       double* __restrict__ q) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Ns * P) return;
+  int i = t / P, d = t - i * P;
+  double c = coords[(size_t)c_idx[i] * P + d];
+  double s = coords[(size_t)s_idx[i] * P + d];
+  q[t] = c - (c - s) * zz[i];
+}
+
+__global__ void stretch_accept_kernel(double* __restrict__ coords, double* __restrict__ lp, int P,
+                                      const int* __restrict__ s_idx, const double* __restrict__ q,
+                                      const double* __restrict__ new_lp,
+                                      const double* __restrict__ zz,
+                                      const double* __restrict__ lnu, int Ns,
+                                      int* __restrict__ accepted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ns) return;
+  int s = s_idx[i];
+  double lnpdiff = (P - 1) * log(zz[i]) + new_lp[i] - lp[s];
+  int acc = lnpdiff > lnu[i];
+  if (acc) {
+    for (int d = 0; d < P; ++d) coords[(size_t)s * P + d] = q[(size_t)i * P + d];
+    lp[s] = new_lp[i];
+  }
+  accepted[i] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int nb_version(void) { return 100; }
+
+const char* nb_strerror(int code) {
+  if (code == 0) return "ok";
+  if (code == NB_EINVAL) return "invalid argument";
+  if (code == NB_ETOOLARGE) return "grid too large for the shared-memory tiling";
+  if (code == NB_EALIGN) return "alignment requirement violated";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+int nb_contract_smem_bytes(int N, int rows_per_tile) {
+  int pitch = (N + 1) & ~1;
+  long long b = 2LL * rows_per_tile * pitch * 8 + 16;
+  return b > 227 * 1024 ? 0 : (int)b;
+}
+
+int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
+                  double* out, void* stream) {
+  if (!pd_params || !e_eV || !out || W < 0 || N < 0 || kind < 0 || kind > NB_PD_LOGPAR)
+    return NB_EINVAL;
+  if (W == 0 || N == 0) return 0;
+  dim3 grid((N + 255) / 256, W);
+  pdist_eval_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, e_eV, N, out);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+// nraw is an extension used by the exact contraction: n[w][j] itself
+int nb_pd_prep_ex(int kind, const double* pd_params, int W, const double* x, int N,
+                  double e_mul1, double e_mul2, double n_scale, const double* invdlx,
+                  double* xn, double* ds1, double* nraw, int wpitch, void* stream) {
+  if (!pd_params || !x || !invdlx || !xn || !ds1 || W < 0 || N < 2 || wpitch < N ||
+      kind < 0 || kind > NB_PD_LOGPAR)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  dim3 grid((N + 255) / 256, W);
+  pd_prep_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, x, N, e_mul1, e_mul2,
+                                                      n_scale, invdlx, xn, ds1, nraw, wpitch);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_pd_prep(int kind, const double* pd_params, int W, const double* x, int N, double e_mul1,
+               double e_mul2, double n_scale, const double* invdlx, double* xn, double* ds1,
+               int wpitch, void* stream) {
+  return nb_pd_prep_ex(kind, pd_params, W, x, N, e_mul1, e_mul2, n_scale, invdlx, xn, ds1,
+                       nullptr, wpitch, stream);
+}
+
+int nb_particle_energy(int kind, const double* pd_params, int W, const double* x, int N,
+                       double e_mul1, double e_mul2, double n_scale, double x_to_energy,
+                       double* out, void* stream) {
+  if (!pd_params || !x || !out || W < 0 || N < 2 || kind < 0 || kind > NB_PD_LOGPAR)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  particle_energy_kernel<<<W, 128, 0, as_stream(stream)>>>(kind, pd_params, x, N, e_mul1,
+                                                           e_mul2, n_scale, x_to_energy, out);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ic_planck_table(const double* gam, int N, const double* Eph, int N_E,
+                       const double* seed_T, const double* seed_theta, int S, double* K,
+                       int pitch, int row0, void* stream) {
+  if (!gam || !Eph || !seed_T || !seed_theta || !K || N < 2 || N_E < 1 || S < 1 ||
+      pitch < N || row0 < 0)
+    return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, S * N_E);
+  ic_planck_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(gam, N, Eph, N_E, seed_T,
+                                                              seed_theta, S, K, pitch, row0);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ic_seed_table(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
+                     const double* phn, int Ns, double* K, int pitch, int row0, void* stream) {
+  if (!gam || !Eph || !eps0 || !phn || !K || N < 2 || N_E < 1 || Ns < 1 || pitch < N ||
+      row0 < 0)
+    return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, N_E, 1);
+  ic_seed_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(gam, N, Eph, N_E, eps0, phn, Ns, 0,
+                                                            K, pitch, row0, 0);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ic_seed_table_batched(const double* gam, int N, const double* Eph, int N_E,
+                             const double* eps0, const double* phn, int Ns, int W, double* K,
+                             int pitch, void* stream) {
+  if (!gam || !Eph || !eps0 || !phn || !K || N < 2 || N_E < 1 || Ns < 1 || pitch < N || W < 0)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  if (W > 65535) return NB_ETOOLARGE;
+  dim3 grid((pitch + 127) / 128, N_E, W);
+  ic_seed_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(
+      gam, N, Eph, N_E, eps0, phn, Ns, Ns, K, pitch, 0, (long long)N_E * pitch);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_brems_table(const double* gam, int N, const double* eps, int N_E, double* K, int pitch,
+                   int row0, void* stream) {
+  if (!gam || !eps || !K || N < 2 || N_E < 1 || pitch < N || row0 < 0) return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, N_E);
+  brems_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(gam, N, eps, N_E, K, pitch, row0);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_pp_analytic_table(int hiEmodel, int nuclear_enhancement, const double* Ep_GeV, int N,
+                         const double* Eg_GeV, int N_E, double* K, int pitch, int row0,
+                         void* stream) {
+  if (!Ep_GeV || !Eg_GeV || !K || N < 2 || N_E < 1 || pitch < N || row0 < 0 || hiEmodel < 0 ||
+      hiEmodel > NB_PP_QGSJET)
+    return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, N_E);
+  pp_analytic_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(
+      hiEmodel, nuclear_enhancement, Ep_GeV, N, Eg_GeV, N_E, K, pitch, row0);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_pp_lut_table(const double* tx, int nx, const double* ty, int ny, const double* c,
+                    const double* Ep_GeV, int N, const double* Eg_GeV, int N_E, double* K,
+                    int pitch, int row0, void* stream) {
+  if (!tx || !ty || !c || !Ep_GeV || !Eg_GeV || !K || nx < 8 || ny < 8 || N < 2 || N_E < 1 ||
+      pitch < N || row0 < 0)
+    return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, N_E);
+  pp_lut_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(tx, nx, ty, ny, c, Ep_GeV, N, Eg_GeV,
+                                                           N_E, K, pitch, row0);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_table_finalize(const double* K, int R, int N, int pitch, const double* invdlx,
+                      double* lrs, void* stream) {
+  if (!K || !invdlx || !lrs || R < 1 || N < 2 || pitch < N) return NB_EINVAL;
+  dim3 grid((pitch + 127) / 128, R);
+  table_finalize_kernel<<<grid, 128, 0, as_stream(stream)>>>(K, N, pitch, invdlx, lrs);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"
+
+template <int RT, bool EXACT>
+static int launch_contract(const ContractArgs& a, int smem, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(contract_kernel<RT, EXACT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
+  contract_kernel<RT, EXACT><<<grid, 256, smem, st>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" {
+
+int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
+                long long K_wstride, const double* xn, const double* ds1, int wpitch, int W,
+                const double* dlx, const double* xgrid, const double* coef, double* out,
+                int exact, void* stream) {
+  if (!K || !xn || !out || R < 1 || N < 2 || pitch < N || wpitch < N || W < 0)
+    return NB_EINVAL;
+  if (!exact && (!lrs || !ds1 || !dlx)) return NB_EINVAL;
+  if (exact && !xgrid) return NB_EINVAL;
+  if (K_wstride != 0) return NB_EINVAL;  // per-walker tables go through nb_contract_batched
+  if ((pitch & 1) || ((uintptr_t)K & 15) || (lrs && ((uintptr_t)lrs & 15))) return NB_EALIGN;
+  if (W == 0) return 0;
+  ContractArgs a;
+  a.K = K; a.lrs = lrs; a.R = R; a.N = N; a.pitch = pitch;
+  a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch; a.W = W;
+  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out;
+  a.m = odd_chunk(N - 1);
+  // rows per tile: largest of 8/4/2 whose K+lrs tile stays <= ~96 KB (2 CTAs/SM)
+  int narr = exact ? 1 : 2;
+  long long row_bytes = (long long)narr * pitch * 8;
+  int RT = 8;
+  while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
+  if (RT * row_bytes + 16 > 227 * 1024) return NB_ETOOLARGE;
+  int smem = (int)(RT * row_bytes + 16);
+  // walkers per CTA: enough CTAs to fill 148 SMs twice when W allows it
+  int row_tiles = (R + RT - 1) / RT;
+  int wpc = 8;
+  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 4 * 148) wpc <<= 1;
+  a.w_per_cta = wpc;
+  cudaStream_t st = as_stream(stream);
+  if (exact) {
+    if (RT == 8) return launch_contract<8, true>(a, smem, st);
+    if (RT == 4) return launch_contract<4, true>(a, smem, st);
+    return launch_contract<2, true>(a, smem, st);
+  }
+  if (RT == 8) return launch_contract<8, false>(a, smem, st);
+  if (RT == 4) return launch_contract<4, false>(a, smem, st);
+  return launch_contract<2, false>(a, smem, st);
+}
+
+int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1, int wpitch,
+                   const double* invdlx, const double* dlx, const double* B, int W,
+                   const double* E_erg, int N_E, double* out, void* stream) {
+  if (!gam || !xn || !ds1 || !invdlx || !dlx || !B || !E_erg || !out || N < 2 || wpitch < N ||
+      W < 0 || N_E < 1)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  SynArgs a;
+  a.gam = gam; a.N = N; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
+  a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
+  a.m = odd_chunk(N - 1);
+  long long smem = 6LL * N * 8;
+  if (smem > 227 * 1024) return NB_ETOOLARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(synchrotron_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  // photon energies per CTA: 8 (one per warp) unless that launches far more CTAs than
+  // 4 waves of 148 SMs
+  int epc = 8;
+  while (epc < N_E && (long long)W * ((N_E + epc - 1) / epc) > 4 * 148) epc <<= 1;
+  a.e_per_cta = epc;
+  dim3 grid(W, (N_E + epc - 1) / epc);
+  synchrotron_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
+                      const double* unit_fac, const double* data_flux, const double* err_lo,
+                      const double* err_hi, const int* ul, const double* cl, const double* prior,
+                      double* flux_model, double* lnp, void* stream) {
+  if (!terms_host || n_terms < 1 || n_terms > NB_MAX_TERMS || W < 0 || N_E < 1 || !unit_fac)
+    return NB_EINVAL;
+  if (lnp && (!data_flux || !err_lo || !err_hi || !ul || !cl)) return NB_EINVAL;
+  if (!lnp && !flux_model) return NB_EINVAL;
+  if (W == 0) return 0;
+  CombineArgs a;
+  for (int t = 0; t < n_terms; ++t) a.terms[t] = terms_host[t];
+  if (!a.terms[n_terms - 1].group_end) return NB_EINVAL;
+  a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
+  a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
+  a.prior = prior; a.flux_model = flux_model; a.lnp = lnp;
+  combine_lnprob_kernel<<<(W + 63) / 64, 64, 0, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
+                       const double* zz, int Ns, double* q, void* stream) {
+  if (!coords || !s_idx || !c_idx || !zz || !q || P < 1 || Ns < 0) return NB_EINVAL;
+  if (Ns == 0) return 0;
+  int n = Ns * P;
+  stretch_propose_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords, P, s_idx, c_idx,
+                                                                         zz, Ns, q);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const double* q,
+                      const double* new_lp, const double* zz, const double* lnu, int Ns,
+                      int* accepted, void* stream) {
+  if (!coords || !lp || !s_idx || !q || !new_lp || !zz || !lnu || !accepted || P < 1 || Ns < 0)
+    return NB_EINVAL;
+  if (Ns == 0) return 0;
+  stretch_accept_kernel<<<(Ns + 127) / 128, 128, 0, as_stream(stream)>>>(
+      coords, lp, P, s_idx, q, new_lp, zz, lnu, Ns, accepted);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

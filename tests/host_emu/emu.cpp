@@ -1,0 +1,168 @@
+// emu.cpp -- TEST-ONLY host build of naima_b200/csrc/nb_math.cuh.
+//
+// The per-cell arithmetic of the CUDA kernels lives in `__host__ __device__`
+// functions; this file compiles them with g++ and emulates the kernels' thread
+// decomposition (lane ranges, shuffle-tree order) in plain loops so that the
+// formulas can be checked against the oracle on a box without a GPU
+// (tests/test_host_emu.py).  It is never loaded by the product: naima_b200 has
+// no CPU execution path.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../naima_b200/csrc/nb_math.cuh"
+
+using namespace nb;
+
+static double tree32(const double* v) {
+  // __shfl_down_sync tree of warp_sum(): offsets 16, 8, 4, 2, 1; lane 0 result
+  double t[32];
+  memcpy(t, v, sizeof(t));
+  for (int o = 16; o > 0; o >>= 1)
+    for (int l = 0; l < 32; ++l) t[l] = t[l] + ((l + o < 32) ? t[l + o] : t[l]);
+  return t[0];
+}
+
+extern "C" {
+
+void emu_pd_eval(int kind, const double* p, const double* e, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = pd_eval(kind, p, e[i]);
+}
+
+void emu_interval_exact(const double* x, const double* y, int n, double* out) {
+  for (int i = 0; i < n - 1; ++i) out[i] = interval_exact(x[i], x[i + 1], y[i], y[i + 1]);
+}
+
+void emu_gtilde(const double* x, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = gtilde(x[i]);
+}
+
+void emu_ic_planck(const double* gam, int N, const double* Eph, int N_E, double T,
+                   double theta, double* out) {
+  for (int e = 0; e < N_E; ++e)
+    for (int j = 0; j < N; ++j)
+      out[e * N + j] = (theta != theta) ? ic_iso_planck(gam[j], T, Eph[e])
+                                        : ic_ani_planck(gam[j], T, Eph[e], theta);
+}
+
+void emu_ic_seed(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
+                 const double* phn, int Ns, double* out) {
+  for (int e = 0; e < N_E; ++e)
+    for (int j = 0; j < N; ++j) {
+      double g = gam[j], ep = Eph[e], v;
+      if (Ns == 1) {
+        v = ic_mono_f(g, eps0[0], ep);
+        v *= phn[0] / (eps0[0] * eps0[0]);
+      } else {
+        double x1 = eps0[0];
+        double y1 = ic_mono_f(g, x1, ep) * phn[0] / x1;
+        double acc = 0.0;
+        for (int s = 1; s < Ns; ++s) {
+          double x2 = eps0[s];
+          double y2 = ic_mono_f(g, x2, ep) * phn[s] / x2;
+          acc += interval_exact(x1, x2, y1, y2);
+          x1 = x2;
+          y1 = y2;
+        }
+        v = acc;
+      }
+      v *= (3.0 / 4.0) * SIGT * 29979245800.0 / (g * g);
+      out[e * N + j] = v;
+    }
+}
+
+void emu_brems(const double* gam, int N, const double* eps, int N_E, double* see, double* s1) {
+  for (int e = 0; e < N_E; ++e)
+    for (int j = 0; j < N; ++j) {
+      see[e * N + j] = brems_sigma_ee(gam[j], eps[e]) / MEC2_EV;
+      s1[e * N + j] = brems_sigma_1(gam[j], eps[e]);
+    }
+}
+
+void emu_pp_diffsigma(const double* Ep, int N, double Eg, int model, int nuc, double* out) {
+  for (int j = 0; j < N; ++j) out[j] = pp_diffsigma(Ep[j], Eg, model, nuc);
+}
+
+void emu_bspl(const double* tx, int nx, const double* ty, int ny, const double* c,
+              const double* x, int n, double y, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = bspl_eval2d(tx, nx, ty, ny, c, x[i], y);
+}
+
+// pd_prep_kernel
+void emu_pd_prep(int kind, const double* p, const double* x, int N, double m1, double m2,
+                 double ns, const double* invdlx, double* xn, double* ds1, double* nraw) {
+  for (int j = 0; j < N; ++j) {
+    nraw[j] = pd_eval(kind, p, (x[j] * m1) * m2) * ns;
+    xn[j] = x[j] * nraw[j];
+  }
+  for (int j = 0; j < N - 1; ++j) ds1[j] = log(nraw[j + 1] / nraw[j]) * invdlx[j] + 1.0;
+  ds1[N - 1] = 0.0;
+}
+
+// table_finalize_kernel
+void emu_finalize(const double* K, int R, int N, int pitch, const double* invdlx, double* lrs) {
+  for (int r = 0; r < R; ++r)
+    for (int j = 0; j < pitch; ++j)
+      lrs[r * pitch + j] =
+          (j < N - 1) ? log(K[r * pitch + j + 1] / K[r * pitch + j]) * invdlx[j] : 0.0;
+}
+
+// contract_kernel<RT=1>, one walker; lane decomposition + shuffle tree
+void emu_contract(const double* K, const double* lrs, int R, int N, int pitch, const double* xn,
+                  const double* ds1, const double* dlx, const double* xgrid, int exact,
+                  double* out) {
+  int nint = N - 1, m = odd_chunk(nint);
+  for (int r = 0; r < R; ++r) {
+    double part[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
+      double acc = 0.0;
+      if (i0 < nint) {
+        if (exact)
+          contract_lane_exact<1>(xn, xgrid, K + (size_t)r * pitch, pitch, i0, i1, &acc);
+        else
+          contract_lane_fast<1>(xn, ds1, dlx, K + (size_t)r * pitch, lrs + (size_t)r * pitch,
+                                pitch, i0, i1, &acc);
+      }
+      part[lane] = acc;
+    }
+    out[r] = tree32(part);
+  }
+}
+
+// synchrotron_kernel for one walker
+void emu_synchrotron(const double* gam, int N, const double* xn, const double* ds1,
+                     const double* invdlx, const double* dlx, double B, const double* E_erg,
+                     int N_E, double* out) {
+  double* iec = (double*)malloc(sizeof(double) * N);
+  double* cb = (double*)malloc(sizeof(double) * N);
+  for (int j = 0; j < N; ++j) syn_node(gam[j], B, &iec[j], &cb[j]);
+  int nint = N - 1, m = odd_chunk(nint);
+  for (int e = 0; e < N_E; ++e) {
+    double part[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
+      part[lane] = (i0 < nint) ? syn_lane(E_erg[e], cbrt(E_erg[e]), iec, cb, xn, ds1, invdlx,
+                                          dlx, i0, i1)
+                               : 0.0;
+    }
+    out[e] = syn_finish(B, E_erg[e], tree32(part));
+  }
+  free(iec);
+  free(cb);
+}
+
+// combine_lnprob_kernel
+void emu_combine_lnprob(const nb_term* terms, int n_terms, int W, int N_E,
+                        const double* unit_fac, const double* data_flux, const double* err_lo,
+                        const double* err_hi, const int* ul, const double* cl,
+                        const double* prior, double* flux_model, double* lnp) {
+  CombineArgs a;
+  for (int t = 0; t < n_terms; ++t) a.terms[t] = terms[t];
+  a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
+  a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
+  a.prior = prior; a.flux_model = flux_model; a.lnp = lnp;
+  for (int w = 0; w < W; ++w) combine_lnprob_walker(a, w);
+}
+
+}  // extern "C"
