@@ -1,0 +1,226 @@
+"""Pin the CPU oracle (oracle/naima_oracle.py) to the reference.
+
+Three kinds of pins:
+  1. the known-answer numbers of the reference's own tests/test_models.py, replayed
+     at that file's tolerance (assert_allclose default rtol 1e-7);
+  2. the lnprob known answer of docs/_static/RXJ1713_IC_results.ecsv:10-11;
+  3. tests/golden/ref_exec.npz -- outputs of the reference's unit-free functions
+     exec'd from its source text (tests/golden/make_golden.py).
+CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import oracle.naima_oracle as o
+
+TeV = 1e12
+ENERGY = np.logspace(0, 15, 1000)  # eV, tests/test_models.py:40
+EEMIN, EEMAX = 100e9, 1e15  # tests/test_models.py:37
+KPC = o.kpc_cm
+LUT_FILE = os.path.join(os.path.dirname(__file__), "..", "naima_b200", "data",
+                        "pp_kafexhiu14_pythia8_nucenh_bspline.npz")
+
+
+def dists():
+    """tests/test_models.py:52-65 ``particle_dists`` (amplitude 1/mec2)."""
+    amp = 1.0 / o.mec2_eV
+    ECPL = o.PDist("ExponentialCutoffPowerLaw", amp, 20 * TeV, 2.0, 10 * TeV, 1.0)
+    PL = o.PDist("PowerLaw", amp, 20 * TeV, 2.0)
+    BPL = o.PDist("BrokenPowerLaw", amp, 20 * TeV, 1 * TeV, 1.5, 2.5)
+    return ECPL, PL, BPL
+
+
+def lum(spec):
+    """trapz_loglog(spec * E, E) -> erg/s (spec in 1/(s eV), E in eV)."""
+    return o.trapz_loglog(spec * ENERGY, ENERGY) * o.eV_erg
+
+
+def test_synchrotron_goldens(goldens):
+    # tests/test_models.py:67-103: default B = 3.24 uG (radiative.py:273), 0-distance flux
+    ref = goldens["synchrotron_lum"]["value"]
+    Weref = goldens["We"]["value"]
+    for pd, lr, wr in zip(dists(), ref, Weref):
+        spec = o.synchrotron_spectrum(pd, ENERGY, 3.24e-6, EEMIN, EEMAX)
+        assert_allclose(lum(spec), lr, rtol=1e-7)
+        assert_allclose(o.compute_We(pd, EEMIN, EEMAX, 100), wr, rtol=1e-7)
+    spec = o.synchrotron_spectrum(dists()[0], ENERGY, 1.0, EEMIN, EEMAX)
+    assert_allclose(lum(spec), goldens["synchrotron_lum_B1G"]["value"], rtol=1e-7)
+
+
+def test_ic_goldens(goldens):
+    # tests/test_models.py:197-226
+    for pd, lr in zip(dists(), goldens["ic_lum"]["value"]):
+        spec = o.ic_spectrum(pd, ENERGY, ["CMB"], EEMIN, EEMAX)
+        assert_allclose(lum(spec), lr, rtol=1e-7)
+    # :221-226 uses the default electron grid (Eemin = 1 GeV, Eemax = 1e9 mec2)
+    spec = o.ic_spectrum(dists()[0], ENERGY, ["CMB", "FIR", "NIR"])
+    assert_allclose(lum(spec), goldens["ic_lum_3seeds"]["value"], rtol=1e-7)
+
+
+def test_aniso_ic_goldens(goldens):
+    # tests/test_models.py:229-252: seed ["Star", 20000 K, 0.1 erg/cm3, angle]
+    PL = dists()[1]
+    for ang, lr in zip(goldens["ic_aniso_lum"]["angles_deg"], goldens["ic_aniso_lum"]["value"]):
+        seed = ("thermal", 20000.0, 0.1, np.deg2rad(ang))
+        spec = o.ic_spectrum(PL, ENERGY, [seed], EEMIN, EEMAX)
+        assert_allclose(lum(spec), lr, rtol=1e-7)
+
+
+def test_ic_mono_vs_planck():
+    # tests/test_models.py:254-287: 30 K grey body (1 eV/cm3) vs monochromatic seed
+    # at the peak of E^2 n(E) vs tabulated blackbody seed, all within rtol 1e-2
+    PL = o.PDist("PowerLaw", 1.0, 1 * TeV, 3.0)
+    T, w = 30.0, 1.0 * o.eV_erg
+    Ephbb = np.logspace(-3.5, -1.5, 100)  # eV
+    kT = 8.617333262145179e-05 * T
+    hc = 1.2398419843320028e-04  # eV cm
+    bb = 8 * np.pi * Ephbb**2 / hc**3 / np.expm1(Ephbb / kT)  # 1/(eV cm3)
+    Ebbmax = Ephbb[np.argmax(Ephbb**2 * bb)]
+    bb = bb * (w / (o.ar_cgs * T**4))
+    eopts = dict(Eemin_eV=10e9, Eemax_eV=10000e9, nEed=1000)
+    Eph = np.logspace(-1, 1, 3) * 1e9
+    khang = o.ic_spectrum(PL, Eph, [("thermal", T, w)], **eopts)
+    mono = o.ic_spectrum(PL, Eph, [("mono", Ebbmax, w)], **eopts)
+    arr = o.ic_spectrum(PL, Eph, [("array", Ephbb, bb)], **eopts)
+    assert_allclose(mono, khang, rtol=1e-2)
+    assert_allclose(arr, khang, rtol=1e-2)
+
+
+def test_bremsstrahlung_golden(goldens):
+    # tests/test_models.py:178-194: ECPL, Eemin = mec2, energy2 = logspace(8,14,100) eV
+    ECPL = dists()[0]
+    E2 = np.logspace(8, 14, 100)
+    spec = o.bremsstrahlung_spectrum(ECPL, E2, Eemin_eV=o.mec2_eV)
+    assert_allclose(o.trapz_loglog(spec * E2, E2) * o.eV_erg,
+                    goldens["bremsstrahlung_lum"]["value"], rtol=1e-7)
+
+
+def _lut():
+    f = np.load(LUT_FILE)
+    from scipy.interpolate import bisplev
+
+    tck = (f["tx"], f["ty"], f["c"], 3, 3)
+
+    def fn(Ep, Eg):
+        return np.atleast_1d(bisplev(np.log10(Ep), np.log10(Eg), tck)).flatten()
+
+    return fn
+
+
+def pp_dists():
+    """tests/test_models.py:396-397: amplitude reset to 1/TeV."""
+    amp = 1.0 / TeV
+    ECPL = o.PDist("ExponentialCutoffPowerLaw", amp, 20 * TeV, 2.0, 10 * TeV, 1.0)
+    PL = o.PDist("PowerLaw", amp, 20 * TeV, 2.0)
+    BPL = o.PDist("BrokenPowerLaw", amp, 20 * TeV, 1 * TeV, 1.5, 2.5)
+    return ECPL, PL, BPL
+
+
+def test_piondecay_goldens(goldens):
+    # tests/test_models.py:391-427; goldens are printed to 9 digits there
+    E = np.logspace(-3, 3, 60) * TeV
+
+    def lum60(spec):
+        return o.trapz_loglog(spec * E, E) * o.eV_erg
+
+    for pd, l_lut, l_nolut, wp in zip(
+        pp_dists(), goldens["pp_lum_LUT"]["value"], goldens["pp_lum_noLUT"]["value"],
+        goldens["Wp"]["value"],
+    ):
+        spec = o.piondecay_spectrum(pd, E, Epmax_GeV=1e6, lut=_lut())
+        assert_allclose(lum60(spec), l_lut, rtol=1e-7)
+        spec = o.piondecay_spectrum(pd, E, Epmax_GeV=1e6, useLUT=False)
+        assert_allclose(lum60(spec), l_nolut, rtol=1e-7)
+        assert_allclose(o.compute_Wp(pd, o.mpc2_GeV + o.T_TH + 1e-4, 1e6, 100), wp, rtol=1e-7)
+    # tests/test_models.py:431-450
+    E = np.logspace(9, 13, 20)
+    spec = o.piondecay_spectrum(pp_dists()[0], E, Epmax_GeV=1e6, useLUT=False,
+                                nuclear_enhancement=False)
+    assert_allclose(o.trapz_loglog(spec * E, E) * o.eV_erg, goldens["pp_lum_no_nuc"]["value"],
+                    rtol=1e-7)
+
+
+def test_lut_probe(lut_probe):
+    """The shipped B-spline coefficients reproduce the reference LookupTable
+    (RectBivariateSpline of the packaged table) incl. the clamped region."""
+    fn = _lut()
+    for k, eg in enumerate(lut_probe["Eg"]):
+        assert_allclose(fn(lut_probe["Ep"], eg), lut_probe["ds"][k], rtol=1e-12, atol=1e-45)
+
+
+def test_lnprob_known_answer(goldens, rxj_data):
+    """docs/_static/RXJ1713_IC_results.ecsv:10-11 with docs/_static/RXJ1713_IC.py."""
+    g = goldens["lnprob_RXJ1713_IC"]
+    pars = g["ML_pars"]
+    E = rxj_data["hess_energy_TeV"] * TeV
+    data = dict(
+        flux=rxj_data["hess_flux"], flux_error_lo=rxj_data["hess_flux_error"],
+        flux_error_hi=rxj_data["hess_flux_error"], ul=rxj_data["hess_ul"].astype(bool),
+        cl=np.full(E.size, float(rxj_data["hess_cl"])),
+    )
+
+    def model(p, d):
+        pd = o.PDist("ExponentialCutoffPowerLaw", p[0], 10 * TeV, p[1], 10 ** p[2] * TeV, 1.0)
+        seeds = ["CMB", ("thermal", 26.5, 0.415 * o.eV_erg)]
+        spec = o.ic_spectrum(pd, E, seeds)
+        return o.flux_from_spectrum(spec, 1.0 * KPC) * 1e12  # 1/(s cm2 TeV)
+
+    lp, _ = o.lnprob(pars, data, model, None)
+    assert_allclose(lp, g["MaxLogLikelihood"], rtol=1e-12)
+
+
+# --- vectors exec'd from the reference source --------------------------------
+def test_ref_exec_trapz(ref_exec):
+    r = ref_exec
+    assert_allclose(o.trapz_loglog(r["tl_y"], r["tl_x"]), r["tl_sum"], rtol=1e-15)
+    np.testing.assert_array_equal(o.trapz_loglog(r["tl_y"], r["tl_x"], intervals=True), r["tl_int"])
+    assert_allclose(o.trapz_loglog(r["tl_y"].T.copy(), r["tl_x"], axis=0), r["tl_axis0"], rtol=1e-15)
+
+
+def test_ref_exec_pdists(ref_exec):
+    r = ref_exec
+    e = r["pd_e"]
+    eq = np.testing.assert_array_equal
+    eq(o.pl_eval(e, 1.3e33, 1e13, 2.41), r["pd_pl"])
+    eq(o.ecpl_eval(e, 1.3e33, 1e13, 2.41, 4.8e13, 1.0), r["pd_ecpl"])
+    eq(o.ecpl_eval(e, 1.3e33, 1e13, 1.7, 2e12, 2.0), r["pd_ecpl_b2"])
+    eq(o.bpl_eval(e, 2e30, 2e13, 1e12, 1.5, 2.5), r["pd_bpl"])
+    eq(o.ecbpl_eval(e, 3.7e36, 1e12, 2.65e11, 1.5, 3.233, 1.863e15, 2.0), r["pd_ecbpl"])
+    eq(o.logparabola_eval(e, 1e30, 2e13, 1.7, 0.2), r["pd_lp"])
+
+
+def test_ref_exec_ic_kernels(ref_exec):
+    r = ref_exec
+    eq = np.testing.assert_array_equal
+    eq(o.G12(r["g_x"], [0.857, 0.153, 1.840, 0.254]), r["g12_a1"])
+    eq(o.G34(r["g_x"], [0.606, 0.443, 1.481, 0.540, 0.319]), r["g34_a3"])
+    with np.errstate(all="ignore"):
+        eq(o.iso_ic_on_planck(r["ic_gam"], 2.72548, r["ic_Eph"]), r["ic_iso_cmb"])
+        eq(o.iso_ic_on_planck(r["ic_gam"], 3000.0, r["ic_Eph"]), r["ic_iso_nir"])
+        eq(o.ani_ic_on_planck(r["ic_gam"], 20000.0, r["ic_Eph"], np.deg2rad(60.0)), r["ic_ani_60"])
+        eq(o.ani_ic_on_planck(r["ic_gam"], 30.0, r["ic_Eph"], np.deg2rad(135.0)), r["ic_ani_135"])
+    eq(o.heaviside(np.array([-2.0, -0.0, 0.0, 3.0])), r["heaviside"])
+
+
+@pytest.mark.parametrize("model", ["Pythia8", "Geant4", "SIBYLL", "QGSJET"])
+@pytest.mark.parametrize("nuc", [True, False])
+def test_ref_exec_piondecay(ref_exec, model, nuc):
+    r = ref_exec
+    pp = o.PionDecayNumerics(model, nuc)
+    ds = np.array([pp.diffsigma(r["pp_Ep"], eg) for eg in r["pp_Eg"]])
+    np.testing.assert_array_equal(ds, r["pp_ds_%s_%d" % (model, nuc)])
+
+
+def test_ref_exec_piondecay_parts(ref_exec):
+    r = ref_exec
+    pp = o.PionDecayNumerics("Pythia8", True)
+    Tp = r["pp_Ep"] - o.mpc2_GeV
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(pp.sigma_inel(Tp), r["pp_sigma_inel"])
+        np.testing.assert_array_equal(pp.sigma_pi(Tp), r["pp_sigma_pi"])
+        np.testing.assert_array_equal(pp.Amax(Tp), r["pp_Amax"])
+        np.testing.assert_array_equal(pp.calc_Egmax(Tp), r["pp_Egmax"])
+        np.testing.assert_array_equal(pp.nuclear_factor(Tp), r["pp_nuc"])
