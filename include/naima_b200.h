@@ -63,6 +63,13 @@ const char* nb_strerror(int code);
 /* shared-memory bytes nb_contract needs for a grid of N nodes (0 if too large) */
 int nb_contract_smem_bytes(int N, int rows_per_tile);
 
+/* --- log-log trapezoid as a stand-alone op (utils.py:285-355) ------------------
+ * out[r] = trapz_loglog(y[r][0..N), x) in the reference's operation order;
+ * x is shared (x_ld == 0) or per row (x[r][0..N), row stride x_ld).  `intervals`
+ * (may be NULL) receives the N-1 interval values per row; `out` may be NULL. */
+int nb_trapz_loglog(const double* y, int R, int N, int ld, const double* x, int x_ld,
+                    double* out, double* intervals, void* stream);
+
 /* --- particle distribution ------------------------------------------------
  * out[w][i] = PD.eval(e[i], params[w])                     models.py:87-335 */
 int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
@@ -160,14 +167,15 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
 
 /* --- combine + likelihood (BaseRadiative.flux radiative.py:102-111,
  * lnprobmodel/lnprob core.py:64-121) ------------------------------------------
- * model[w][e] = unit_fac[e] * sum_groups ( (sum_{terms in group} coef * src[w][off+e]) / div_g )
- * A term with coef == NULL uses 1.  Terms are summed in the order given.  */
+ * model[w][e] = unit_fac[e] * sum_groups ( (sum_{terms in group} wscale[w] * src[w][off+e]) / div_g )
+ * Terms and groups are summed in the order given.  */
 typedef struct nb_term {
-  const double* src;  /* [W][ld] rows produced by nb_contract / nb_synchrotron */
-  int ld;             /* row length of src */
-  int off;            /* first row of this component */
-  int group_end;      /* != 0: close the group after this term, dividing by div */
-  double div;         /* 4 pi d^2, or 1 */
+  const double* src;    /* [W][ld] rows produced by nb_contract / nb_synchrotron */
+  const double* wscale; /* NULL, or a per-walker factor [W] (fitted nh, n0, ...) */
+  int ld;               /* row length of src */
+  int off;              /* first row of this component */
+  int group_end;        /* != 0: close the group after this term, dividing by div */
+  double div;           /* 4 pi d^2, or 1 */
 } nb_term;
 
 /* flux_model[W][N_E] (may be NULL) receives the model in data units;
@@ -181,6 +189,55 @@ int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
                       const double* err_hi, const int* ul, const double* cl,
                       const double* prior, double* flux_model, double* lnp, void* stream);
 
+/* --- parameter map + priors ------------------------------------------------
+ * What the user's model(pars, data) / lnprior(pars) callbacks do on the host in
+ * the reference (examples/RXJ1713_SynIC.py:19-62, core.py:34-58), declaratively:
+ *   out[dst_off_k + w * dst_stride_k] = scale_k * f_k(pars[w][src_k])
+ *                                       (src_k < 0: the constant scale_k)
+ *   f: NB_FN_ID x, NB_FN_POW10 10**x, NB_FN_EXP e**x
+ * so one launch fills every [W][NB_PD_MAXPAR] particle-distribution block
+ * (stride NB_PD_MAXPAR) and every per-walker scalar column (stride 1) of `out`.
+ *   prior[w] = sum over entries, in order, of
+ *     NB_PRIOR_UNIFORM      a <= v <= b ? 0 : -inf                   core.py:34-39
+ *     NB_PRIOR_NORMAL       -0.5*(2 pi b) - (v-a)^2/(2 b)  (literal) core.py:42-44
+ *     NB_PRIOR_LOGUNIFORM   v > 0 && v >= a && v <= b ? 1/v : -inf   core.py:47-58
+ * map_host / priors_host are HOST arrays (copied into the launch).  prior_out may
+ * be NULL. */
+#define NB_FN_ID 0
+#define NB_FN_POW10 1
+#define NB_FN_EXP 2
+#define NB_PRIOR_UNIFORM 0
+#define NB_PRIOR_NORMAL 1
+#define NB_PRIOR_LOGUNIFORM 2
+#define NB_MAX_MAP 32
+#define NB_MAX_PRIORS 16
+typedef struct nb_parmap {
+  int src;
+  int fn;
+  double scale;
+  long long dst_off;
+  int dst_stride;
+} nb_parmap;
+typedef struct nb_prior {
+  int par;
+  int kind;
+  double a, b;
+} nb_prior;
+int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
+                 double* out, const nb_prior* priors_host, int n_priors, double* prior_out,
+                 void* stream);
+
+/* --- IC on a tabulated seed, fused (synchrotron self-Compton) ----------------
+ * radiative.py:609-655 + 684 in one launch, reference operation order:
+ *   out[w][out_off + e] = Eph[e] * trapz_loglog(nraw[w,:] * K_w[e,:], gam)
+ *   K_w[e,j] = 3/4 sigma_T c / gam_j^2 *
+ *              trapz_loglog_s(f_AA81(gam_j, eps0_s, Eph_e) * phn[w][s] / eps0_s, eps0)
+ * phn_wstride: Ns for a per-walker seed density phn[W][Ns], 0 for a shared one. */
+int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch,
+                        const double* Eph, int N_E, const double* eps0, const double* phn,
+                        int Ns, int phn_wstride, int W, double* out, int out_ld, int out_off,
+                        void* stream);
+
 /* --- ensemble stretch move (emcee StretchMove, driven from core.py:127-160) --
  * q[i][:] = c[i][:] - (c[i][:] - s[i][:]) * zz[i]  for Ns walkers of the active
  * half; s/c are gathered rows (device), zz[Ns]. */
@@ -192,6 +249,28 @@ int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int*
 int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const double* q,
                       const double* new_lp, const double* zz, const double* lnu, int Ns,
                       int* accepted, void* stream);
+
+/* Device-resident variant for CUDA-graph replay: the draws of n_steps ensemble
+ * steps are resident as s_idx/c_idx [n_steps][2][Ns] (int32), zz/lnu
+ * [n_steps][2][Ns]; the current step t is read from *step (device int32).
+ * nb_stretch_move proposes the active half `split` of step t; nb_stretch_update
+ * accepts/rejects it (also the per-walker blob rows blobs[W][nb] when nb > 0),
+ * counts acceptances in n_accepted[W], and for split == 1 appends the ensemble
+ * to chain[t][W][P] / chain_lp[t][W] / chain_blobs[t][W][nb] (each may be NULL)
+ * and increments *step. */
+int nb_stretch_move(const double* coords, int P, int Ns, int split, const int* step,
+                    const int* s_idx, const int* c_idx, const double* zz, double* q,
+                    void* stream);
+int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, int P, int Ns,
+                      int split, int* step, const int* s_idx, const double* zz,
+                      const double* lnu, const double* q, const double* new_lp,
+                      const double* new_blobs, int* n_accepted, double* chain,
+                      double* chain_lp, double* chain_blobs, void* stream);
+
+/* --- measurement aid: fp64 FMA throughput probe -------------------------------
+ * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;
+ * the caller times it with CUDA events to obtain the fp64 roofline denominator. */
+int nb_fp64_peak_probe(double* out, int blocks, int threads, int iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of the C ABI declared in include/naima_b200.h.
+
+There is no CPU fallback: importing the compute layer without the built
+library, or calling it without a CUDA device, raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnaima_b200.so")
+
+c_int, c_dbl, c_ll, vp = ctypes.c_int, ctypes.c_double, ctypes.c_longlong, ctypes.c_void_p
+
+NB_PD_MAXPAR = 8
+NB_MAX_TERMS = 16
+NB_MAX_PAR = 16
+PD_KIND = {"PowerLaw": 0, "ExponentialCutoffPowerLaw": 1, "BrokenPowerLaw": 2,
+           "ExponentialCutoffBrokenPowerLaw": 3, "LogParabola": 4}
+PP_MODEL = {"Geant4": 0, "Pythia8": 1, "SIBYLL": 2, "QGSJET": 3}
+
+
+class nb_term(ctypes.Structure):
+    _fields_ = [("src", vp), ("wscale", vp), ("ld", c_int), ("off", c_int),
+                ("group_end", c_int), ("div", c_dbl)]
+
+
+class nb_parmap(ctypes.Structure):
+    # out[w][k] = f(pars[w][src]) * scale (or the constant `scale` when src < 0)
+    _fields_ = [("src", c_int), ("fn", c_int), ("scale", c_dbl), ("dst_off", c_ll),
+                ("dst_stride", c_int)]
+
+
+class nb_prior(ctypes.Structure):
+    _fields_ = [("par", c_int), ("kind", c_int), ("a", c_dbl), ("b", c_dbl)]
+
+
+# name -> (argtypes); every function returns int
+PROTOTYPES = {
+    "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
+    "nb_pdist_eval": [c_int, vp, c_int, vp, c_int, vp, vp],
+    "nb_pd_prep": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, vp, vp, vp, c_int, vp],
+    "nb_pd_prep_ex": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, vp, vp, vp, vp, c_int, vp],
+    "nb_particle_energy": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, vp, vp],
+    "nb_ic_planck_table": [vp, c_int, vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp],
+    "nb_ic_seed_table": [vp, c_int, vp, c_int, vp, vp, c_int, vp, c_int, c_int, vp],
+    "nb_ic_seed_spectrum": [vp, c_int, vp, c_int, vp, c_int, vp, vp, c_int, c_int, c_int, vp,
+                            c_int, c_int, vp],
+    "nb_brems_table": [vp, c_int, vp, c_int, vp, c_int, c_int, vp],
+    "nb_pp_analytic_table": [c_int, c_int, vp, c_int, vp, c_int, vp, c_int, c_int, vp],
+    "nb_pp_lut_table": [vp, c_int, vp, c_int, vp, vp, c_int, vp, c_int, vp, c_int, c_int, vp],
+    "nb_table_finalize": [vp, c_int, c_int, c_int, vp, vp, vp],
+    "nb_contract": [vp, vp, c_int, c_int, c_int, c_ll, vp, vp, c_int, c_int, vp, vp, vp, vp,
+                    c_int, vp],
+    "nb_synchrotron": [vp, c_int, vp, vp, c_int, vp, vp, vp, c_int, vp, c_int, vp, vp],
+    "nb_combine_lnprob": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp, vp,
+                          vp, vp, vp, vp],
+    "nb_param_map": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
+                     ctypes.POINTER(nb_prior), c_int, vp, vp],
+    "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
+    "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
+    "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],
+    "nb_stretch_update": [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp,
+                          vp, vp, vp, vp, vp, vp, vp],
+    "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "naima_b200: %s is missing -- build it with `python -m naima_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the binding disagree
+            fn.argtypes = args
+            fn.restype = c_int
+        L.nb_version.restype = c_int
+        L.nb_strerror.restype = ctypes.c_char_p
+        L.nb_strerror.argtypes = [c_int]
+        _lib = L
+    return _lib
+
+
+class NaimaB200Error(RuntimeError):
+    pass
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = lib().nb_strerror(code).decode()
+        if code == -1:
+            raise ValueError("naima_b200 %s: %s" % (what, msg))
+        raise NaimaB200Error("naima_b200 %s: %s (code %d)" % (what, msg, code))

@@ -401,6 +401,201 @@ __global__ void stretch_accept_kernel(double* __restrict__ coords, double* __res
   accepted[i] = acc;
 }
 
+
+// ---------------------------------------------------------------------------
+// parameter map + priors: one thread per walker
+// ---------------------------------------------------------------------------
+struct ParamMapArgs {
+  nb_parmap map[NB_MAX_MAP];
+  nb_prior pri[NB_MAX_PRIORS];
+  int n_out, n_pri, W, P;
+  const double* pars;
+  double* out;
+  double* prior_out;
+};
+
+__global__ void param_map_kernel(ParamMapArgs a) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.W) return;
+  const double* p = a.pars + (size_t)w * a.P;
+  for (int k = 0; k < a.n_out; ++k) {
+    const nb_parmap m = a.map[k];
+    double v = m.scale;
+    if (m.src >= 0) {
+      double x = p[m.src];
+      if (m.fn == NB_FN_POW10) x = pow(10.0, x);
+      else if (m.fn == NB_FN_EXP) x = exp(x);
+      v = x * m.scale;
+    }
+    a.out[m.dst_off + (long long)w * m.dst_stride] = v;
+  }
+  if (a.prior_out) {
+    double lp = 0.0;
+    for (int k = 0; k < a.n_pri; ++k) lp += prior_eval(a.pri[k].kind, p[a.pri[k].par], a.pri[k].a, a.pri[k].b);
+    a.prior_out[w] = lp;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// IC on a tabulated seed, fused: CTA = (photon energy e, walker w)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ic_seed_spectrum_kernel(
+    const double* __restrict__ gam, int N, const double* __restrict__ nraw, int wpitch,
+    const double* __restrict__ Eph, const double* __restrict__ eps0,
+    const double* __restrict__ phn, int Ns, int phn_wstride, double* __restrict__ out,
+    int out_ld, int out_off) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_e0 = reinterpret_cast<double*>(smem_raw);  // [Ns]
+  double* s_ph = s_e0 + Ns;                            // [Ns] phn/eps0
+  double* s_y = s_ph + Ns;                             // [N]  n_e * K
+  __shared__ double s_red[8];
+  const int e = blockIdx.x, w = blockIdx.y;
+  const double* ph = phn + (size_t)w * phn_wstride;
+  for (int s = threadIdx.x; s < Ns; s += blockDim.x) {
+    double x = eps0[s];
+    s_e0[s] = x;
+    s_ph[s] = ph[s] / x;
+  }
+  __syncthreads();
+  const double ep = Eph[e];
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    double g = gam[j];
+    double v;
+    if (Ns == 1) {
+      v = ic_mono_f(g, s_e0[0], ep) * (s_ph[0] / s_e0[0]);
+    } else {
+      double x1 = s_e0[0];
+      double y1 = ic_mono_f(g, x1, ep) * s_ph[0];
+      double acc = 0.0;
+      for (int s = 1; s < Ns; ++s) {
+        double x2 = s_e0[s];
+        double y2 = ic_mono_f(g, x2, ep) * s_ph[s];
+        acc += interval_exact(x1, x2, y1, y2);
+        x1 = x2;
+        y1 = y2;
+      }
+      v = acc;
+    }
+    v *= (3.0 / 4.0) * SIGT * 29979245800.0 / (g * g);
+    s_y[j] = nraw[(size_t)w * wpitch + j] * v;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < N - 1; j += blockDim.x)
+    acc += interval_exact(gam[j], gam[j + 1], s_y[j], s_y[j + 1]);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += s_red[k];
+    out[(size_t)w * out_ld + out_off + e] = ep * t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// device-resident stretch move (draws resident for n_steps, step index on device)
+// ---------------------------------------------------------------------------
+__global__ void stretch_move_kernel(const double* __restrict__ coords, int P, int Ns, int split,
+                                    const int* __restrict__ step, const int* __restrict__ s_idx,
+                                    const int* __restrict__ c_idx, const double* __restrict__ zz,
+                                    double* __restrict__ q) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Ns * P) return;
+  size_t base = ((size_t)(*step) * 2 + split) * Ns;
+  int i = t / P, d = t - i * P;
+  double c = coords[(size_t)c_idx[base + i] * P + d];
+  double s = coords[(size_t)s_idx[base + i] * P + d];
+  q[t] = c - (c - s) * zz[base + i];
+}
+
+__global__ void stretch_update_kernel(double* __restrict__ coords, double* __restrict__ lp,
+                                      double* __restrict__ blobs, int nb, int P, int Ns, int split,
+                                      const int* __restrict__ step, const int* __restrict__ s_idx,
+                                      const double* __restrict__ zz, const double* __restrict__ lnu,
+                                      const double* __restrict__ q,
+                                      const double* __restrict__ new_lp,
+                                      const double* __restrict__ new_blobs,
+                                      int* __restrict__ n_accepted) {
+  // one warp per proposal: lanes copy the blob row
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (i >= Ns) return;
+  size_t base = ((size_t)(*step) * 2 + split) * Ns;
+  int s = s_idx[base + i];
+  double nl = new_lp[i];
+  double lnpdiff = (P - 1) * log(zz[base + i]) + nl - lp[s];
+  bool acc = lnpdiff > lnu[base + i];
+  if (acc) {
+    for (int d = lane; d < P; d += 32) coords[(size_t)s * P + d] = q[(size_t)i * P + d];
+    for (int d = lane; d < nb; d += 32) blobs[(size_t)s * nb + d] = new_blobs[(size_t)i * nb + d];
+    if (lane == 0) {
+      lp[s] = nl;
+      n_accepted[s] += 1;
+    }
+  }
+}
+
+__global__ void stretch_store_kernel(const double* __restrict__ coords,
+                                     const double* __restrict__ lp,
+                                     const double* __restrict__ blobs, int nb, int W, int P,
+                                     int* __restrict__ step, double* __restrict__ chain,
+                                     double* __restrict__ chain_lp,
+                                     double* __restrict__ chain_blobs) {
+  // single CTA so the step increment is ordered after every read of *step
+  const size_t t = (size_t)(*step);
+  if (chain)
+    for (int k = threadIdx.x; k < W * P; k += blockDim.x) chain[t * W * P + k] = coords[k];
+  if (chain_lp)
+    for (int k = threadIdx.x; k < W; k += blockDim.x) chain_lp[t * W + k] = lp[k];
+  if (chain_blobs)
+    for (int k = threadIdx.x; k < W * nb; k += blockDim.x)
+      chain_blobs[t * W * nb + k] = blobs[k];
+  __syncthreads();
+  if (threadIdx.x == 0) *step = (int)t + 1;
+}
+
+// ---------------------------------------------------------------------------
+// fp64 FMA throughput probe (roofline denominator, measured by the caller)
+// ---------------------------------------------------------------------------
+__global__ void fp64_probe_kernel(double* out, int iters) {
+  double a[16];
+  const double m = 1.0000001, c = 1e-9;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = threadIdx.x * 1e-3 + k;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fma(a[k], m, c);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) t += a[k];
+  if (t == -1.0) out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+
+// ---------------------------------------------------------------------------
+// a1 as a stand-alone op: trapz_loglog of R rows y[r][0..N) over x (shared x[N]
+// or per-row x[r][0..N) when x_ld > 0), reference operation order; warp per row
+// ---------------------------------------------------------------------------
+__global__ void trapz_loglog_kernel(const double* __restrict__ y, int R, int N, int ld,
+                                    const double* __restrict__ x, int x_ld,
+                                    double* __restrict__ out, double* __restrict__ iv) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const double* yr = y + (size_t)r * ld;
+  const double* xr = x + (size_t)r * x_ld;
+  double acc = 0.0;
+  for (int i = lane; i < N - 1; i += 32) {
+    double v = interval_exact(xr[i], xr[i + 1], yr[i], yr[i + 1]);
+    if (iv) iv[(size_t)r * (N - 1) + i] = v;
+    acc += v;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && out) out[r] = acc;
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -679,6 +874,118 @@ int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const
   if (Ns == 0) return 0;
   stretch_accept_kernel<<<(Ns + 127) / 128, 128, 0, as_stream(stream)>>>(
       coords, lp, P, s_idx, q, new_lp, zz, lnu, Ns, accepted);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+
+int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, int n_out,
+                 double* out, const nb_prior* priors_host, int n_priors, double* prior_out,
+                 void* stream) {
+  if (!pars || W < 0 || P < 1 || n_out < 0 || n_out > NB_MAX_MAP || n_priors < 0 ||
+      n_priors > NB_MAX_PRIORS || (n_out > 0 && (!map_host || !out)) ||
+      (n_priors > 0 && !priors_host))
+    return NB_EINVAL;
+  ParamMapArgs a;
+  for (int k = 0; k < n_out; ++k) {
+    a.map[k] = map_host[k];
+    if (a.map[k].src >= P || a.map[k].fn < 0 || a.map[k].fn > NB_FN_EXP ||
+        a.map[k].dst_off < 0 || a.map[k].dst_stride < 0)
+      return NB_EINVAL;
+  }
+  for (int k = 0; k < n_priors; ++k) {
+    a.pri[k] = priors_host[k];
+    if (a.pri[k].par < 0 || a.pri[k].par >= P || a.pri[k].kind < 0 ||
+        a.pri[k].kind > NB_PRIOR_LOGUNIFORM)
+      return NB_EINVAL;
+  }
+  if (W == 0) return 0;
+  a.n_out = n_out; a.n_pri = n_priors; a.W = W; a.P = P;
+  a.pars = pars; a.out = out; a.prior_out = prior_out;
+  param_map_kernel<<<(W + 63) / 64, 64, 0, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch,
+                        const double* Eph, int N_E, const double* eps0, const double* phn,
+                        int Ns, int phn_wstride, int W, double* out, int out_ld, int out_off,
+                        void* stream) {
+  if (!gam || !nraw || !Eph || !eps0 || !phn || !out || N < 2 || wpitch < N || N_E < 1 ||
+      Ns < 1 || W < 0 || out_off < 0 || out_ld < out_off + N_E ||
+      (phn_wstride != 0 && phn_wstride < Ns))
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  if (W > 65535) return NB_ETOOLARGE;
+  long long smem = (2LL * Ns + N) * 8;
+  if (smem > 227 * 1024) return NB_ETOOLARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ic_seed_spectrum_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(N_E, W);
+  ic_seed_spectrum_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(
+      gam, N, nraw, wpitch, Eph, eps0, phn, Ns, phn_wstride, out, out_ld, out_off);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_stretch_move(const double* coords, int P, int Ns, int split, const int* step,
+                    const int* s_idx, const int* c_idx, const double* zz, double* q,
+                    void* stream) {
+  if (!coords || !step || !s_idx || !c_idx || !zz || !q || P < 1 || Ns < 0 || split < 0 ||
+      split > 1)
+    return NB_EINVAL;
+  if (Ns == 0) return 0;
+  int n = Ns * P;
+  stretch_move_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords, P, Ns, split, step,
+                                                                      s_idx, c_idx, zz, q);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, int P, int Ns,
+                      int split, int* step, const int* s_idx, const double* zz,
+                      const double* lnu, const double* q, const double* new_lp,
+                      const double* new_blobs, int* n_accepted, double* chain,
+                      double* chain_lp, double* chain_blobs, void* stream) {
+  if (!coords || !lp || !step || !s_idx || !zz || !lnu || !q || !new_lp || !n_accepted ||
+      W < 1 || P < 1 || Ns < 0 || split < 0 || split > 1 || nb < 0 ||
+      (nb > 0 && (!blobs || !new_blobs)))
+    return NB_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  if (Ns > 0) {
+    stretch_update_kernel<<<(Ns * 32 + 255) / 256, 256, 0, st>>>(
+        coords, lp, blobs, nb, P, Ns, split, step, s_idx, zz, lnu, q, new_lp, new_blobs,
+        n_accepted);
+    NB_CHECK_LAUNCH();
+  }
+  if (split == 1) {
+    stretch_store_kernel<<<1, 1024, 0, st>>>(coords, lp, blobs, nb, W, P, step, chain, chain_lp,
+                                             nb > 0 ? chain_blobs : nullptr);
+    NB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int nb_fp64_peak_probe(double* out, int blocks, int threads, int iters, void* stream) {
+  if (!out || blocks < 1 || threads < 1 || threads > 1024 || iters < 1) return NB_EINVAL;
+  fp64_probe_kernel<<<blocks, threads, 0, as_stream(stream)>>>(out, iters);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+
+int nb_trapz_loglog(const double* y, int R, int N, int ld, const double* x, int x_ld,
+                    double* out, double* intervals, void* stream) {
+  if (!y || !x || (!out && !intervals) || R < 0 || N < 1 || ld < N || (x_ld != 0 && x_ld < N))
+    return NB_EINVAL;
+  if (R == 0) return 0;
+  trapz_loglog_kernel<<<(R * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(y, R, N, ld, x, x_ld,
+                                                                           out, intervals);
   NB_CHECK_LAUNCH();
   return 0;
 }

@@ -484,6 +484,15 @@ NB_HD double lnprob_term(double model, double flux, double err_lo, double err_hi
   return -(d * d) / (2.0 * (s * s));
 }
 
+// priors (core.py:34-58), literal formulas
+NB_HD double prior_eval(int kind, double v, double a, double b) {
+  if (kind == NB_PRIOR_UNIFORM) return (a <= v && v <= b) ? 0.0 : -INFINITY;
+  if (kind == NB_PRIOR_NORMAL) return -0.5 * (2 * NB_PI * b) - ((v - a) * (v - a)) / (2.0 * b);
+  // log-uniform: returns 1/value (sic)
+  if (v > 0 && v >= a) return (v <= b) ? 1 / v : -INFINITY;
+  return -INFINITY;
+}
+
 // ---------------------------------------------------------------------------
 // per-lane bodies of the hot kernels (lane = contiguous interval range [i0,i1))
 // ---------------------------------------------------------------------------
@@ -601,6 +610,7 @@ NB_HD double combine_model(const CombineArgs& a, int w, int e) {
   for (int t = 0; t < a.n_terms; ++t) {
     const nb_term& T = a.terms[t];
     double v = T.src[(size_t)w * T.ld + T.off + e];
+    if (T.wscale) v *= T.wscale[w];
     g = first_in_group ? v : g + v;
     first_in_group = false;
     if (T.group_end) {

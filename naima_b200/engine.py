@@ -1,0 +1,420 @@
+# -*- coding: utf-8 -*-
+"""Device engine: grids, emissivity tables and kernel launches.
+
+Thin, stateless-looking Python over the C ABI (include/naima_b200.h).  PyTorch
+tensors are used only as device-memory containers and for the stream handle.
+Everything is float64 in the fixed units of the C ABI (eV, G, K, cm, rad).
+
+Layout in HBM:
+  grid        x[pitch], dlx[pitch], invdlx[pitch]           per particle grid
+  table       K[R][pitch], lrs[R][pitch], coef[R]           per (process, grid, photon energies)
+  operands    xn[W][pitch], ds1[W][pitch] (, nraw[W][pitch]) per launch
+  results     spec[W][R]                                      per launch
+Row r = component * N_E + photon-energy index.
+"""
+import ctypes
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PD_KIND, PP_MODEL, NB_PD_MAXPAR, check, lib, nb_term
+
+# CODATA 2018 / astropy>=6.1 values in cgs, composed as the reference composes
+# them (radiative.py:36-40)
+c_cgs = 29979245800.0
+m_e_g = 9.1093837015e-28
+sigma_sb_cgs = 5.6703744191844314e-05
+eV_erg = 1.602176634e-12
+erg_eV = 1e-7 / 1.602176634e-19
+mec2_erg = m_e_g * c_cgs**2
+mec2_eV = mec2_erg / eV_erg
+ar_cgs = 4 * sigma_sb_cgs / c_cgs
+mpc2_GeV = 0.9382720881604903
+T_TH = 0.27966184
+T_CMB = 2.72548
+
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+# reference operation order (log10/pow per interval) instead of the hoisted
+# contraction; settable at run time (tests exercise both)
+EXACT = False
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("naima_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_dev(a, dtype=torch.float64):
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a).to(device=device(), dtype=dtype)
+
+
+def empty(*shape, dtype=torch.float64):
+    return torch.empty(*shape, dtype=dtype, device=device())
+
+
+def zeros(*shape, dtype=torch.float64):
+    return torch.zeros(*shape, dtype=dtype, device=device())
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def even(n):
+    return (n + 1) & ~1
+
+
+# ------------------------------------------------------------------------------
+# particle grids
+# ------------------------------------------------------------------------------
+class Grid:
+    """Log-spaced particle grid (radiative.py:147-154, 1002-1009) on the device."""
+
+    def __init__(self, x, species):
+        self.x = np.asarray(x, dtype=float)
+        self.key = (species, self.x.size, hash(self.x.tobytes()))
+        self.N = self.x.size
+        self.pitch = even(self.N)
+        self.species = species
+        pad = np.zeros(self.pitch)
+        pad[: self.N] = self.x
+        dlx = np.zeros(self.pitch)
+        dlx[: self.N - 1] = np.log(self.x[1:] / self.x[:-1])
+        inv = np.zeros(self.pitch)
+        inv[: self.N - 1] = 1.0 / dlx[: self.N - 1]
+        self._host = (pad, dlx, inv)
+        self._dev = None
+        if species == "electron":  # e = (gam * mec2[erg]) * (erg -> eV); n per unit gam
+            self.e_mul1, self.e_mul2, self.n_scale = mec2_erg, erg_eV, mec2_eV
+            self.x_to_erg = mec2_erg
+        else:  # protons: x = Ep in GeV; J per GeV
+            self.e_mul1, self.e_mul2, self.n_scale = 1e9, 1.0, 1e9
+            self.x_to_erg = 1e9 * eV_erg
+
+
+    def _device(self):
+        if self._dev is None:  # uploaded on first use so that tracing needs no GPU
+            self._dev = tuple(to_dev(a) for a in self._host)
+        return self._dev
+
+    x_d = property(lambda self: self._device()[0])
+    dlx_d = property(lambda self: self._device()[1])
+    invdlx_d = property(lambda self: self._device()[2])
+
+
+_GRIDS = OrderedDict()
+
+
+def _cache_get(cache, key, make, maxsize):
+    if key in cache:
+        cache.move_to_end(key)
+        return cache[key]
+    val = make()
+    cache[key] = val
+    while len(cache) > maxsize:
+        cache.popitem(last=False)
+    return val
+
+
+def electron_grid(Eemin_eV, Eemax_eV, nEed):
+    """radiative.py:147-154 (identical arithmetic to the oracle's electron_grid)."""
+    def make():
+        l0 = np.log10(Eemin_eV * eV_erg / mec2_erg)
+        l1 = np.log10(Eemax_eV * eV_erg / mec2_erg)
+        return Grid(np.logspace(l0, l1, max(10, int(nEed * (l1 - l0)))), "electron")
+    return _cache_get(_GRIDS, ("e", float(Eemin_eV), float(Eemax_eV), float(nEed)), make, 64)
+
+
+def proton_grid(Epmin_GeV, Epmax_GeV, nEpd):
+    """radiative.py:1002-1009."""
+    def make():
+        n = max(10, int(nEpd * (np.log10(Epmax_GeV / Epmin_GeV))))
+        return Grid(np.logspace(np.log10(Epmin_GeV), np.log10(Epmax_GeV), n), "proton")
+    return _cache_get(_GRIDS, ("p", float(Epmin_GeV), float(Epmax_GeV), float(nEpd)), make, 64)
+
+
+# ------------------------------------------------------------------------------
+# particle distributions
+# ------------------------------------------------------------------------------
+def pd_params_array(kind, params):
+    """Broadcast reference-order eval() parameters to a [W][8] host array."""
+    cols = [np.atleast_1d(np.asarray(p, dtype=float)) for p in params]
+    W = max(c.size for c in cols)
+    out = np.zeros((W, NB_PD_MAXPAR))
+    for k, c in enumerate(cols):
+        if c.size not in (1, W):
+            raise ValueError("particle distribution parameters have inconsistent batch sizes")
+        out[:, k] = c
+    return out
+
+
+def pdist_eval(kind, params_d, W, e_eV):
+    """out[w][i] = PD.eval(e[i]) on the device (models.py eval staticmethods)."""
+    e_d = to_dev(np.atleast_1d(e_eV))
+    out = empty(W, e_d.numel())
+    check(lib().nb_pdist_eval(PD_KIND[kind], ptr(params_d), W, ptr(e_d), e_d.numel(), ptr(out),
+                              stream()), "nb_pdist_eval")
+    return out
+
+
+class Prepared:
+    __slots__ = ("xn", "ds1", "nraw", "W", "grid")
+
+
+def pd_prep(grid, kind, params_d, W, need_raw=None, out=None):
+    """Integration operands of W walkers on `grid` (nb_pd_prep)."""
+    need_raw = EXACT if need_raw is None else need_raw
+    pr = out if out is not None else Prepared()
+    if out is None:
+        pr.xn, pr.ds1 = empty(W, grid.pitch), empty(W, grid.pitch)
+        pr.nraw = empty(W, grid.pitch) if need_raw else None
+        pr.W, pr.grid = W, grid
+    check(lib().nb_pd_prep_ex(PD_KIND[kind], ptr(params_d), W, ptr(grid.x_d), grid.N,
+                              grid.e_mul1, grid.e_mul2, grid.n_scale, ptr(grid.invdlx_d),
+                              ptr(pr.xn), ptr(pr.ds1), ptr(pr.nraw), grid.pitch, stream()),
+          "nb_pd_prep")
+    return pr
+
+
+def particle_energy(grid, kind, params_d, W, out=None):
+    """W[w] = trapz_loglog(x n, x * x_to_erg) in erg (We / Wp)."""
+    out = empty(W) if out is None else out
+    check(lib().nb_particle_energy(PD_KIND[kind], ptr(params_d), W, ptr(grid.x_d), grid.N,
+                                   grid.e_mul1, grid.e_mul2, grid.n_scale, grid.x_to_erg,
+                                   ptr(out), stream()), "nb_particle_energy")
+    return out
+
+
+# ------------------------------------------------------------------------------
+# emissivity tables
+# ------------------------------------------------------------------------------
+class Table:
+    """Walker-independent emissivity rows K[R][pitch] (+ log-slopes, + coef[R])."""
+
+    def __init__(self, grid, R, n_comp, N_E):
+        self.grid, self.R, self.n_comp, self.N_E = grid, R, n_comp, N_E
+        self.K = zeros(R, grid.pitch)
+        self.lrs = zeros(R, grid.pitch)
+        self.coef = None
+
+    def finalize(self, coef):
+        g = self.grid
+        check(lib().nb_table_finalize(ptr(self.K), self.R, g.N, g.pitch, ptr(g.invdlx_d),
+                                      ptr(self.lrs), stream()), "nb_table_finalize")
+        self.coef = to_dev(coef)
+        return self
+
+
+_TABLES = OrderedDict()
+_TABLES_MAX = 32
+
+
+def _ekey(E):
+    E = np.ascontiguousarray(E, dtype=float)
+    return (E.size, hash(E.tobytes()))
+
+
+def ic_table(grid, E_eV, seeds):
+    """IC rows for thermal (iso / aniso) and monochromatic / tabulated seeds.
+
+    seeds: tuple of ("thermal", T_K, u_erg_cm3[, theta_rad]) | ("mono", E_eV, u_erg_cm3)
+           | ("array", E_eV[Ns] tuple, dn/dE[1/(eV cm3)] tuple)
+    coef[r] = uf * Eph / E_eV  (radiative.py:684-687)."""
+    E_eV = np.ascontiguousarray(E_eV, dtype=float)
+
+    def make():
+        N_E, S = E_eV.size, len(seeds)
+        Eph = E_eV * eV_erg / mec2_erg
+        Eph_d = to_dev(Eph)
+        tb = Table(grid, S * N_E, S, N_E)
+        coef = np.empty(S * N_E)
+        for s, seed in enumerate(seeds):
+            if seed[0] == "thermal":
+                T, uu = seed[1], seed[2]
+                if uu == 0:
+                    uu = ar_cgs * T**4
+                uf = uu / (ar_cgs * T**4)
+                th = seed[3] if len(seed) > 3 else np.nan
+                check(lib().nb_ic_planck_table(
+                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(to_dev([T])), ptr(to_dev([th])),
+                    1, ptr(tb.K), grid.pitch, s * N_E, stream()), "nb_ic_planck_table")
+            else:
+                uf = 1.0
+                if seed[0] == "mono":
+                    eps0 = np.atleast_1d(seed[1]) / mec2_eV
+                    phn = np.atleast_1d(seed[2]) / mec2_erg
+                else:
+                    eps0 = np.asarray(seed[1], dtype=float) / mec2_eV
+                    phn = np.asarray(seed[2], dtype=float) * mec2_eV
+                check(lib().nb_ic_seed_table(
+                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(to_dev(eps0)), ptr(to_dev(phn)),
+                    eps0.size, ptr(tb.K), grid.pitch, s * N_E, stream()), "nb_ic_seed_table")
+            coef[s * N_E:(s + 1) * N_E] = uf * Eph / E_eV
+        return tb.finalize(coef)
+
+    return _cache_get(_TABLES, ("ic", grid.key, _ekey(E_eV), seeds), make, _TABLES_MAX)
+
+
+def brems_table(grid, E_eV):
+    """Rows [0,N_E): sigma_ee/mec2_eV, rows [N_E,2N_E): sigma_1; coef folds c and
+    the per-eV conversion (radiative.py:940-971)."""
+    E_eV = np.ascontiguousarray(E_eV, dtype=float)
+
+    def make():
+        N_E = E_eV.size
+        eps_d = to_dev(E_eV * eV_erg / mec2_erg)
+        tb = Table(grid, 2 * N_E, 2, N_E)
+        check(lib().nb_brems_table(ptr(grid.x_d), grid.N, ptr(eps_d), N_E, ptr(tb.K),
+                                   grid.pitch, 0, stream()), "nb_brems_table")
+        coef = np.concatenate([np.full(N_E, c_cgs), np.full(N_E, c_cgs / mec2_eV)])
+        return tb.finalize(coef)
+
+    return _cache_get(_TABLES, ("br", grid.key, _ekey(E_eV)), make, _TABLES_MAX)
+
+
+_LUT = {}
+
+
+def _pp_lut():
+    if "pythia8" not in _LUT:
+        f = np.load(os.path.join(DATA_DIR, "pp_kafexhiu14_pythia8_nucenh_bspline.npz"))
+        _LUT["pythia8"] = (to_dev(f["tx"]), to_dev(f["ty"]), to_dev(f["c"]))
+    return _LUT["pythia8"]
+
+
+def pp_table(grid, E_eV, useLUT, hiEmodel, nuclear_enhancement):
+    """dsigma/dEgamma rows; coef = c * 1e-9 (1/(s GeV) -> 1/(s eV)), radiative.py:1523-1536."""
+    E_eV = np.ascontiguousarray(E_eV, dtype=float)
+
+    def make():
+        N_E = E_eV.size
+        Eg_d = to_dev(E_eV * 1e-9)
+        tb = Table(grid, N_E, 1, N_E)
+        if useLUT:
+            tx, ty, c = _pp_lut()
+            check(lib().nb_pp_lut_table(ptr(tx), tx.numel(), ptr(ty), ty.numel(), ptr(c),
+                                        ptr(grid.x_d), grid.N, ptr(Eg_d), N_E, ptr(tb.K),
+                                        grid.pitch, 0, stream()), "nb_pp_lut_table")
+        else:
+            check(lib().nb_pp_analytic_table(PP_MODEL[hiEmodel], int(bool(nuclear_enhancement)),
+                                             ptr(grid.x_d), grid.N, ptr(Eg_d), N_E, ptr(tb.K),
+                                             grid.pitch, 0, stream()), "nb_pp_analytic_table")
+        return tb.finalize(np.full(N_E, c_cgs * 1e-9))
+
+    key = ("pp", grid.key, _ekey(E_eV), bool(useLUT), hiEmodel, bool(nuclear_enhancement))
+    return _cache_get(_TABLES, key, make, _TABLES_MAX)
+
+
+# ------------------------------------------------------------------------------
+# hot kernels
+# ------------------------------------------------------------------------------
+def contract(table, prep, out=None, exact=None):
+    """out[w][r] = coef[r] * trapz_loglog(n[w,:] K[r,:], x)."""
+    exact = EXACT if exact is None else exact
+    g = table.grid
+    out = empty(prep.W, table.R) if out is None else out
+    if exact and prep.nraw is None:
+        raise ValueError("exact contraction needs pd_prep(need_raw=True)")
+    check(lib().nb_contract(ptr(table.K), ptr(table.lrs), table.R, g.N, g.pitch, 0,
+                            ptr(prep.nraw if exact else prep.xn), ptr(prep.ds1), g.pitch, prep.W,
+                            ptr(g.dlx_d), ptr(g.x_d), ptr(table.coef), ptr(out),
+                            1 if exact else 0, stream()), "nb_contract")
+    return out
+
+
+def synchrotron(grid, prep, B_d, E_erg_d, out=None):
+    """Synchrotron._spectrum (radiative.py:282-342): out[w][e] in 1/(s eV)."""
+    N_E = E_erg_d.numel()
+    out = empty(prep.W, N_E) if out is None else out
+    check(lib().nb_synchrotron(ptr(grid.x_d), grid.N, ptr(prep.xn), ptr(prep.ds1), grid.pitch,
+                               ptr(grid.invdlx_d), ptr(grid.dlx_d), ptr(B_d), prep.W,
+                               ptr(E_erg_d), N_E, ptr(out), stream()), "nb_synchrotron")
+    return out
+
+
+def ic_seed_spectrum(grid, prep, E_eV, seed_E_eV, phn_d, per_walker, out, out_off):
+    """Fused IC on a tabulated seed whose density may differ per walker (SSC)."""
+    Eph = np.ascontiguousarray(E_eV, dtype=float) * eV_erg / mec2_erg
+    eps0 = np.ascontiguousarray(seed_E_eV, dtype=float) / mec2_eV
+    check(lib().nb_ic_seed_spectrum(ptr(grid.x_d), grid.N, ptr(prep.nraw), grid.pitch,
+                                    ptr(to_dev(Eph)), Eph.size, ptr(to_dev(eps0)), ptr(phn_d),
+                                    eps0.size, eps0.size if per_walker else 0, prep.W, ptr(out),
+                                    out.shape[1], out_off, stream()), "nb_ic_seed_spectrum")
+    return out
+
+
+def make_terms(terms):
+    """terms: list of (src tensor [W][ld], off, group_end, div, wscale tensor|None)."""
+    arr = (nb_term * len(terms))()
+    for k, (src, off, ge, div, ws) in enumerate(terms):
+        arr[k].src = src.data_ptr()
+        arr[k].wscale = ws.data_ptr() if ws is not None else None
+        arr[k].ld = src.shape[1]
+        arr[k].off = off
+        arr[k].group_end = int(ge)
+        arr[k].div = float(div)
+    return arr
+
+
+def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, lnp_out=None):
+    """flux model (radiative.py:102-111) and, with `data`, lnprob (core.py:64-121)."""
+    arr = make_terms(terms) if not isinstance(terms, ctypes.Array) else terms
+    d = data
+    check(lib().nb_combine_lnprob(
+        arr, len(arr), W, N_E, ptr(unit_fac_d),
+        ptr(d.flux) if d else None, ptr(d.err_lo) if d else None, ptr(d.err_hi) if d else None,
+        ptr(d.ul) if d else None, ptr(d.cl) if d else None, ptr(prior_d), ptr(flux_out),
+        ptr(lnp_out), stream()), "nb_combine_lnprob")
+
+
+def trapz_loglog(y, x, intervals=False):
+    """utils.py:285-355 on the device: y [R][N] host array, x [N] or [R][N]."""
+    y = np.ascontiguousarray(y, dtype=float)
+    x = np.ascontiguousarray(x, dtype=float)
+    R, N = y.shape
+    y_d, x_d = to_dev(y), to_dev(x)
+    out = empty(R)
+    iv = empty(R, max(N - 1, 1)) if intervals else None
+    check(lib().nb_trapz_loglog(ptr(y_d), R, N, N, ptr(x_d), N if x.ndim == 2 else 0, ptr(out),
+                                ptr(iv), stream()), "nb_trapz_loglog")
+    return (iv[:, : N - 1] if intervals else out).cpu().numpy()
+
+
+class DeviceData:
+    """Data columns of core.py:64-94 on the device, in the data table's flux unit."""
+
+    def __init__(self, flux, err_lo, err_hi, ul, cl):
+        self.N_E = int(np.size(flux))
+        self.flux, self.err_lo, self.err_hi = to_dev(flux), to_dev(err_lo), to_dev(err_hi)
+        self.ul = to_dev(np.asarray(ul).astype(np.int32), dtype=torch.int32)
+        self.cl = to_dev(np.broadcast_to(np.asarray(cl, dtype=float), (self.N_E,)))
+
+
+def fp64_peak_tflops(iters=4096, reps=5):
+    """Measured fp64 FMA throughput of this GPU (2 flops per DFMA), TFLOP/s."""
+    sm = torch.cuda.get_device_properties(device()).multi_processor_count
+    blocks, threads = sm * 8, 256
+    out = empty(blocks * threads)
+    fn = lib().nb_fp64_peak_probe
+    check(fn(ptr(out), blocks, threads, iters, stream()))
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(ptr(out), blocks, threads, iters, stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = max(best, blocks * threads * iters * 16 * 2 / (ms * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,183 @@
+# -*- coding: utf-8 -*-
+"""Walker sharding across GPUs (one process per GPU, torch.distributed).
+
+The reference's only parallelism is a multiprocessing.Pool over walkers
+(core.py:446-457).  Here the proposals of a half-ensemble are independent units:
+rank r evaluates rows [r*per, (r+1)*per) of the proposal matrix and ONE
+all-gather per half-step exchanges the log-probabilities (and the model-flux
+blobs every rank needs to keep its replica of the ensemble state).  Positions
+stay replicated without communication because every rank runs the same
+proposal/accept random stream.  Because each walker is evaluated by exactly one
+rank with identical code, chains are bitwise identical for any world size.
+
+Backends: NCCL on device tensors (product), gloo on CPU tensors (host-logic
+tests with a stand-in evaluator; the product path has no CPU compute).
+"""
+import numpy as np
+
+from .sampler import DeviceEnsemble, EnsembleSampler
+
+__all__ = ["shard_bounds", "ShardedSampler", "ShardedDeviceEnsemble"]
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world_info(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_bounds(n, world):
+    """Equal-size padded shards: per = ceil(n/world); rank r owns [r*per, min((r+1)*per, n))."""
+    per = -(-n // world)
+    return per, [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
+
+
+class ShardedSampler(EnsembleSampler):
+    """Host-driven stretch-move sampler whose half-ensemble evaluation is sharded.
+
+    evaluator(q[per, P]) -> (lnp[per], flux[per, N_E] | None): a LikelihoodPlan
+    wrapper in the product, any callable in the CPU tests."""
+
+    def __init__(self, nwalkers, ndim, evaluator, seed=0, group=None, **kw):
+        if seed is None:
+            raise ValueError("ShardedSampler needs an explicit seed shared by all ranks")
+        self.group = group
+        self.rank, self.world = world_info(group)
+        self._eval = evaluator
+        self._plan = evaluator if hasattr(evaluator, "blobs_for") else None
+        super().__init__(nwalkers, ndim, self._sharded_log_prob, vectorize=True, seed=seed, **kw)
+        self.collectives = 0
+
+    def _sharded_log_prob(self, q):
+        import torch
+
+        n = q.shape[0]
+        per, bounds = shard_bounds(n, self.world)
+        lo, hi = bounds[self.rank]
+        mine = np.empty((per, q.shape[1]))
+        mine[: hi - lo] = q[lo:hi]
+        if hi - lo < per:  # pad with a valid row so the batch size is fixed
+            mine[hi - lo:] = q[hi - 1] if hi > lo else q[0]
+        res = self._eval(mine)
+        lnp, flux = np.asarray(res[0], dtype=float), res[1]
+        nf = 0 if flux is None else flux.shape[1]
+        pack = np.empty((per, 1 + nf))
+        pack[:, 0] = lnp
+        if nf:
+            pack[:, 1:] = flux
+        if self.world > 1:
+            dist = _dist()
+            dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+            local = torch.from_numpy(pack).to(dev)
+            full = torch.empty((self.world * per, 1 + nf), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(full, local, group=self.group)
+            self.collectives += 1
+            full = full.cpu().numpy()
+        else:
+            full = pack
+        out = np.concatenate([full[r * per: r * per + (b - a)] for r, (a, b) in enumerate(bounds)])
+        lnp_all = out[:, 0].copy()
+        if not nf:
+            return lnp_all
+        flux_all = out[:, 1:]
+        if self._plan is not None:
+            from .sampler import BlobBatch
+
+            return lnp_all, BlobBatch(self._plan, flux_all, [])
+        return lnp_all, [(f,) for f in flux_all]
+
+
+class ShardedDeviceEnsemble(DeviceEnsemble):
+    """Device-resident ensemble step with the likelihood plan sharded over ranks:
+    per half-step  propose (replicated) -> plan on this rank's rows -> all-gather
+    of [lnp | flux] rows over NCCL -> accept (replicated)."""
+
+    def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None):
+        import torch
+
+        from . import engine as eng
+
+        if seed is None:
+            raise ValueError("ShardedDeviceEnsemble needs an explicit seed shared by all ranks")
+        self.group = group
+        self.rank, self.world = world_info(group)
+        super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=store_blobs,
+                         use_graph=False)
+        self.per, self.bounds = shard_bounds(self.Ns, self.world)
+        self.ex = plan.executable(self.per)
+        self.q_full = eng.zeros(self.per * self.world, self.P)
+        self.ncol = 1 + self.nb
+        self.pack_local = eng.zeros(self.per, self.ncol)
+        self.pack_full = eng.zeros(self.per * self.world, self.ncol)
+        self.lnp_full = eng.zeros(self.per * self.world)
+        self.flux_full = eng.zeros(self.per * self.world, max(self.nb, 1))
+        self.collectives = 0
+        if self.per * self.world != self.Ns:
+            raise ValueError("the half-ensemble (%d) must divide evenly over %d ranks"
+                             % (self.Ns, self.world))
+        self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 2) + 1
+        self._torch = torch
+
+    def set_state(self, coords):
+        """Evaluate the initial ensemble sharded, then replicate."""
+        from . import engine as eng
+
+        coords = np.ascontiguousarray(coords, dtype=float)
+        W = coords.shape[0]
+        per, bounds = shard_bounds(W, self.world)
+        if per * self.world != W:
+            raise ValueError("walkers must divide evenly over ranks")
+        lo, hi = bounds[self.rank]
+        lnp, flux, _ = self.plan(coords[lo:hi])
+        pack = np.concatenate([lnp[:, None], flux], axis=1)
+        if self.world > 1:
+            dist = _dist()
+            local = eng.to_dev(pack)
+            full = eng.zeros(W, pack.shape[1])
+            dist.all_gather_into_tensor(full, local, group=self.group)
+            pack = full.cpu().numpy()
+        if np.any(np.isnan(pack[:, 0])):
+            raise ValueError("The initial log_prob was NaN")
+        self.coords.copy_(eng.to_dev(coords))
+        self.lp.copy_(eng.to_dev(pack[:, 0].copy()))
+        if self.nb:
+            self.blobs.copy_(eng.to_dev(np.ascontiguousarray(pack[:, 1:])))
+        self.n_acc.zero_()
+
+    def _enqueue_step(self):
+        from . import engine as eng
+        from ._lib import check, lib
+
+        L, ptr, ex = lib(), eng.ptr, self.ex
+        lo = self.rank * self.per
+        for split in range(2):
+            check(L.nb_stretch_move(ptr(self.coords), self.P, self.Ns, split, ptr(self.step),
+                                    ptr(self.s_idx), ptr(self.c_idx), ptr(self.zz),
+                                    ptr(self.q_full), eng.stream()), "nb_stretch_move")
+            ex.pars.copy_(self.q_full[lo:lo + self.per])
+            self.plan._enqueue(ex)
+            if self.world > 1:
+                self.pack_local[:, 0].copy_(ex.lnp)
+                if self.nb:
+                    self.pack_local[:, 1:].copy_(ex.flux)
+                _dist().all_gather_into_tensor(self.pack_full, self.pack_local, group=self.group)
+                self.collectives += 1
+                self.lnp_full.copy_(self.pack_full[:, 0])
+                if self.nb:
+                    self.flux_full.copy_(self.pack_full[:, 1:])
+                new_lp, new_bl = self.lnp_full, self.flux_full
+            else:
+                new_lp, new_bl = ex.lnp, ex.flux
+            check(L.nb_stretch_update(
+                ptr(self.coords), ptr(self.lp), ptr(self.blobs) if self.nb else None, self.nb,
+                self.W, self.P, self.Ns, split, ptr(self.step), ptr(self.s_idx), ptr(self.zz),
+                ptr(self.lnu), ptr(self.q_full), ptr(new_lp), ptr(new_bl) if self.nb else None,
+                ptr(self.n_acc), ptr(self.chain), ptr(self.chain_lp),
+                ptr(self.chain_blobs) if self.nb else None, eng.stream()), "nb_stretch_update")

@@ -1,0 +1,479 @@
+# -*- coding: utf-8 -*-
+"""Affine-invariant ensemble sampler with the slice of the ``emcee`` (>=3.0) API
+that naima drives (core.py:127-160, 446-491, 523-536).
+
+emcee is a third-party dependency of the reference and is not installed in this
+image; this is a restatement of its published algorithm (Goodman & Weare 2010
+stretch move with the red-blue split of Foreman-Mackey et al. 2013) written from
+the call sites in naima and memory of emcee 3.1's behaviour -- parity with emcee
+itself is UNPINNED (the reference's tests hold no numeric fixture for it).  The
+draw order (shuffle of the split, then per half: zz, partner index, accept
+uniforms) follows emcee's so that a seeded ``numpy.random.RandomState`` produces
+the same kind of stream.
+
+Two execution modes:
+  * host-driven (this class): proposals/accepts in NumPy on the host, the
+    log-probability of each half-ensemble evaluated in ONE batched device call
+    (``vectorize=True`` semantics; the reference maps one lnprob per walker over
+    a multiprocessing.Pool);
+  * device-resident (:class:`DeviceEnsemble`): coordinates, log-probabilities and
+    blobs stay in HBM, pre-drawn random numbers are resident, and a whole step
+    (propose -> likelihood plan -> accept, twice) is one CUDA-graph replay.
+"""
+import numpy as np
+
+__all__ = ["EnsembleSampler", "State", "DeviceEnsemble"]
+
+
+class State:
+    """emcee.State: coords [W,P], log_prob [W], blobs, random_state."""
+
+    def __init__(self, coords, log_prob=None, blobs=None, random_state=None, copy=False):
+        if isinstance(coords, State):
+            log_prob, blobs, random_state = coords.log_prob, coords.blobs, coords.random_state
+            coords = coords.coords
+        dc = (lambda x: np.array(x, copy=True)) if copy else (lambda x: x)
+        self.coords = dc(np.atleast_2d(np.asarray(coords, dtype=float)))
+        self.log_prob = None if log_prob is None else dc(np.asarray(log_prob, dtype=float))
+        self.blobs = blobs
+        self.random_state = random_state
+
+    def __iter__(self):
+        # emcee allows `pos, lnp, rstate[, blobs] = state`
+        if self.blobs is None:
+            return iter((self.coords, self.log_prob, self.random_state))
+        return iter((self.coords, self.log_prob, self.random_state, self.blobs))
+
+    def __len__(self):
+        return 3 if self.blobs is None else 4
+
+    def __getitem__(self, i):
+        return list(iter(self))[i]
+
+
+def walkers_independent(coords):
+    """emcee.ensemble.walkers_independent: condition-number test of the ensemble."""
+    if not np.all(np.isfinite(coords)):
+        return False
+    C = coords - np.mean(coords, axis=0)[None, :]
+    C_colmax = np.amax(np.abs(C), axis=0)
+    if np.any(C_colmax == 0):
+        return False
+    C = C / C_colmax
+    C_colsum = np.sqrt(np.sum(C**2, axis=0))
+    C = C / C_colsum
+    return np.linalg.cond(C.astype(float)) <= 1e8
+
+
+class EnsembleSampler:
+    """Stretch-move ensemble sampler.
+
+    log_prob_fn(p, *args, **kwargs) is called per walker (``vectorize=False``,
+    returns ``lnp`` or ``(lnp, *blobs)``) or once per half-ensemble with
+    ``p[Ns, P]`` (``vectorize=True``, returns ``lnp[Ns]`` or ``(lnp[Ns], blobs)``
+    where blobs is a sequence of Ns per-walker blob tuples or a BlobBatch)."""
+
+    def __init__(self, nwalkers, ndim, log_prob_fn, args=None, kwargs=None, pool=None, a=2.0,
+                 vectorize=False, blobs_dtype=None, seed=None, live_dangerously=False,
+                 moves=None, backend=None):
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        self.log_prob_fn = log_prob_fn
+        self.args = [] if args is None else list(args)
+        self.kwargs = {} if kwargs is None else dict(kwargs)
+        self.pool = pool
+        self.a = float(a)
+        self.vectorize = vectorize
+        self.blobs_dtype = blobs_dtype
+        self.live_dangerously = live_dangerously
+        self._random = np.random.mtrand.RandomState(seed)
+        self._previous_state = None
+        self.reset()
+
+    # -- storage ---------------------------------------------------------------------
+    def reset(self):
+        self.iteration = 0
+        self._accepted = np.zeros(self.nwalkers)
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty((0, self.nwalkers))
+        self._blobs = []  # one entry per stored step: list of per-walker blobs | BlobBatch
+
+    @property
+    def random_state(self):
+        return self._random.get_state()
+
+    @random_state.setter
+    def random_state(self, state):
+        try:
+            self._random.set_state(state)
+        except Exception:
+            pass
+
+    def _grow(self, n):
+        self._chain = np.concatenate([self._chain, np.empty((n, self.nwalkers, self.ndim))])
+        self._log_prob = np.concatenate([self._log_prob, np.empty((n, self.nwalkers))])
+
+    def get_chain(self, flat=False, thin=1, discard=0):
+        v = self._chain[discard + thin - 1:self.iteration:thin]
+        return v.reshape((-1, self.ndim)) if flat else v
+
+    def get_log_prob(self, flat=False, thin=1, discard=0):
+        v = self._log_prob[discard + thin - 1:self.iteration:thin]
+        return v.reshape(-1) if flat else v
+
+    def get_blobs(self, flat=False, thin=1, discard=0):
+        if not self._blobs:
+            return None
+        steps = self._blobs[discard + thin - 1:self.iteration:thin]
+        out = np.empty((len(steps), self.nwalkers), dtype=object)
+        for i, st in enumerate(steps):
+            for w in range(self.nwalkers):
+                out[i, w] = st[w]
+        return out.reshape(-1) if flat else out
+
+    def get_last_sample(self):
+        return self._previous_state
+
+    @property
+    def acceptance_fraction(self):
+        return self._accepted / float(max(self.iteration, 1))
+
+    # legacy emcee-2 style accessors used around naima
+    @property
+    def chain(self):
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def flatchain(self):
+        return self.get_chain(flat=True)
+
+    @property
+    def lnprobability(self):
+        return self.get_log_prob().T
+
+    @property
+    def blobs(self):
+        return self.get_blobs()
+
+    # -- log-probability -------------------------------------------------------------
+    def compute_log_prob(self, coords):
+        p = np.asarray(coords, dtype=float)
+        if np.any(np.isinf(p)):
+            raise ValueError("At least one parameter value was infinite")
+        if np.any(np.isnan(p)):
+            raise ValueError("At least one parameter value was NaN")
+        if self.vectorize:
+            res = self.log_prob_fn(p, *self.args, **self.kwargs)
+            if isinstance(res, tuple):
+                log_prob, blobs = np.asarray(res[0], dtype=float), res[1]
+            else:
+                log_prob, blobs = np.asarray(res, dtype=float), None
+        else:
+            map_fn = self.pool.map if self.pool is not None else map
+            results = list(map_fn(_Wrapper(self.log_prob_fn, self.args, self.kwargs), list(p)))
+            try:
+                log_prob = np.array([float(r[0]) for r in results])
+                blobs = [tuple(r[1:]) for r in results]
+            except (IndexError, TypeError):
+                log_prob = np.array([float(r) for r in results])
+                blobs = None
+        if np.any(np.isnan(log_prob)):
+            raise ValueError("Probability function returned NaN")
+        return log_prob, blobs
+
+    # -- sampling --------------------------------------------------------------------
+    def _propose_half(self, state, inds, split):
+        """One half of the red-blue stretch move; returns the updated state and the
+        acceptance mask of the active walkers."""
+        S1 = inds == split
+        s = state.coords[S1]
+        c = state.coords[~S1]
+        Ns, Nc = len(s), len(c)
+        zz = ((self.a - 1.0) * self._random.rand(Ns) + 1) ** 2.0 / self.a
+        factors = (self.ndim - 1.0) * np.log(zz)
+        rint = self._random.randint(Nc, size=(Ns,))
+        q = c[rint] - (c[rint] - s) * zz[:, None]
+        new_log_prob, new_blobs = self.compute_log_prob(q)
+        lnpdiff = factors + new_log_prob - state.log_prob[S1]
+        accepted = lnpdiff > np.log(self._random.rand(Ns))
+        idx = np.flatnonzero(S1)[accepted]
+        state.coords[idx] = q[accepted]
+        state.log_prob[idx] = new_log_prob[accepted]
+        if new_blobs is not None:
+            if state.blobs is None:
+                raise ValueError("log_prob_fn returned blobs only for some calls")
+            acc_i = np.flatnonzero(accepted)
+            for j, i in zip(idx, acc_i):
+                state.blobs[j] = new_blobs[i]
+        return idx
+
+    def sample(self, initial_state, log_prob0=None, rstate0=None, blobs0=None, iterations=1,
+               tune=False, skip_initial_state_check=False, thin_by=1, thin=None, store=True,
+               progress=False):
+        state = State(initial_state, copy=True)
+        if np.shape(state.coords) != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions {0}".format(np.shape(state.coords)))
+        if not skip_initial_state_check and not walkers_independent(state.coords):
+            raise ValueError("Initial state has a large condition number. Make sure that your "
+                             "walkers are linearly independent for the best performance")
+        if self.nwalkers < 2 * self.ndim and not self.live_dangerously:
+            raise ValueError("It is unadvisable to use a red-blue move with fewer walkers than "
+                             "twice the number of dimensions.")
+        if rstate0 is not None:
+            self.random_state = rstate0
+        if log_prob0 is not None:
+            state.log_prob = np.asarray(log_prob0, dtype=float)
+        if blobs0 is not None:
+            state.blobs = blobs0
+        if state.log_prob is None:
+            state.log_prob, blobs = self.compute_log_prob(state.coords)
+            state.blobs = None if blobs is None else [blobs[w] for w in range(self.nwalkers)]
+        if np.shape(state.log_prob) != (self.nwalkers,):
+            raise ValueError("incompatible input dimensions")
+        if np.any(np.isnan(state.log_prob)):
+            raise ValueError("The initial log_prob was NaN")
+        if store:
+            self._grow(int(iterations))
+        all_inds = np.arange(self.nwalkers)
+        for _ in range(int(iterations)):
+            # emcee draws the move with random.choice(moves, p=weights) every iteration
+            self._random.choice(1, p=[1.0])
+            inds = all_inds % 2
+            self._random.shuffle(inds)
+            for split in range(2):
+                idx = self._propose_half(state, inds, split)
+                self._accepted[idx] += 1
+            state.random_state = self.random_state
+            if store:
+                self._chain[self.iteration] = state.coords
+                self._log_prob[self.iteration] = state.log_prob
+                if state.blobs is not None:
+                    self._blobs.append(list(state.blobs))
+            self.iteration += 1
+            self._previous_state = state
+            yield State(state, copy=True)
+
+    def run_mcmc(self, initial_state, nsteps, **kwargs):
+        if initial_state is None:
+            if self._previous_state is None:
+                raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been "
+                                 "called.")
+            initial_state = self._previous_state
+        results = None
+        for results in self.sample(initial_state, iterations=nsteps, **kwargs):
+            pass
+        self._previous_state = results
+        return results
+
+
+class _Wrapper:
+    def __init__(self, f, args, kwargs):
+        self.f, self.args, self.kwargs = f, args, kwargs
+
+    def __call__(self, x):
+        return self.f(x, *self.args, **self.kwargs)
+
+
+class BlobBatch:
+    """Per-walker blobs of a batched evaluation, materialised lazily: indexing
+    with a walker index yields the reference's blob tuple for that walker."""
+
+    def __init__(self, plan, flux, blob_arrays):
+        self.plan, self.flux, self.blob_arrays = plan, flux, blob_arrays
+
+    def __len__(self):
+        return self.flux.shape[0]
+
+    def __getitem__(self, w):
+        return _LazyBlob(self, w)
+
+
+class _LazyBlob:
+    """Blob tuple of one walker, built on first access (keeps the sampling loop
+    free of per-walker Python object construction)."""
+
+    __slots__ = ("batch", "w", "_t")
+
+    def __init__(self, batch, w):
+        self.batch, self.w, self._t = batch, w, None
+
+    def _get(self):
+        if self._t is None:
+            b = self.batch
+            self._t = b.plan.blobs_for(b.flux, b.blob_arrays, self.w)
+        return self._t
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __len__(self):
+        return len(self._get())
+
+    def __iter__(self):
+        return iter(self._get())
+
+
+class DeviceEnsemble:
+    """Device-resident stretch-move loop over a LikelihoodPlan.
+
+    Positions, log-probabilities and model-flux blobs live in HBM; the random
+    draws of a block of steps are generated with the same NumPy stream as the
+    host sampler and uploaded once per block; each ensemble step is one CUDA
+    graph replay (2 x [propose, plan, accept] + store).  The chain is read back
+    once at the end of the block.
+    """
+
+    def __init__(self, plan, nwalkers, a=2.0, seed=None, store_blobs=True, use_graph=True):
+        import torch
+
+        from . import engine as eng
+
+        if nwalkers % 2:
+            raise ValueError("DeviceEnsemble needs an even number of walkers")
+        if nwalkers < 2 * plan.P:
+            raise ValueError("It is unadvisable to use a red-blue move with fewer walkers than "
+                             "twice the number of dimensions.")
+        self.plan, self.W, self.P, self.a = plan, int(nwalkers), plan.P, float(a)
+        self.Ns = self.W // 2
+        self.nb = plan.N_E if store_blobs else 0
+        self._random = np.random.mtrand.RandomState(seed)
+        self.ex = plan.executable(self.Ns)
+        self.coords = eng.zeros(self.W, self.P)
+        self.lp = eng.zeros(self.W)
+        self.blobs = eng.zeros(self.W, max(self.nb, 1))
+        self.n_acc = eng.zeros(self.W, dtype=torch.int32)
+        self.step = eng.zeros(1, dtype=torch.int32)
+        self.use_graph = use_graph
+        self._graph = None
+        self._block = 0
+        self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 2) + 1
+
+    def set_state(self, coords):
+        """Upload positions and evaluate their log-probability (one batched call)."""
+        from . import engine as eng
+
+        coords = np.ascontiguousarray(coords, dtype=float)
+        lnp, flux, _ = self.plan(coords)
+        if np.any(np.isnan(lnp)):
+            raise ValueError("The initial log_prob was NaN")
+        self.coords.copy_(eng.to_dev(coords))
+        self.lp.copy_(eng.to_dev(lnp))
+        if self.nb:
+            self.blobs.copy_(eng.to_dev(flux))
+        self.n_acc.zero_()
+
+    def _draw_block(self, n):
+        W, Ns = self.W, self.Ns
+        s_idx = np.empty((n, 2, Ns), dtype=np.int32)
+        c_idx = np.empty((n, 2, Ns), dtype=np.int32)
+        zz = np.empty((n, 2, Ns))
+        lnu = np.empty((n, 2, Ns))
+        all_inds = np.arange(W)
+        for t in range(n):
+            self._random.choice(1, p=[1.0])
+            inds = all_inds % 2
+            self._random.shuffle(inds)
+            for split in range(2):
+                S1 = inds == split
+                s_idx[t, split] = np.flatnonzero(S1)
+                comp = np.flatnonzero(~S1)
+                zz[t, split] = ((self.a - 1.0) * self._random.rand(Ns) + 1) ** 2.0 / self.a
+                c_idx[t, split] = comp[self._random.randint(Ns, size=(Ns,))]
+                lnu[t, split] = np.log(self._random.rand(Ns))
+        return s_idx, c_idx, zz, lnu
+
+    def _alloc_block(self, n):
+        import torch
+
+        from . import engine as eng
+
+        if self._block >= n:
+            return
+        self._block = n
+        W, Ns = self.W, self.Ns
+        self.s_idx = eng.zeros(n, 2, Ns, dtype=torch.int32)
+        self.c_idx = eng.zeros(n, 2, Ns, dtype=torch.int32)
+        self.zz = eng.zeros(n, 2, Ns)
+        self.lnu = eng.zeros(n, 2, Ns)
+        self.chain = eng.zeros(n, W, self.P)
+        self.chain_lp = eng.zeros(n, W)
+        self.chain_blobs = eng.zeros(n, W, self.nb) if self.nb else None
+        self._graph = None
+
+    def _enqueue_step(self):
+        from . import engine as eng
+        from ._lib import check, lib
+
+        L, ptr, ex = lib(), eng.ptr, self.ex
+        for split in range(2):
+            check(L.nb_stretch_move(ptr(self.coords), self.P, self.Ns, split, ptr(self.step),
+                                    ptr(self.s_idx), ptr(self.c_idx), ptr(self.zz), ptr(ex.pars),
+                                    eng.stream()), "nb_stretch_move")
+            self.plan._enqueue(ex)
+            check(L.nb_stretch_update(
+                ptr(self.coords), ptr(self.lp), ptr(self.blobs) if self.nb else None, self.nb,
+                self.W, self.P, self.Ns, split, ptr(self.step), ptr(self.s_idx), ptr(self.zz),
+                ptr(self.lnu), ptr(ex.pars), ptr(ex.lnp), ptr(ex.flux) if self.nb else None,
+                ptr(self.n_acc), ptr(self.chain), ptr(self.chain_lp),
+                ptr(self.chain_blobs) if self.nb else None, eng.stream()), "nb_stretch_update")
+
+    def load_draws(self, nsteps):
+        """Draw and upload the random numbers of the next `nsteps` steps."""
+        import torch
+
+        from . import engine as eng
+
+        self._alloc_block(nsteps)
+        s_idx, c_idx, zz, lnu = self._draw_block(nsteps)
+        self.s_idx[:nsteps].copy_(eng.to_dev(s_idx, dtype=torch.int32))
+        self.c_idx[:nsteps].copy_(eng.to_dev(c_idx, dtype=torch.int32))
+        self.zz[:nsteps].copy_(eng.to_dev(zz))
+        self.lnu[:nsteps].copy_(eng.to_dev(lnu))
+        self.step.zero_()
+
+    def run_loaded(self, nsteps):
+        """Run `nsteps` steps on the loaded draws (asynchronous; no host sync)."""
+        import torch
+
+        if self.use_graph and self._graph is None:
+            # warm-up outside capture, then rewind the step counter and state
+            c0, l0, b0, a0 = (self.coords.clone(), self.lp.clone(), self.blobs.clone(),
+                              self.n_acc.clone())
+            self._enqueue_step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s):
+                    self._enqueue_step()
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = g
+            self.coords.copy_(c0)
+            self.lp.copy_(l0)
+            self.blobs.copy_(b0)
+            self.n_acc.copy_(a0)
+            self.step.zero_()
+        for _ in range(nsteps):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._enqueue_step()
+
+    def run(self, nsteps):
+        """Draw, upload, run and read back `nsteps` steps: returns (chain, log_prob,
+        blobs|None) as host arrays [nsteps, W, ...]."""
+        import torch
+
+        self.load_draws(nsteps)
+        self.run_loaded(nsteps)
+        torch.cuda.synchronize()
+        chain = self.chain[:nsteps].cpu().numpy()
+        lp = self.chain_lp[:nsteps].cpu().numpy()
+        blobs = self.chain_blobs[:nsteps].cpu().numpy() if self.nb else None
+        if np.any(np.isnan(lp)):
+            raise ValueError("Probability function returned NaN")
+        return chain, lp, blobs
+
+    @property
+    def acceptance_counts(self):
+        return self.n_acc.cpu().numpy()

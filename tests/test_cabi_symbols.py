@@ -1,0 +1,86 @@
+"""The C-ABI library loads and exports every symbol include/naima_b200.h
+declares, and the ctypes binding agrees with the header on every parameter
+count (no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "naima_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(nb_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from naima_b200.build import build_library
+
+    return ctypes.CDLL(build_library())
+
+
+def test_header_declares_the_path():
+    fns = header_functions()
+    for name in ("nb_trapz_loglog", "nb_pdist_eval", "nb_pd_prep", "nb_particle_energy",
+                 "nb_ic_planck_table", "nb_ic_seed_table", "nb_ic_seed_spectrum",
+                 "nb_brems_table", "nb_pp_analytic_table", "nb_pp_lut_table",
+                 "nb_table_finalize", "nb_contract", "nb_synchrotron", "nb_combine_lnprob",
+                 "nb_param_map", "nb_stretch_propose", "nb_stretch_accept", "nb_stretch_move",
+                 "nb_stretch_update", "nb_version", "nb_strerror"):
+        assert name in fns, name
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    for name in header_functions():
+        assert hasattr(built_lib, name), "missing symbol %s" % name
+
+
+def test_ctypes_binding_matches_header(built_lib):
+    from naima_b200 import _lib
+
+    fns = header_functions()
+    for name, argtypes in _lib.PROTOTYPES.items():
+        assert name in fns, "binding for undeclared function %s" % name
+        assert len(argtypes) == fns[name], (name, len(argtypes), fns[name])
+    unbound = set(fns) - set(_lib.PROTOTYPES) - {"nb_version", "nb_strerror",
+                                                  "nb_contract_smem_bytes",
+                                                  "nb_ic_seed_table_batched"}
+    assert not unbound, unbound
+    L = _lib.lib()  # loads without a GPU and sets every prototype
+    assert L.nb_version() >= 100
+    assert L.nb_strerror(-1).decode() == "invalid argument"
+
+
+def test_struct_layouts():
+    from naima_b200 import _lib
+
+    assert ctypes.sizeof(_lib.nb_term) == 40
+    assert ctypes.sizeof(_lib.nb_parmap) == 32
+    assert ctypes.sizeof(_lib.nb_prior) == 24
+
+
+def test_product_has_no_cpu_path():
+    """Compute entry points refuse to run without a CUDA device."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import naima_b200 as nb
+    from naima_b200 import units as u
+    from naima_b200.models import InverseCompton, PowerLaw
+
+    ic = InverseCompton(PowerLaw(1e30 / u.eV, 1 * u.TeV, 2.1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ic.flux([1, 10] * u.TeV)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nb.trapz_loglog([1.0, 2.0], [1.0, 2.0])

@@ -29,8 +29,8 @@ def P(a):
 
 
 class Term(ctypes.Structure):
-    _fields_ = [("src", ctypes.c_void_p), ("ld", ctypes.c_int), ("off", ctypes.c_int),
-                ("group_end", ctypes.c_int), ("div", ctypes.c_double)]
+    _fields_ = [("src", ctypes.c_void_p), ("wscale", ctypes.c_void_p), ("ld", ctypes.c_int),
+                ("off", ctypes.c_int), ("group_end", ctypes.c_int), ("div", ctypes.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -266,8 +266,8 @@ def test_combine_lnprob(emu, rxj_data):
     b = flux * np.exp(0.3 * rng.normal(size=(W, N_E))) * 4 * np.pi * 0.5
     src = np.ascontiguousarray(np.concatenate([a, b], axis=1))  # [W][2 N_E]
     div = 4 * np.pi
-    terms = (Term * 2)(Term(src.ctypes.data, 2 * N_E, 0, 0, 1.0),
-                       Term(src.ctypes.data, 2 * N_E, N_E, 1, div))
+    terms = (Term * 2)(Term(src.ctypes.data, None, 2 * N_E, 0, 0, 1.0),
+                       Term(src.ctypes.data, None, 2 * N_E, N_E, 1, div))
     unit = np.full(N_E, 1.0)
     elo = rxj_data["hess_flux_error"].copy()
     ehi = 1.3 * elo

@@ -1,0 +1,191 @@
+"""Host-side logic that needs no GPU: units layer, data-table validation, the
+tracing of user callbacks into a plan description, the ensemble sampler's
+stretch move against the oracle's NumPy restatement, Nelder-Mead."""
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import naima_b200 as nb
+from helpers import (ElectronIC, ElectronSynIC, lnprior_IC, lnprior_SynIC, oracle_stretch_sampler,
+                     rxj_tables)
+from naima_b200 import fused
+from naima_b200 import units as u
+
+
+def test_units_conversions():
+    assert (100 * u.GeV).to("eV").value == 1e11
+    assert (1 * u.PeV).to("eV").value == 1e15
+    assert_allclose((1 * u.kpc).to("cm").value, 3.0856775814913673e21, rtol=1e-15)
+    assert_allclose((1 * u.Unit("mec2")).to("eV").value, 510998.9499961642, rtol=1e-15)
+    q = u.Quantity([1.0, 2.0], "1/(s cm2 eV)")
+    assert q.unit.physical_type == "differential flux"
+    assert_allclose(q.to("1/(s cm2 TeV)").value, [1e12, 2e12])
+    sed = (q * u.Quantity([1.0, 2.0], "TeV") ** 2).to("erg/(cm2 s)")
+    assert sed.unit.physical_type == "flux"
+    assert_allclose(sed.value, np.array([1.0, 8.0]) * 1e24 * 1.602176634e-12)
+    assert (0.415 * u.eV / u.cm**3).unit.physical_type == "pressure"
+    assert (1 / (u.eV * u.cm**3)).unit.physical_type == "differential number density"
+    assert (10 ** np.float64(3) / u.eV).unit.physical_type == "differential energy"
+    assert (3 * u.uG).to("G").value == 3e-6
+    assert_allclose((45 * u.deg).to("rad").value, np.pi / 4)
+    assert u.Unit("1 / (cm2 s TeV)") == u.Unit("1/(s TeV cm2)")
+    with pytest.raises(u.UnitConversionError):
+        (1 * u.eV).to("cm")
+    with pytest.raises(u.UnitsError):
+        (1 * u.eV) + 1.0
+    assert ((1 * u.kpc) != 0) and not np.all((0 * u.kpc) != 0)
+    assert_allclose(((2 * u.erg) / (4 * u.erg)).decompose().value, 0.5)
+    assert_allclose(float(u.Quantity(3.0, "TeV") / u.Quantity(1.5, "GeV")), 2000.0)
+
+
+def test_read_ipac_and_validate(tmp_path):
+    txt = ("\\ comment\n\\cl=0.95\n|energy|   flux|flux_error|  ul|\n|double| double|    double|long|\n"
+           "|   TeV|1 / (cm2 s TeV)|1 / (cm2 s TeV)|    |\n"
+           " 1.0 1e-11 1e-12 0\n 0.5 4e-11 3e-12 0\n 2.0 2e-12 1e-12 1\n")
+    f = tmp_path / "t.dat"
+    f.write_text(txt)
+    t = nb.read_ipac(str(f))
+    assert t.meta["keywords"]["cl"]["value"] == 0.95
+    d = nb.validate_data_table(t)
+    assert_allclose(d["energy"].value, [0.5, 1.0, 2.0])  # sorted (regression #247)
+    assert list(d["ul"]) == [False, False, True] and np.all(d["cl"] == 0.95)
+    assert d["flux"].unit == u.Unit("1/(s TeV cm2)")
+    assert "energy_error_lo" in d and "flux_error_hi" in d
+    with pytest.raises(TypeError):
+        nb.validate_data_table({"energy": 1})
+    bad = nb.DataTable()
+    bad["energy"] = [1, 2] * u.TeV
+    bad["flux"] = u.Quantity([1, 2], "1/(cm2 s TeV)")
+    with pytest.raises(TypeError):
+        nb.validate_data_table(bad)  # no flux_error
+    bad["flux_error"] = u.Quantity([1, 2], "TeV")
+    with pytest.raises(TypeError):
+        nb.validate_data_table(bad)  # wrong physical type
+
+
+def test_validate_multiple_tables_and_sed_conversion():
+    suz, hess = rxj_tables()
+    d = nb.validate_data_table([suz, hess])
+    assert len(d) == 36 + 28 and d["flux"].unit.physical_type == "flux"
+    assert np.all(np.diff(d["energy"].to("eV").value) > 0)
+    assert set(np.unique(d["group"])) == {0, 1}
+    d2 = nb.validate_data_table([suz, hess], sed=False)
+    assert d2["flux"].unit.physical_type == "differential flux"
+    E = d["energy"]
+    assert_allclose((d2["flux"] * E**2).to("erg/(cm2 s)").value, d["flux"].value, rtol=1e-14)
+    funit, sedf = nb.sed_conversion(E, u.Unit("1/(s cm2 eV)"), True)
+    assert funit.physical_type == "flux" and sedf.unit.physical_type != "dimensionless"
+    with pytest.raises(u.UnitsError):
+        nb.sed_conversion(E, u.Unit("cm"), True)
+    t = nb.build_data_table([1, 2, 3] * u.TeV, u.Quantity([3, 2, 1], "1/(cm2 s TeV)"),
+                            flux_error=u.Quantity([1, 1, 1], "1/(cm2 s TeV)"), ul=[0, 0, 1],
+                            cl=0.99)
+    assert np.all(nb.validate_data_table(t)["cl"] == 0.99)
+
+
+def test_trace_synic():
+    suz, hess = rxj_tables()
+    data = nb.validate_data_table([suz, hess])
+    flux, blobs, sp = fused.trace(ElectronSynIC, lnprior_SynIC, data, 4)
+    kinds = [type(c).__name__ for c, _, _ in flux.groups]
+    assert kinds == ["InverseCompton", "Synchrotron"]
+    assert flux.unit == u.Unit("1/(s cm2 eV)") and not flux.sed
+    assert_allclose(flux.groups[0][1], 4 * np.pi * 3.0856775814913673e21**2)
+    assert blobs[0].kind == "W"
+    assert sp.terms == [(0, 0, 0.0, np.inf), (1, 0, -1.0, 5.0), (3, 0, 0.0, np.inf)]
+    pd = flux.groups[0][0].particle_distribution
+    vals = pd._eval_params(nb.models._val(pd.amplitude, "1/eV"))
+    assert (vals[0].src, vals[0].fn, vals[0].scale) == (0, fused.FN_POW10, 1.0)
+    assert vals[1] == 1e13 and (vals[2].src, vals[2].fn) == (1, fused.FN_ID)
+    assert (vals[3].src, vals[3].fn, vals[3].scale) == (2, fused.FN_POW10, 1e12)
+    B = nb.models._val(flux.groups[1][0].B, "G")
+    assert (B.src, B.fn) == (3, fused.FN_ID) and B.scale == pytest.approx(1e-6, rel=1e-15)
+
+
+def test_trace_ic_blobs_and_failures():
+    _, hess = rxj_tables()
+    data = nb.validate_data_table(hess)
+    flux, blobs, sp = fused.trace(ElectronIC, lnprior_IC, data, 3)
+    assert flux.unit == data["flux"].unit
+    assert isinstance(blobs[0], tuple) and blobs[0][1].kind == "pdist" and blobs[1].kind == "W"
+
+    def bad1(pars, data):
+        return ElectronIC([pars[0] + 1.0, pars[1], pars[2]], data)
+
+    def bad2(pars, data):
+        if pars[1] > 2:
+            return ElectronIC(pars, data)
+        return ElectronIC(pars, data)
+
+    def bad3(pars, data):
+        return np.ones(len(data["energy"])) * u.Unit("1/(s cm2 TeV)")
+
+    for bad in (bad1, bad2, bad3):
+        with pytest.raises(fused.TraceError):
+            fused.trace(bad, lnprior_IC, data, 3)
+    with pytest.raises(fused.TraceError):
+        fused.trace(ElectronIC, lambda p: -0.5 * p[1] ** 2, data, 3)
+
+
+def _gauss_lnprob(q):
+    q = np.atleast_2d(q)
+    return -0.5 * np.sum((q - np.array([1.0, -2.0, 0.5])) ** 2 / np.array([1.0, 4.0, 0.25]), axis=1)
+
+
+def test_ensemble_sampler_matches_oracle_stretch_move():
+    rng = np.random.default_rng(2)
+    W, P, n = 12, 3, 25
+    p0 = rng.normal(size=(W, P))
+    s = nb.EnsembleSampler(W, P, _gauss_lnprob, vectorize=True, seed=99)
+    st = s.run_mcmc(p0, n)
+    chain, lps = oracle_stretch_sampler(_gauss_lnprob, p0, n, 99)
+    assert np.array_equal(s.get_chain(), chain) and np.array_equal(s.get_log_prob(), lps)
+    assert np.array_equal(st.coords, chain[-1])
+    assert s.get_chain(flat=True).shape == (n * W, P)
+    assert 0.2 < s.acceptance_fraction.mean() < 0.9
+    # per-walker calling convention with blobs
+    s2 = nb.EnsembleSampler(W, P, lambda p: (float(_gauss_lnprob(p)[0]), p.sum(), "x"), seed=99)
+    s2.run_mcmc(p0, n)
+    assert np.array_equal(s2.get_chain(), chain)
+    b = s2.get_blobs()
+    assert b.shape == (n, W) and b[3, 4][1] == "x"
+    assert b[-1, 0][0] == pytest.approx(chain[-1, 0].sum())
+    s2.reset()
+    assert s2.get_chain().shape == (0, W, P) and s2.iteration == 0
+
+
+def test_ensemble_sampler_errors():
+    p0 = np.random.default_rng(0).normal(size=(8, 3))
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(4, 3, _gauss_lnprob, vectorize=True).run_mcmc(p0[:4], 1)
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(8, 3, _gauss_lnprob, vectorize=True).run_mcmc(p0[:6], 1)
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(8, 3, _gauss_lnprob, vectorize=True).run_mcmc(np.ones((8, 3)), 1)
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(8, 3, lambda q: np.full(len(q), np.nan), vectorize=True).run_mcmc(p0, 1)
+    bad = p0.copy()
+    bad[0, 0] = np.inf
+    with pytest.raises(ValueError):
+        nb.EnsembleSampler(8, 3, _gauss_lnprob, vectorize=True).run_mcmc(
+            bad, 1, skip_initial_state_check=True)
+
+
+def test_nelder_mead():
+    from naima_b200.minimize import minimize
+
+    f = lambda x: (x[0] - 3.0) ** 2 + 10 * (x[1] + 1.0) ** 2 + 2.0
+    r = minimize(f, [1.0, 1.0], options={"xtol": 1e-6, "ftol": 1e-9, "maxfev": 2000})
+    assert r["success"] and r["status"] == 0
+    assert_allclose(r["x"], [3.0, -1.0], rtol=1e-4)
+    r = minimize(f, [1.0, 1.0], options={"maxfev": 5})
+    assert r["status"] == 1 and not r["success"]
+
+
+def test_priors_scalar_conventions():
+    assert nb.uniform_prior(1, 0, 2) == 0.0 and nb.uniform_prior(-1, 0, 2) == -np.inf
+    assert nb.normal_prior(1.0, 1.0, 2.0) == -0.5 * (2 * np.pi * 2.0)
+    assert nb.log_uniform_prior(4.0, 1, None) == 0.25
+    assert nb.log_uniform_prior(0.5, 1, 3) == -np.inf
