@@ -238,6 +238,7 @@ def ic_table(grid, E_eV, seeds):
         Eph_d = to_dev(Eph)
         tb = Table(grid, S * N_E, S, N_E)
         coef = np.empty(S * N_E)
+        keep = tb.inputs = [Eph_d]  # device inputs stay alive with the table
         for s, seed in enumerate(seeds):
             if seed[0] == "thermal":
                 T, uu = seed[1], seed[2]
@@ -245,9 +246,13 @@ def ic_table(grid, E_eV, seeds):
                     uu = ar_cgs * T**4
                 uf = uu / (ar_cgs * T**4)
                 th = seed[3] if len(seed) > 3 else np.nan
+                # named locals: a temporary tensor would be freed (and its block
+                # reused by the next upload) before the kernel reads it
+                T_d, th_d = to_dev([T]), to_dev([th])
                 check(lib().nb_ic_planck_table(
-                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(to_dev([T])), ptr(to_dev([th])),
+                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(T_d), ptr(th_d),
                     1, ptr(tb.K), grid.pitch, s * N_E, stream()), "nb_ic_planck_table")
+                keep.extend([T_d, th_d])
             else:
                 uf = 1.0
                 if seed[0] == "mono":
@@ -256,9 +261,11 @@ def ic_table(grid, E_eV, seeds):
                 else:
                     eps0 = np.asarray(seed[1], dtype=float) / mec2_eV
                     phn = np.asarray(seed[2], dtype=float) * mec2_eV
+                eps0_d, phn_d = to_dev(eps0), to_dev(phn)
                 check(lib().nb_ic_seed_table(
-                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(to_dev(eps0)), ptr(to_dev(phn)),
+                    ptr(grid.x_d), grid.N, ptr(Eph_d), N_E, ptr(eps0_d), ptr(phn_d),
                     eps0.size, ptr(tb.K), grid.pitch, s * N_E, stream()), "nb_ic_seed_table")
+                keep.extend([eps0_d, phn_d])
             coef[s * N_E:(s + 1) * N_E] = uf * Eph / E_eV
         return tb.finalize(coef)
 
@@ -346,8 +353,9 @@ def ic_seed_spectrum(grid, prep, E_eV, seed_E_eV, phn_d, per_walker, out, out_of
     """Fused IC on a tabulated seed whose density may differ per walker (SSC)."""
     Eph = np.ascontiguousarray(E_eV, dtype=float) * eV_erg / mec2_erg
     eps0 = np.ascontiguousarray(seed_E_eV, dtype=float) / mec2_eV
+    Eph_d, eps0_d = to_dev(Eph), to_dev(eps0)
     check(lib().nb_ic_seed_spectrum(ptr(grid.x_d), grid.N, ptr(prep.nraw), grid.pitch,
-                                    ptr(to_dev(Eph)), Eph.size, ptr(to_dev(eps0)), ptr(phn_d),
+                                    ptr(Eph_d), Eph.size, ptr(eps0_d), ptr(phn_d),
                                     eps0.size, eps0.size if per_walker else 0, prep.W, ptr(out),
                                     out.shape[1], out_off, stream()), "nb_ic_seed_spectrum")
     return out
