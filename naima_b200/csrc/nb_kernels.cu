@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) ic_seed_spectrum_kernel(
   double* s_e0 = reinterpret_cast<double*>(smem_raw);  // [Ns]
   double* s_ph = s_e0 + Ns;                            // [Ns] phn/eps0
   double* s_y = s_ph + Ns;                             // [N]  n_e * K
-  __shared__ double s_red[8];
+  double* s_red = s_y + N;                             // [8]  per-warp partial sums
   const int e = blockIdx.x, w = blockIdx.y;
   const double* ph = phn + (size_t)w * phn_wstride;
   for (int s = threadIdx.x; s < Ns; s += blockDim.x) {
@@ -917,7 +917,7 @@ int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch
     return NB_EINVAL;
   if (W == 0) return 0;
   if (W > 65535) return NB_ETOOLARGE;
-  long long smem = (2LL * Ns + N) * 8;
+  long long smem = (2LL * Ns + N + 8) * 8;
   if (smem > 227 * 1024) return NB_ETOOLARGE;
   static bool attr_set = false;
   if (!attr_set) {
