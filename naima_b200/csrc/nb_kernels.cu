@@ -315,56 +315,105 @@ struct SynArgs {
   const double* E_erg;
   int N_E;
   double* out;
-  int m;        // odd chunk per lane
   int e_per_cta;
 };
 
 __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx
+  // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx; per photon energy: first live node
   double* s_iec = reinterpret_cast<double*>(smem_raw);
   double* s_cb = s_iec + a.N;
   double* s_xn = s_cb + a.N;
   double* s_ds = s_xn + a.N;
   double* s_idl = s_ds + a.N;
   double* s_dl = s_idl + a.N;
+  int* s_js = reinterpret_cast<int*>(s_dl + a.N);  // [e_per_cta]
+  __shared__ int s_jmin;
 
   const int w = blockIdx.x;
   const double Bw = a.B[w];
-  for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nint = a.N - 1;
+  const int ebeg = blockIdx.y * a.e_per_cta;
+  const int eend = min(ebeg + a.e_per_cta, a.N_E);
+
+  // nodes whose exp(-E/Ec) underflows to zero contribute nothing: find, per photon
+  // energy, the first node that can be non-zero, and only set up nodes from the
+  // smallest of them on
+  if (threadIdx.x == 0) s_jmin = a.N;
+  __syncthreads();
+  for (int e = ebeg + threadIdx.x; e < eend; e += blockDim.x) {
+    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[e]);
+    s_js[e - ebeg] = js;
+    atomicMin(&s_jmin, js);
+  }
+  __syncthreads();
+  const int jmin = s_jmin;
+  for (int j = jmin + threadIdx.x; j < a.N; j += blockDim.x) {
     syn_node(a.gam[j], Bw, &s_iec[j], &s_cb[j]);
     s_xn[j] = a.xn[(size_t)w * a.wpitch + j];
     s_ds[j] = a.ds1[(size_t)w * a.wpitch + j];
-    if (j < a.N - 1) {
+    if (j < nint) {
       s_idl[j] = a.invdlx[j];
       s_dl[j] = a.dlx[j];
     }
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nint = a.N - 1;
-  const int i0 = lane * a.m;
-  const int i1 = min(i0 + a.m, nint);
-  const int ebeg = blockIdx.y * a.e_per_cta;
-  const int eend = min(ebeg + a.e_per_cta, a.N_E);
-
   for (int e = ebeg + warp; e < eend; e += 8) {
-    double E = a.E_erg[e];
+    const double E = a.E_erg[e];
+    const int js = s_js[e - ebeg];
+    const int len = nint - js;
     double acc = 0.0;
-    if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
-    acc = warp_sum(acc);
+    if (len > 0) {
+      const int m = odd_chunk(len);
+      const int i0 = js + lane * m;
+      const int i1 = min(i0 + m, nint);
+      if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
+      acc = warp_sum(acc);
+    }
     if (lane == 0) a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, E, acc);
   }
 }
 
 // ---------------------------------------------------------------------------
-// combine + likelihood: one thread per walker (N_E is O(100))
+// combine + likelihood: one warp per walker.  Lanes evaluate the model flux and the
+// Gaussian terms of the photon energies e = lane, lane + 32, ... into shared memory;
+// lane 0 then adds the terms in numpy's summation order (a few hundred cycles).
 // ---------------------------------------------------------------------------
-__global__ void combine_lnprob_kernel(CombineArgs a) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int COMBINE_WARPS = 4;
+
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(CombineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * COMBINE_WARPS + warp;
   if (w >= a.W) return;
-  combine_lnprob_walker(a, w);
+  double* s_t = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.N_E;
+  int n = 0, nviol = 0, nul = 0;
+  for (int e = lane; e < a.N_E; e += 32) {
+    double m = combine_model(a, w, e);
+    if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+    if (!a.lnp) continue;
+    if (a.ul[e]) {
+      ++nul;
+      if (m > a.data_flux[e]) ++nviol;
+    } else {
+      ++n;
+      s_t[e] = lnprob_term(m, a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+    }
+  }
+  if (!a.lnp) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+    nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+    nul += __shfl_xor_sync(0xffffffffu, nul, o);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double seq = numpy_order_sum(a.N_E, a.ul, n, [&](int e) { return s_t[e]; });
+    a.lnp[w] = lnprob_finish(a, w, seq, nul, nviol);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -814,21 +863,20 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
   SynArgs a;
   a.gam = gam; a.N = N; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
   a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
-  a.m = odd_chunk(N - 1);
-  long long smem = 6LL * N * 8;
-  if (smem > 227 * 1024) return NB_ETOOLARGE;
+  // photon energies per CTA: 8 (one per warp) unless that launches far more CTAs than
+  // 8 waves of 148 SMs (each CTA repeats the per-walker node set-up)
+  int epc = 8;
+  while (epc < N_E && (long long)W * ((N_E + epc - 1) / epc) > 8 * 148) epc <<= 1;
+  a.e_per_cta = epc;
+  long long smem = 6LL * N * 8 + 4LL * epc;
+  if (smem > 226 * 1024) return NB_ETOOLARGE;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synchrotron_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  // photon energies per CTA: 8 (one per warp) unless that launches far more CTAs than
-  // 4 waves of 148 SMs
-  int epc = 8;
-  while (epc < N_E && (long long)W * ((N_E + epc - 1) / epc) > 4 * 148) epc <<= 1;
-  a.e_per_cta = epc;
   dim3 grid(W, (N_E + epc - 1) / epc);
   synchrotron_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(a);
   NB_CHECK_LAUNCH();
@@ -850,7 +898,10 @@ int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
   a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
   a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
   a.prior = prior; a.flux_model = flux_model; a.lnp = lnp;
-  combine_lnprob_kernel<<<(W + 63) / 64, 64, 0, as_stream(stream)>>>(a);
+  size_t smem = (size_t)COMBINE_WARPS * N_E * sizeof(double);
+  if (smem > 48 * 1024) return NB_ETOOLARGE;
+  combine_lnprob_kernel<<<(W + COMBINE_WARPS - 1) / COMBINE_WARPS, COMBINE_WARPS * 32, smem,
+                          as_stream(stream)>>>(a);
   NB_CHECK_LAUNCH();
   return 0;
 }

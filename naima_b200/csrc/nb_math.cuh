@@ -100,13 +100,43 @@ NB_HD double interval_exact(double x1, double x2, double y1, double y2) {
   return v;
 }
 
+// 1/b to ~1 ulp: hardware seed (MUFU.RCP64H, rel. error <= 2^-23) + one cubically
+// convergent Newton step (3 DFMA).  Not correctly rounded -- the IEEE division it
+// replaces costs ~25 instructions plus a slow path for zero/NaN operands, which the
+// zero-padded emissivity tables hit all the time.  Zero, inf, NaN and denormal b give
+// NaN/inf here; every caller masks those cases with its own selects.
+NB_HD double fast_rcp(double b) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);
+#else
+  return 1.0 / b;
+#endif
+}
+
 // hoisted form: xy = x*y at both nodes, bp1 = b + 1 with
 // b = ln(y2/y1)/ln(x2/x1), dlx = ln(x2/x1).  (x2/x1)^b == y2/y1, so
 // y1 (x2 (x2/x1)^b - x1) == x2 y2 - x1 y1.
 NB_HD double interval_fast(double xy1, double xy2, double bp1, double dlx) {
-  double v = (xy2 - xy1) / bp1;
+  double v = (xy2 - xy1) * fast_rcp(bp1);
+#if defined(__CUDA_ARCH__)
+  // the classification runs on the integer pipe (the fp64 pipe is the bottleneck):
+  // regular slope <=> 1e-10 < |bp1| < inf, tested on the high word (cut at 1.0000002e-10;
+  // both branches agree to 1e-12 there); NaN/inf slopes take the log branch like the
+  // reference's `abs(b + 1) > 1e-10` being False for NaN
+  unsigned hb = (unsigned)__double2hiint(bp1) & 0x7fffffffu;
+  bool regular = (hb - 0x3DDB7CE0u) < (0x7FF00000u - 0x3DDB7CE0u);
+  if (!regular) v = xy1 * dlx;
+  unsigned z1 = ((unsigned)__double2hiint(xy1) << 1) | (unsigned)__double2loint(xy1);
+  unsigned z2 = ((unsigned)__double2hiint(xy2) << 1) | (unsigned)__double2loint(xy2);
+  if (z1 == 0u || z2 == 0u) v = 0.0;
+#else
   if (!(fabs(bp1) > 1e-10)) v = xy1 * dlx;  // also the NaN-slope branch
   if (xy1 == 0.0 || xy2 == 0.0) v = 0.0;
+#endif
   return v;
 }
 
@@ -496,7 +526,7 @@ NB_HD double prior_eval(int kind, double v, double a, double b) {
 // ---------------------------------------------------------------------------
 // per-lane bodies of the hot kernels (lane = contiguous interval range [i0,i1))
 // ---------------------------------------------------------------------------
-inline int odd_chunk(int nint) {
+NB_HD int odd_chunk(int nint) {
   int m = (nint + 31) / 32;
   if (m < 1) m = 1;
   if ((m & 1) == 0) ++m;
@@ -556,6 +586,53 @@ NB_HD void syn_node(double g, double B, double* iec, double* cb) {
   *cb = cbrt(i);
 }
 
+// rational part of Gtilde with one reciprocal square root:
+//   R = 1.808 cb gt2 / (gt3 sqrt(1 + 3.4 cb^2)) = 1.808 cb gt2 rsqrt(gt3^2 (1 + 3.4 cb^2))
+NB_HD double gtilde_rational_fast(double cb) {
+  double cb2 = cb * cb;
+  double cb4 = cb2 * cb2;
+  double gt2 = fma(0.347, cb4, fma(2.210, cb2, 1.0));
+  double gt3 = fma(0.217, cb4, fma(1.353, cb2, 1.0));
+  double d = (gt3 * gt3) * fma(3.4, cb2, 1.0);
+#if defined(__CUDA_ARCH__)
+  return (1.808 * cb) * gt2 * rsqrt(d);
+#else
+  return (1.808 * cb) * gt2 / sqrt(d);
+#endif
+}
+
+// ln(R2/R1) for neighbouring nodes: 2 atanh((R2-R1)/(R2+R1)) by its series while
+// |s| <= 0.05 (truncation < 2e-17 relative; default grids have |s| < 0.008), log otherwise
+NB_HD double log_ratio(double R1, double R2) {
+  double s = (R2 - R1) * fast_rcp(R2 + R1);
+  double s2 = s * s;
+  double p = fma(s2, 1.0 / 11.0, 1.0 / 9.0);
+  p = fma(p, s2, 1.0 / 7.0);
+  p = fma(p, s2, 1.0 / 5.0);
+  p = fma(p, s2, 1.0 / 3.0);
+  p = fma(p, s2, 1.0);
+  double v = (2.0 * s) * p;
+  if (!(fabs(s) <= 0.05)) v = log(R2 / R1);
+  return v;
+}
+
+// exp(-x) contributes exactly 0 once x > 745.14; nodes are ordered by decreasing x
+// (x = E / (kB g^2)), so every interval left of the first node with x <= 746 is zero.
+// Returns that node's index (0 when B is not a positive finite number).
+NB_HD int syn_first_node(const double* gam, int N, double B, double E_erg) {
+  double kB = 3 * E_ESU * HBAR_CGS * B;
+  kB /= 2 * (M_E_G * C_CGS);
+  double g2 = E_erg / (746.0 * kB);  // x <= 746  <=>  g^2 >= g2
+  if (!(g2 > 0.0) || !(g2 < 1e300)) return 0;
+  int lo = 0, hi = N;  // first j with gam[j]^2 >= g2
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    double g = gam[mid];
+    if (g * g >= g2) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 // synchrotron lane: integral of x*n*Gtilde(E/Ec) over intervals [i0,i1) with
 // ln(y2/y1) = ln(n2/n1) + ln(R2/R1) - (x2 - x1)
 NB_HD double syn_lane(double E, double cbE, const double* s_iec, const double* s_cb,
@@ -563,13 +640,13 @@ NB_HD double syn_lane(double E, double cbE, const double* s_iec, const double* s
                       const double* s_dl, int i0, int i1) {
   double acc = 0.0;
   double x1 = E * s_iec[i0];
-  double R1 = gtilde_rational(cbE * s_cb[i0]);
+  double R1 = gtilde_rational_fast(cbE * s_cb[i0]);
   double xy1 = s_xn[i0] * (R1 * exp(-x1));
   for (int i = i0; i < i1; ++i) {
     double x2 = E * s_iec[i + 1];
-    double R2 = gtilde_rational(cbE * s_cb[i + 1]);
+    double R2 = gtilde_rational_fast(cbE * s_cb[i + 1]);
     double xy2 = s_xn[i + 1] * (R2 * exp(-x2));
-    double bp1 = s_ds[i] + (log(R2 / R1) - (x2 - x1)) * s_idl[i];
+    double bp1 = s_ds[i] + (log_ratio(R1, R2) - (x2 - x1)) * s_idl[i];
     acc += interval_fast(xy1, xy2, bp1, s_dl[i]);
     x1 = x2;
     R1 = R2;
@@ -623,29 +700,18 @@ NB_HD double combine_model(const CombineArgs& a, int w, int e) {
   return total * a.unit_fac[e];
 }
 
-NB_HD void combine_lnprob_walker(const CombineArgs& a, int w) {
-  if (!a.lnp) {
-    for (int e = 0; e < a.N_E; ++e) a.flux_model[(size_t)w * a.N_E + e] = combine_model(a, w, e);
-    return;
-  }
-  int n = 0;
-  for (int e = 0; e < a.N_E; ++e) n += a.ul[e] ? 0 : 1;
-  // numpy pairwise summation order for n < 8 and 8 <= n <= 128 (np.sum of
-  // core.py:87); blocks of 8 accumulators beyond that.
+// Sum of the n non-upper-limit terms get(e), e ascending, in numpy's pairwise
+// summation order for n < 8 and 8 <= n <= 128 (np.sum of core.py:87); blocks of 8
+// accumulators beyond that.
+template <class GetT>
+NB_HD double numpy_order_sum(int N_E, const int* ul, int n, GetT get) {
   double r[8];
   double seq = 0.0;
   int k = 0;  // index among the non-UL points
   const int nblk = n - (n % 8);
-  int nviol = 0, nul = 0;
-  for (int e = 0; e < a.N_E; ++e) {
-    double m = combine_model(a, w, e);
-    if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
-    if (a.ul[e]) {
-      ++nul;
-      if (m > a.data_flux[e]) ++nviol;
-      continue;
-    }
-    double t = lnprob_term(m, a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+  for (int e = 0; e < N_E; ++e) {
+    if (ul[e]) continue;
+    double t = get(e);
     if (n < 8) {
       seq = (k == 0) ? t : seq + t;
     } else if (k < 8) {
@@ -660,13 +726,41 @@ NB_HD void combine_lnprob_walker(const CombineArgs& a, int w) {
   }
   if (n >= 8 && n == nblk) seq = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
   if (n == 0) seq = 0.0;
-  double total = seq;
+  return seq;
+}
+
+// lnprob from the Gaussian sum, the upper-limit violations and the prior (core.py:89-121)
+NB_HD double lnprob_finish(const CombineArgs& a, int w, double gauss_sum, int nul, int nviol) {
+  double total = gauss_sum;
   if (nul > 0) {
     double clv = (nviol < a.N_E) ? a.cl[nviol] : NAN;
     total += nviol * log(1.0 - clv);
   }
   double pr = a.prior ? a.prior[w] : 0.0;
-  a.lnp[w] = isinf(pr) ? pr : total + pr;
+  return isinf(pr) ? pr : total + pr;
+}
+
+// serial form (one walker): host emulation and the reference for the warp kernel
+NB_HD void combine_lnprob_walker(const CombineArgs& a, int w) {
+  if (!a.lnp) {
+    for (int e = 0; e < a.N_E; ++e) a.flux_model[(size_t)w * a.N_E + e] = combine_model(a, w, e);
+    return;
+  }
+  int n = 0, nviol = 0, nul = 0;
+  for (int e = 0; e < a.N_E; ++e) {
+    double m = combine_model(a, w, e);
+    if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+    if (a.ul[e]) {
+      ++nul;
+      if (m > a.data_flux[e]) ++nviol;
+    } else {
+      ++n;
+    }
+  }
+  double seq = numpy_order_sum(a.N_E, a.ul, n, [&](int e) {
+    return lnprob_term(combine_model(a, w, e), a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+  });
+  a.lnp[w] = lnprob_finish(a, w, seq, nul, nviol);
 }
 
 // FITPACK bispev at one point with clamping to the knot range

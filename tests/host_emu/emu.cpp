@@ -137,16 +137,19 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
   double* iec = (double*)malloc(sizeof(double) * N);
   double* cb = (double*)malloc(sizeof(double) * N);
   for (int j = 0; j < N; ++j) syn_node(gam[j], B, &iec[j], &cb[j]);
-  int nint = N - 1, m = odd_chunk(nint);
+  int nint = N - 1;
   for (int e = 0; e < N_E; ++e) {
     double part[32];
+    int js = syn_first_node(gam, N, B, E_erg[e]);
+    int len = nint - js;
+    int m = odd_chunk(len > 0 ? len : 1);
     for (int lane = 0; lane < 32; ++lane) {
-      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
-      part[lane] = (i0 < nint) ? syn_lane(E_erg[e], cbrt(E_erg[e]), iec, cb, xn, ds1, invdlx,
-                                          dlx, i0, i1)
-                               : 0.0;
+      int i0 = js + lane * m, i1 = i0 + m < nint ? i0 + m : nint;
+      part[lane] = (len > 0 && i0 < nint)
+                       ? syn_lane(E_erg[e], cbrt(E_erg[e]), iec, cb, xn, ds1, invdlx, dlx, i0, i1)
+                       : 0.0;
     }
-    out[e] = syn_finish(B, E_erg[e], tree32(part));
+    out[e] = syn_finish(B, E_erg[e], len > 0 ? tree32(part) : 0.0);
   }
   free(iec);
   free(cb);
