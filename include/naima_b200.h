@@ -227,6 +227,33 @@ int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, in
                  double* out, const nb_prior* priors_host, int n_priors, double* prior_out,
                  void* stream);
 
+/* --- per-walker set-up, fused ----------------------------------------------------
+ * nb_param_map, then for every job the nb_pd_prep operands of one particle
+ * distribution on one grid and/or its total particle energy (nb_particle_energy), in
+ * ONE launch (one CTA per walker): what BaseElectron._nelec / _gam / compute_We
+ * (radiative.py:147-195) and the user's model() parameter arithmetic do per lnprob call.
+ * `pm` is the nb_param_map output buffer; job.pd_off is the offset (in doubles) of the
+ * job's [W][NB_PD_MAXPAR] parameter block inside it.  jobs_host is a HOST array. */
+#define NB_MAX_PREP_JOBS 8
+typedef struct nb_prep_job {
+  int kind;             /* NB_PD_* */
+  int N;                /* grid nodes */
+  long long pd_off;
+  const double* x;      /* grid [N] */
+  const double* invdlx; /* [N-1]; may be NULL when xn == NULL */
+  double e_mul1, e_mul2, n_scale;
+  double* xn;           /* [W][wpitch] or NULL (energy only) */
+  double* ds1;
+  double* nraw;         /* may be NULL */
+  int wpitch;
+  int pad_;
+  double x_to_energy;
+  double* energy_out;   /* [W] or NULL */
+} nb_prep_job;
+int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
+                   double* pm, const nb_prior* priors_host, int n_priors, double* prior_out,
+                   const nb_prep_job* jobs_host, int n_jobs, void* stream);
+
 /* --- IC on a tabulated seed, fused (synchrotron self-Compton) ----------------
  * radiative.py:609-655 + 684 in one launch, reference operation order:
  *   out[w][out_off + e] = Eph[e] * trapz_loglog(nraw[w,:] * K_w[e,:], gam)

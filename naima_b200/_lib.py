@@ -35,6 +35,13 @@ class nb_prior(ctypes.Structure):
     _fields_ = [("par", c_int), ("kind", c_int), ("a", c_dbl), ("b", c_dbl)]
 
 
+class nb_prep_job(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("N", c_int), ("pd_off", c_ll), ("x", vp), ("invdlx", vp),
+                ("e_mul1", c_dbl), ("e_mul2", c_dbl), ("n_scale", c_dbl), ("xn", vp),
+                ("ds1", vp), ("nraw", vp), ("wpitch", c_int), ("pad_", c_int),
+                ("x_to_energy", c_dbl), ("energy_out", vp)]
+
+
 # name -> (argtypes); every function returns int
 PROTOTYPES = {
     "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
@@ -57,6 +64,8 @@ PROTOTYPES = {
                           vp, vp, vp, vp],
     "nb_param_map": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
                      ctypes.POINTER(nb_prior), c_int, vp, vp],
+    "nb_walker_prep": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
+                       ctypes.POINTER(nb_prior), c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

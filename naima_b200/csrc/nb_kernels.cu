@@ -383,35 +383,62 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
 // ---------------------------------------------------------------------------
 constexpr int COMBINE_WARPS = 4;
 
-__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(CombineArgs a) {
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
+    const __grid_constant__ CombineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
   if (w >= a.W) return;
+  // s_t[k]: Gaussian term of the k-th non-upper-limit point (k ascending with e)
   double* s_t = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.N_E;
   int n = 0, nviol = 0, nul = 0;
-  for (int e = lane; e < a.N_E; e += 32) {
-    double m = combine_model(a, w, e);
-    if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
-    if (!a.lnp) continue;
-    if (a.ul[e]) {
-      ++nul;
-      if (m > a.data_flux[e]) ++nviol;
-    } else {
-      ++n;
-      s_t[e] = lnprob_term(m, a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+  for (int e0 = 0; e0 < a.N_E; e0 += 32) {
+    const int e = e0 + lane;
+    bool is_pt = false;
+    double t = 0.0;
+    if (e < a.N_E) {
+      double m = combine_model(a, w, e);
+      if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+      if (a.lnp) {
+        if (a.ul[e]) {
+          ++nul;
+          if (m > a.data_flux[e]) ++nviol;
+        } else {
+          is_pt = true;
+          t = lnprob_term(m, a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+        }
+      }
     }
+    unsigned mask = __ballot_sync(0xffffffffu, is_pt);
+    if (is_pt) s_t[n + __popc(mask & ((1u << lane) - 1u))] = t;
+    n += __popc(mask);
   }
   if (!a.lnp) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    n += __shfl_xor_sync(0xffffffffu, n, o);
     nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
     nul += __shfl_xor_sync(0xffffffffu, nul, o);
   }
   __syncwarp();
+  // numpy's summation order (np.sum of core.py:87; see numpy_order_sum): n < 8
+  // sequential; else 8 strided accumulators r[j] = sum_i t[8 i + j] over the full
+  // blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) -- exactly the xor-1,
+  // xor-2, xor-4 shuffle tree over lanes 0..7 -- then the tail added sequentially
+  double seq = 0.0;
+  const int nblk = n - (n % 8);
+  if (n >= 8) {
+    double r = 0.0;
+    if (lane < 8) {
+      r = s_t[lane];
+      for (int i = 8 + lane; i < nblk; i += 8) r += s_t[i];
+    }
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    seq = r;
+  }
   if (lane == 0) {
-    double seq = numpy_order_sum(a.N_E, a.ul, n, [&](int e) { return s_t[e]; });
+    for (int i = (n >= 8 ? nblk : 0); i < n; ++i) seq = (i == 0) ? s_t[0] : seq + s_t[i];
     a.lnp[w] = lnprob_finish(a, w, seq, nul, nviol);
   }
 }
@@ -482,6 +509,107 @@ __global__ void param_map_kernel(ParamMapArgs a) {
     double lp = 0.0;
     for (int k = 0; k < a.n_pri; ++k) lp += prior_eval(a.pri[k].kind, p[a.pri[k].par], a.pri[k].a, a.pri[k].b);
     a.prior_out[w] = lp;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fused per-walker set-up: parameter map + priors, then every particle-distribution
+// job (integration operands and/or total particle energy).  One CTA per walker.
+// ---------------------------------------------------------------------------
+// blockIdx.x = walker, blockIdx.y = work item: (job, first node) for the integration
+// operands (256 nodes per CTA) or (job, -1) for a total-energy reduction.  Every CTA
+// re-derives its walker's mapped parameters (a handful of pow/exp) so that no CTA waits
+// for another; CTA y == 0 also publishes them (and the prior) for the later kernels.
+struct PrepItem {
+  short job;
+  short energy;  // != 0: total-energy item
+  int j0;
+};
+constexpr int NB_MAX_PREP_ITEMS = 48;
+struct WalkerPrepArgs {
+  ParamMapArgs pm;
+  nb_prep_job jobs[NB_MAX_PREP_JOBS];
+  PrepItem items[NB_MAX_PREP_ITEMS];
+  int n_jobs, n_items;
+};
+
+__global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant__ WalkerPrepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_node = reinterpret_cast<double*>(smem_raw);  // energy items: n at every node
+  __shared__ double s_pm[NB_MAX_MAP];
+  __shared__ double s_n[257];
+  __shared__ double s_red[256];
+  const int w = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool publish = blockIdx.y == 0;
+  const double* p = a.pm.pars + (size_t)w * a.pm.P;
+  if (tid < a.pm.n_out) {
+    const nb_parmap& m = a.pm.map[tid];
+    double v = m.scale;
+    if (m.src >= 0) {
+      double x = p[m.src];
+      if (m.fn == NB_FN_POW10) x = pow(10.0, x);
+      else if (m.fn == NB_FN_EXP) x = exp(x);
+      v = x * m.scale;
+    }
+    s_pm[tid] = v;
+    if (publish) a.pm.out[m.dst_off + (long long)w * m.dst_stride] = v;
+  }
+  if (publish && tid == 32 && a.pm.prior_out) {
+    double lp = 0.0;
+    for (int k = 0; k < a.pm.n_pri; ++k)
+      lp += prior_eval(a.pm.pri[k].kind, p[a.pm.pri[k].par], a.pm.pri[k].a, a.pm.pri[k].b);
+    a.pm.prior_out[w] = lp;
+  }
+  if ((int)blockIdx.y >= a.n_items) return;
+  __syncthreads();
+  const PrepItem it = a.items[blockIdx.y];
+  const nb_prep_job& J = a.jobs[it.job];
+  double pp[PD_MAXPAR];
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) pp[k] = 0.0;
+  for (int k = 0; k < a.pm.n_out; ++k) {
+    long long d = a.pm.map[k].dst_off - J.pd_off;
+    if (a.pm.map[k].dst_stride == PD_MAXPAR && d >= 0 && d < PD_MAXPAR) {
+#pragma unroll
+      for (int q = 0; q < PD_MAXPAR; ++q)
+        if (q == (int)d) pp[q] = s_pm[k];
+    }
+  }
+  if (!it.energy) {
+    const int j = it.j0 + tid;
+    double xj = 0.0, nj = 0.0;
+    if (j < J.N) {
+      xj = J.x[j];
+      nj = pd_eval(J.kind, pp, (xj * J.e_mul1) * J.e_mul2) * J.n_scale;
+      s_n[tid] = nj;
+    }
+    if (tid == 255 && it.j0 + 256 < J.N)  // first node of the next chunk
+      s_n[256] = pd_eval(J.kind, pp, (J.x[it.j0 + 256] * J.e_mul1) * J.e_mul2) * J.n_scale;
+    __syncthreads();
+    if (j < J.N) {
+      size_t o = (size_t)w * J.wpitch + j;
+      J.xn[o] = xj * nj;
+      if (J.nraw) J.nraw[o] = nj;
+      J.ds1[o] = (j < J.N - 1) ? log(s_n[tid + 1] / nj) * J.invdlx[j] + 1.0 : 0.0;
+    }
+  } else {
+    for (int i = tid; i < J.N; i += 256)
+      s_node[i] = pd_eval(J.kind, pp, (J.x[i] * J.e_mul1) * J.e_mul2) * J.n_scale;
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = tid; i < J.N - 1; i += 256) {
+      double x1 = J.x[i], x2 = J.x[i + 1];
+      acc += interval_exact(x1 * J.x_to_energy, x2 * J.x_to_energy, x1 * s_node[i],
+                            x2 * s_node[i + 1]);
+    }
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+      if (tid < s2) s_red[tid] += s_red[tid + s2];
+      __syncthreads();
+    }
+    if (tid == 0) J.energy_out[w] = s_red[0];
   }
 }
 
@@ -863,10 +991,10 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
   SynArgs a;
   a.gam = gam; a.N = N; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
   a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
-  // photon energies per CTA: 8 (one per warp) unless that launches far more CTAs than
-  // 8 waves of 148 SMs (each CTA repeats the per-walker node set-up)
-  int epc = 8;
-  while (epc < N_E && (long long)W * ((N_E + epc - 1) / epc) > 8 * 148) epc <<= 1;
+  // photon energies per CTA: every CTA repeats the per-walker node set-up, so take as
+  // many as still leaves >= 2 CTAs per SM (148 SMs), but at least one per warp
+  int epc = (N_E + 7) & ~7;
+  while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
   a.e_per_cta = epc;
   long long smem = 6LL * N * 8 + 4LL * epc;
   if (smem > 226 * 1024) return NB_ETOOLARGE;
@@ -954,6 +1082,77 @@ int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, in
   a.n_out = n_out; a.n_pri = n_priors; a.W = W; a.P = P;
   a.pars = pars; a.out = out; a.prior_out = prior_out;
   param_map_kernel<<<(W + 63) / 64, 64, 0, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill_param_map(ParamMapArgs& a, const double* pars, int W, int P,
+                          const nb_parmap* map_host, int n_out, double* out,
+                          const nb_prior* priors_host, int n_priors, double* prior_out) {
+  if (!pars || W < 0 || P < 1 || n_out < 0 || n_out > NB_MAX_MAP || n_priors < 0 ||
+      n_priors > NB_MAX_PRIORS || (n_out > 0 && (!map_host || !out)) ||
+      (n_priors > 0 && !priors_host))
+    return NB_EINVAL;
+  for (int k = 0; k < n_out; ++k) {
+    a.map[k] = map_host[k];
+    if (a.map[k].src >= P || a.map[k].fn < 0 || a.map[k].fn > NB_FN_EXP ||
+        a.map[k].dst_off < 0 || a.map[k].dst_stride < 0)
+      return NB_EINVAL;
+  }
+  for (int k = 0; k < n_priors; ++k) {
+    a.pri[k] = priors_host[k];
+    if (a.pri[k].par < 0 || a.pri[k].par >= P || a.pri[k].kind < 0 ||
+        a.pri[k].kind > NB_PRIOR_LOGUNIFORM)
+      return NB_EINVAL;
+  }
+  a.n_out = n_out; a.n_pri = n_priors; a.W = W; a.P = P;
+  a.pars = pars; a.out = out; a.prior_out = prior_out;
+  return 0;
+}
+
+int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
+                   double* pm, const nb_prior* priors_host, int n_priors, double* prior_out,
+                   const nb_prep_job* jobs_host, int n_jobs, void* stream) {
+  WalkerPrepArgs a;
+  int rc = fill_param_map(a.pm, pars, W, P, map_host, n_map, pm, priors_host, n_priors,
+                          prior_out);
+  if (rc) return rc;
+  if (n_jobs < 0 || n_jobs > NB_MAX_PREP_JOBS || (n_jobs > 0 && (!jobs_host || !pm)))
+    return NB_EINVAL;
+  for (int k = 0; k < n_jobs; ++k) {
+    const nb_prep_job& J = jobs_host[k];
+    if (J.kind < 0 || J.kind > NB_PD_LOGPAR || J.N < 2 || !J.x || J.pd_off < 0 ||
+        (!J.xn && !J.energy_out) || (J.xn && (!J.ds1 || !J.invdlx || J.wpitch < J.N)))
+      return NB_EINVAL;
+    a.jobs[k] = J;
+  }
+  a.n_jobs = n_jobs;
+  a.n_items = 0;
+  int max_energy_N = 0;
+  for (int k = 0; k < n_jobs; ++k) {
+    const nb_prep_job& J = a.jobs[k];
+    if (J.xn)
+      for (int j0 = 0; j0 < J.N; j0 += 256) {
+        if (a.n_items == NB_MAX_PREP_ITEMS) return NB_ETOOLARGE;
+        a.items[a.n_items++] = PrepItem{(short)k, 0, j0};
+      }
+    if (J.energy_out) {
+      if (a.n_items == NB_MAX_PREP_ITEMS) return NB_ETOOLARGE;
+      a.items[a.n_items++] = PrepItem{(short)k, 1, 0};
+      if (J.N > max_energy_N) max_energy_N = J.N;
+    }
+  }
+  if (W == 0) return 0;
+  if (W > 65535 * 32) return NB_ETOOLARGE;
+  size_t smem = (size_t)max_energy_N * sizeof(double);
+  if (smem > 200 * 1024) return NB_ETOOLARGE;
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(walker_prep_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid(W, a.n_items > 0 ? a.n_items : 1);
+  walker_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
   NB_CHECK_LAUNCH();
   return 0;
 }

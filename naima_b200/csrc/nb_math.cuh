@@ -624,13 +624,14 @@ NB_HD int syn_first_node(const double* gam, int N, double B, double E_erg) {
   kB /= 2 * (M_E_G * C_CGS);
   double g2 = E_erg / (746.0 * kB);  // x <= 746  <=>  g^2 >= g2
   if (!(g2 > 0.0) || !(g2 < 1e300)) return 0;
-  int lo = 0, hi = N;  // first j with gam[j]^2 >= g2
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    double g = gam[mid];
-    if (g * g >= g2) hi = mid; else lo = mid + 1;
-  }
-  return lo;
+  // first j with gam[j]^2 >= g2: guess from a log-uniform grid, then walk (0-2 steps on
+  // the reference's np.logspace grids; correct, if slow, on any increasing grid)
+  double l0 = log(gam[0]), l1 = log(gam[N - 1]);
+  double t = (0.5 * log(g2) - l0) / (l1 - l0) * (N - 1);
+  int j = (t > 0.0) ? ((t < (double)N) ? (int)t : N) : 0;
+  while (j > 0 && gam[j - 1] * gam[j - 1] >= g2) --j;
+  while (j < N && gam[j] * gam[j] < g2) ++j;
+  return j;
 }
 
 // synchrotron lane: integral of x*n*Gtilde(E/Ec) over intervals [i0,i1) with
@@ -684,6 +685,7 @@ struct CombineArgs {
 NB_HD double combine_model(const CombineArgs& a, int w, int e) {
   double total = 0.0, g = 0.0;
   bool first_in_group = true, first_group = true;
+#pragma unroll 4
   for (int t = 0; t < a.n_terms; ++t) {
     const nb_term& T = a.terms[t];
     double v = T.src[(size_t)w * T.ld + T.off + e];

@@ -23,7 +23,7 @@ import torch
 
 from . import engine as eng
 from . import units as u
-from ._lib import NB_PD_MAXPAR, PD_KIND, check, lib, nb_parmap, nb_prior
+from ._lib import NB_PD_MAXPAR, PD_KIND, check, lib, nb_parmap, nb_prep_job, nb_prior
 from .units import Quantity, Unit
 
 FN_ID, FN_POW10, FN_EXP = 0, 1, 2
@@ -274,6 +274,7 @@ class LikelihoodPlan:
         self._units()
         self._components()
         self._exec = {}
+        self._side = []
         self.launches_per_eval = 0
 
     # -- unit bookkeeping (core.py:64-71, utils.py:219-282) ------------------------
@@ -469,6 +470,29 @@ class LikelihoodPlan:
             elif spec["kind"] == "pdist":
                 ex.blob_bufs.append(eng.zeros(W, spec["e_eV"].size))
                 spec["e_d"] = eng.to_dev(spec["e_eV"])
+        # jobs of the fused per-walker set-up kernel
+        jobs = []
+        for prd, p in zip(self.preps, ex.preps):
+            g = prd["grid"]
+            jobs.append(dict(kind=PD_KIND[self.pds[prd["pd"]][0]._kind], N=g.N,
+                             pd_off=prd["pd"] * W * NB_PD_MAXPAR, x=g.x_d, invdlx=g.invdlx_d,
+                             e_mul1=g.e_mul1, e_mul2=g.e_mul2, n_scale=g.n_scale, xn=p.xn,
+                             ds1=p.ds1, nraw=p.nraw, wpitch=g.pitch))
+        for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
+            if spec["kind"] == "W":
+                g = spec["grid"]
+                jobs.append(dict(kind=PD_KIND[self.pds[spec["pd"]][0]._kind], N=g.N,
+                                 pd_off=spec["pd"] * W * NB_PD_MAXPAR, x=g.x_d,
+                                 e_mul1=g.e_mul1, e_mul2=g.e_mul2, n_scale=g.n_scale,
+                                 x_to_energy=g.x_to_erg, energy_out=buf))
+        if len(jobs) > 8:
+            raise TraceError("too many particle-distribution jobs in one plan")
+        ex.jobs = (nb_prep_job * max(len(jobs), 1))()
+        for k, jd in enumerate(jobs):
+            J = ex.jobs[k]
+            for name, v in jd.items():
+                setattr(J, name, v.data_ptr() if hasattr(v, "data_ptr") else v)
+        ex.n_jobs = len(jobs)
         # pinned staging for the host-facing call
         ex.pars_pin = torch.empty(W, P, dtype=torch.float64).pin_memory()
         ex.lnp_pin = torch.empty(W, dtype=torch.float64).pin_memory()
@@ -508,35 +532,48 @@ class LikelihoodPlan:
         """The launch sequence of one likelihood evaluation of ex.W walkers."""
         L, st, W = lib(), eng.stream(), ex.W
         n = 0
-        check(L.nb_param_map(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map, eng.ptr(ex.pm),
-                             ex.pri, ex.n_pri, eng.ptr(ex.prior), st), "nb_param_map")
+        check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map, eng.ptr(ex.pm),
+                               ex.pri, ex.n_pri, eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st),
+              "nb_walker_prep")
         n += 1
-        for prd, p in zip(self.preps, ex.preps):
-            kind = PD_KIND[self.pds[prd["pd"]][0]._kind]
-            g = prd["grid"]
-            check(L.nb_pd_prep_ex(kind, eng.ptr(ex.pd_block(prd["pd"])), W, eng.ptr(g.x_d), g.N,
-                                  g.e_mul1, g.e_mul2, g.n_scale, eng.ptr(g.invdlx_d),
-                                  eng.ptr(p.xn), eng.ptr(p.ds1), eng.ptr(p.nraw), g.pitch, st),
-                  "nb_pd_prep")
-            n += 1
-        for c, out in zip(self.comps, ex.outs):
+        def launch(c, out):
             p = ex.preps[c["prep"]]
             if c["kind"] == "syn":
                 eng.synchrotron(p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=out)
             else:
                 eng.contract(c["table"], p, out=out)
-            n += 1
+
+        # the radiative components are independent: fork them onto side streams (they
+        # become parallel branches of the captured graph) and join before the combine
+        comps = list(zip(self.comps, ex.outs))
+        main = torch.cuda.current_stream()
+        joins = []
+        if len(comps) > 1:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            while len(self._side) < len(comps) - 1:
+                self._side.append(torch.cuda.Stream())
+            for (c, out), side in zip(comps[1:], self._side):
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    launch(c, out)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                joins.append(done)
+        launch(*comps[0])
+        for done in joins:
+            main.wait_event(done)
+        n += len(comps)
         eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.flux, data=self.ddata,
                     prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp)
         n += 1
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
+            if spec["kind"] != "pdist":
+                continue  # particle energies are jobs of nb_walker_prep
             pdobj = self.pds[spec["pd"]][0]
-            if spec["kind"] == "W":
-                eng.particle_energy(spec["grid"], pdobj._kind, ex.pd_block(spec["pd"]), W, out=buf)
-            else:
-                check(L.nb_pdist_eval(PD_KIND[pdobj._kind], eng.ptr(ex.pd_block(spec["pd"])), W,
-                                      eng.ptr(spec["e_d"]), spec["e_eV"].size, eng.ptr(buf), st),
-                      "nb_pdist_eval")
+            check(L.nb_pdist_eval(PD_KIND[pdobj._kind], eng.ptr(ex.pd_block(spec["pd"])), W,
+                                  eng.ptr(spec["e_d"]), spec["e_eV"].size, eng.ptr(buf), st),
+                  "nb_pdist_eval")
             n += 1
         self.launches_per_eval = n
         return n
