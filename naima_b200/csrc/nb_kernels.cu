@@ -48,36 +48,68 @@ __global__ void pdist_eval_kernel(int kind, const double* __restrict__ params, i
   out[(size_t)w * N + i] = pd_eval(kind, p, e[i]);
 }
 
-__global__ void pd_prep_kernel(int kind, const double* __restrict__ params, int W,
-                               const double* __restrict__ x, int N, double e_mul1, double e_mul2,
-                               double n_scale, const double* __restrict__ invdlx,
-                               double* __restrict__ xn, double* __restrict__ ds1,
-                               double* __restrict__ nraw, int wpitch) {
+// One chunk of 256 nodes of one walker: n on the grid, x*n and the logarithmic slope
+// term ds1 per interval.  nraw != NULL selects the reference-order evaluation (pd_eval
+// with pow, slope from log(n2/n1)) that the exact contraction consumes; otherwise the
+// log-space form (pd_log_*).  s_n / s_nd: 257 entries of scratch shared memory.
+__device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const double* x, int N,
+                                              double e_mul1, double e_mul2, double n_scale,
+                                              const double* invdlx, double* xn, double* ds1,
+                                              double* nraw, size_t row, int j0, double* s_n,
+                                              PdNode* s_nd) {
+  const int tid = threadIdx.x;
+  const int j = j0 + tid;
+  const bool next = (tid == 255 && j0 + 256 < N);  // first node of the next chunk
+  double xj = 0.0, nj = 0.0;
+  PdNode nd;
+  nd.P = nd.c = nd.L = 0.0;
+  nd.side = 0;
+  if (nraw) {
+    if (j < N) {
+      xj = x[j];
+      nj = pd_eval(kind, pp, (xj * e_mul1) * e_mul2) * n_scale;
+      s_n[tid] = nj;
+    }
+    if (next) s_n[256] = pd_eval(kind, pp, (x[j0 + 256] * e_mul1) * e_mul2) * n_scale;
+    __syncthreads();
+    if (j < N) {
+      xn[row + j] = xj * nj;
+      nraw[row + j] = nj;
+      ds1[row + j] = (j < N - 1) ? log(s_n[tid + 1] / nj) * invdlx[j] + 1.0 : 0.0;
+    }
+  } else {
+    const PdLog S = pd_log_setup(kind, pp, n_scale);
+    if (j < N) {
+      xj = x[j];
+      double e = (xj * e_mul1) * e_mul2;
+      nd = pd_log_node(S, e);
+      nj = pd_log_value(S, nd);
+      s_nd[tid] = nd;
+    }
+    if (next) {
+      double e = (x[j0 + 256] * e_mul1) * e_mul2;
+      s_nd[256] = pd_log_node(S, e);
+    }
+    __syncthreads();
+    if (j < N) {
+      xn[row + j] = xj * nj;
+      ds1[row + j] = (j < N - 1) ? pd_log_ds1(S, nd, s_nd[tid + 1], invdlx[j]) : 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pd_prep_kernel(
+    int kind, const double* __restrict__ params, int W, const double* __restrict__ x, int N,
+    double e_mul1, double e_mul2, double n_scale, const double* __restrict__ invdlx,
+    double* __restrict__ xn, double* __restrict__ ds1, double* __restrict__ nraw, int wpitch) {
   __shared__ double s_n[257];
-  int j0 = blockIdx.x * 256;
-  int j = j0 + threadIdx.x;
+  __shared__ PdNode s_nd[257];
   int w = blockIdx.y;
   double p[PD_MAXPAR];
 #pragma unroll
   for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
-  double xj = 0.0, nj = 0.0;
-  if (j < N) {
-    xj = x[j];
-    nj = pd_eval(kind, p, (xj * e_mul1) * e_mul2) * n_scale;
-    s_n[threadIdx.x] = nj;
-  }
-  if (threadIdx.x == 0) {
-    int jl = j0 + 256;
-    if (jl < N) s_n[256] = pd_eval(kind, p, (x[jl] * e_mul1) * e_mul2) * n_scale;
-  }
-  __syncthreads();
-  if (j < N) {
-    size_t o = (size_t)w * wpitch + j;
-    xn[o] = xj * nj;
-    if (nraw) nraw[o] = nj;
-    if (j < N - 1) ds1[o] = log(s_n[threadIdx.x + 1] / nj) * invdlx[j] + 1.0;
-    else ds1[o] = 0.0;
-  }
+  pd_prep_chunk(kind, p, x, N, e_mul1, e_mul2, n_scale, invdlx, xn, ds1, nraw,
+                (size_t)w * wpitch, blockIdx.x * 256, s_n, s_nd);
 }
 
 // W = trapz_loglog(x*n, x*x_to_energy) in reference operation order; one CTA
@@ -397,15 +429,25 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
     bool is_pt = false;
     double t = 0.0;
     if (e < a.N_E) {
+      // issue the data loads before the model (independent; the store below would
+      // otherwise fence them behind the component loads)
+      int ule = 0;
+      double df = 0.0, elo = 0.0, ehi = 0.0;
+      if (a.lnp) {
+        ule = a.ul[e];
+        df = a.data_flux[e];
+        elo = a.err_lo[e];
+        ehi = a.err_hi[e];
+      }
       double m = combine_model(a, w, e);
       if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
       if (a.lnp) {
-        if (a.ul[e]) {
+        if (ule) {
           ++nul;
-          if (m > a.data_flux[e]) ++nviol;
+          if (m > df) ++nviol;
         } else {
           is_pt = true;
-          t = lnprob_term(m, a.data_flux[e], a.err_lo[e], a.err_hi[e]);
+          t = lnprob_term(m, df, elo, ehi);
         }
       }
     }
@@ -456,7 +498,7 @@ __global__ void stretch_propose_kernel(const double* __restrict__ coords, int P,
   int i = t / P, d = t - i * P;
   double c = coords[(size_t)c_idx[i] * P + d];
   double s = coords[(size_t)s_idx[i] * P + d];
-  q[t] = c - (c - s) * zz[i];
+  q[t] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz[i]));  // numpy's rounding, no FMA
 }
 
 __global__ void stretch_accept_kernel(double* __restrict__ coords, double* __restrict__ lp, int P,
@@ -538,6 +580,7 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   double* s_node = reinterpret_cast<double*>(smem_raw);  // energy items: n at every node
   __shared__ double s_pm[NB_MAX_MAP];
   __shared__ double s_n[257];
+  __shared__ PdNode s_nd[257];
   __shared__ double s_red[256];
   const int w = blockIdx.x;
   const int tid = threadIdx.x;
@@ -548,7 +591,7 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
     double v = m.scale;
     if (m.src >= 0) {
       double x = p[m.src];
-      if (m.fn == NB_FN_POW10) x = pow(10.0, x);
+      if (m.fn == NB_FN_POW10) x = exp10(x);
       else if (m.fn == NB_FN_EXP) x = exp(x);
       v = x * m.scale;
     }
@@ -577,25 +620,14 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
     }
   }
   if (!it.energy) {
-    const int j = it.j0 + tid;
-    double xj = 0.0, nj = 0.0;
-    if (j < J.N) {
-      xj = J.x[j];
-      nj = pd_eval(J.kind, pp, (xj * J.e_mul1) * J.e_mul2) * J.n_scale;
-      s_n[tid] = nj;
-    }
-    if (tid == 255 && it.j0 + 256 < J.N)  // first node of the next chunk
-      s_n[256] = pd_eval(J.kind, pp, (J.x[it.j0 + 256] * J.e_mul1) * J.e_mul2) * J.n_scale;
-    __syncthreads();
-    if (j < J.N) {
-      size_t o = (size_t)w * J.wpitch + j;
-      J.xn[o] = xj * nj;
-      if (J.nraw) J.nraw[o] = nj;
-      J.ds1[o] = (j < J.N - 1) ? log(s_n[tid + 1] / nj) * J.invdlx[j] + 1.0 : 0.0;
-    }
+    pd_prep_chunk(J.kind, pp, J.x, J.N, J.e_mul1, J.e_mul2, J.n_scale, J.invdlx, J.xn, J.ds1,
+                  J.nraw, (size_t)w * J.wpitch, it.j0, s_n, s_nd);
   } else {
-    for (int i = tid; i < J.N; i += 256)
-      s_node[i] = pd_eval(J.kind, pp, (J.x[i] * J.e_mul1) * J.e_mul2) * J.n_scale;
+    const PdLog S = pd_log_setup(J.kind, pp, J.n_scale);
+    for (int i = tid; i < J.N; i += 256) {
+      double e = (J.x[i] * J.e_mul1) * J.e_mul2;
+      s_node[i] = pd_log_value(S, pd_log_node(S, e));
+    }
     __syncthreads();
     double acc = 0.0;
     for (int i = tid; i < J.N - 1; i += 256) {
@@ -683,7 +715,7 @@ __global__ void stretch_move_kernel(const double* __restrict__ coords, int P, in
   int i = t / P, d = t - i * P;
   double c = coords[(size_t)c_idx[base + i] * P + d];
   double s = coords[(size_t)s_idx[base + i] * P + d];
-  q[t] = c - (c - s) * zz[base + i];
+  q[t] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz[base + i]));  // numpy's rounding, no FMA
 }
 
 __global__ void stretch_update_kernel(double* __restrict__ coords, double* __restrict__ lp,

@@ -88,7 +88,7 @@ void emu_bspl(const double* tx, int nx, const double* ty, int ny, const double* 
   for (int i = 0; i < n; ++i) out[i] = bspl_eval2d(tx, nx, ty, ny, c, x[i], y);
 }
 
-// pd_prep_kernel
+// pd_prep_chunk, reference-order branch (nraw != NULL): feeds the exact contraction
 void emu_pd_prep(int kind, const double* p, const double* x, int N, double m1, double m2,
                  double ns, const double* invdlx, double* xn, double* ds1, double* nraw) {
   for (int j = 0; j < N; ++j) {
@@ -97,6 +97,22 @@ void emu_pd_prep(int kind, const double* p, const double* x, int N, double m1, d
   }
   for (int j = 0; j < N - 1; ++j) ds1[j] = log(nraw[j + 1] / nraw[j]) * invdlx[j] + 1.0;
   ds1[N - 1] = 0.0;
+}
+
+// pd_prep_chunk, log-space branch: feeds the hoisted contraction and the synchrotron kernel
+void emu_pd_prep_log(int kind, const double* p, const double* x, int N, double m1, double m2,
+                     double ns, const double* invdlx, double* xn, double* ds1, double* n) {
+  PdLog S = pd_log_setup(kind, p, ns);
+  PdNode* nd = (PdNode*)malloc(sizeof(PdNode) * N);
+  for (int j = 0; j < N; ++j) {
+    double e = (x[j] * m1) * m2;
+    nd[j] = pd_log_node(S, e);
+    n[j] = pd_log_value(S, nd[j]);
+    xn[j] = x[j] * n[j];
+  }
+  for (int j = 0; j < N - 1; ++j) ds1[j] = pd_log_ds1(S, nd[j], nd[j + 1], invdlx[j]);
+  ds1[N - 1] = 0.0;
+  free(nd);
 }
 
 // table_finalize_kernel

@@ -160,16 +160,38 @@ def test_bspline(emu, lut_probe):
         assert_allclose(out, lut_probe["ds"][k], rtol=1e-12, atol=1e-45)
 
 
-def _prep(emu, pd, x, m1, m2, ns):
+def _prep(emu, pd, x, m1, m2, ns, exact=True):
+    """exact: reference-order operands (pow, log of the ratio); else the log-space form
+    the hoisted kernels consume."""
     N = x.size
     invdlx = np.zeros(N)
     invdlx[:-1] = 1.0 / np.log(x[1:] / x[:-1])
     xn, ds1, nraw = np.empty(N), np.empty(N), np.empty(N)
+    fn = emu.emu_pd_prep if exact else emu.emu_pd_prep_log
     with np.errstate(all="ignore"):
-        emu.emu_pd_prep(KINDS[pd.kind], P(pdpar(pd)), P(x), N, ctypes.c_double(m1),
-                        ctypes.c_double(m2), ctypes.c_double(ns), P(invdlx), P(xn), P(ds1),
-                        P(nraw))
+        fn(KINDS[pd.kind], P(pdpar(pd)), P(x), N, ctypes.c_double(m1), ctypes.c_double(m2),
+           ctypes.c_double(ns), P(invdlx), P(xn), P(ds1), P(nraw))
     return invdlx, xn, ds1, nraw
+
+
+@pytest.mark.parametrize("pd", PDS, ids=lambda p: p.kind)
+def test_pd_prep_log_vs_reference_order(emu, pd):
+    """The log-space operands agree with the reference-order ones: n to a few 1e-14
+    (|alpha ln(e/e0)| ulps), the slope term to 1e-11 absolute."""
+    gam = o.electron_grid(1e9, 510.9989e12, 100)
+    _, xn, ds1, nraw = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV, exact=True)
+    _, xn2, ds2, n2 = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV, exact=False)
+    ok = nraw > 1e-280
+    assert ok.sum() > 100
+    # the error grows with the cutoff argument c = (e/ec)**beta (exp(-c) turns the
+    # rounding of c into c ulps): 5e-14 over the 40 decades that matter, 1e-12 in the tail
+    main = nraw > 1e-40 * nraw.max()
+    assert_allclose(n2[main], nraw[main], rtol=5e-14)
+    assert_allclose(n2[ok], nraw[ok], rtol=1e-12)
+    # where exp(-c) alone underflows the reference returns 0; ln-space keeps A x^-alpha e^-c
+    assert np.all(n2[nraw == 0] <= 1e-250 * nraw.max())
+    okd = ok[:-1] & ok[1:]
+    assert_allclose(ds2[:-1][okd], ds1[:-1][okd], rtol=0, atol=1e-11 * np.max(np.abs(ds1[:-1][okd])))
 
 
 @pytest.mark.parametrize("pd", PDS[:5], ids=lambda p: p.kind)
@@ -190,8 +212,10 @@ def test_contract_ic(emu, pd, exact):
     R = Kref.shape[0]
     K = np.zeros((R, pitch))
     K[:, :N] = Kref
-    invdlx, xn, ds1, nraw = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV)
-    assert_allclose(nraw, o.nelec(pd, gam), rtol=4e-15)
+    invdlx, xn, ds1, nraw = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV, exact=bool(exact))
+    nref = o.nelec(pd, gam)
+    main = nref > (0 if exact else 1e-40 * nref.max())
+    assert_allclose(nraw[main], nref[main], rtol=4e-15 if exact else 5e-14)
     lrs = np.zeros((R, pitch))
     with np.errstate(all="ignore"):
         emu.emu_finalize(P(K), R, N, pitch, P(invdlx), P(lrs))
@@ -224,7 +248,8 @@ def test_contract_negative_table(emu):
     K[3, 5] = -K[3, 5]
     K[4, -7:] = 0.0
     pd = o.PDist("PowerLaw", 1e-12 * 1e36, 30e12, 2.34)
-    invdlx, xn, ds1, nraw = _prep(emu, pd, x, 1e9, 1.0, 1e9)
+    invdlx, xn_e, ds1_e, nraw = _prep(emu, pd, x, 1e9, 1.0, 1e9, exact=True)
+    _, xn, ds1, _ = _prep(emu, pd, x, 1e9, 1.0, 1e9, exact=False)
     lrs = np.zeros((R, pitch))
     with np.errstate(all="ignore"):
         emu.emu_finalize(P(K), R, N, pitch, P(invdlx), P(lrs))
@@ -233,8 +258,8 @@ def test_contract_negative_table(emu):
     for exact in (0, 1):
         out = np.empty(R)
         with np.errstate(all="ignore"):
-            emu.emu_contract(P(K), P(lrs), R, N, pitch, P(nraw if exact else xn), P(ds1),
-                             P(dlx), P(x), exact, P(out))
+            emu.emu_contract(P(K), P(lrs), R, N, pitch, P(nraw if exact else xn),
+                             P(ds1_e if exact else ds1), P(dlx), P(x), exact, P(out))
             ref = o.trapz_loglog(o.Jprot(pd, x) * K[:, :N], x)
         assert_allclose(out, ref, rtol=1e-12 if exact else 1e-9, atol=0)
 
@@ -245,7 +270,7 @@ def test_synchrotron(emu, pd):
     N = gam.size
     E_eV = np.logspace(-6, 6.5, 26)
     E_erg = E_eV * o.eV_erg
-    invdlx, xn, ds1, _ = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV)
+    invdlx, xn, ds1, _ = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV, exact=False)
     dlx = np.zeros(N)
     dlx[:-1] = np.log(gam[1:] / gam[:-1])
     for B in (3.24e-6, 1e-4, 1.0):
