@@ -294,6 +294,45 @@ int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, 
                       const double* new_blobs, int* n_accepted, double* chain,
                       double* chain_lp, double* chain_blobs, void* stream);
 
+/* Fused form: the whole red-blue half-step in three launches --
+ *   nb_walker_prep_move  (nb_stretch_move + nb_walker_prep: proposals are computed by
+ *                         the set-up CTAs themselves and published to `pars`)
+ *   nb_contract / nb_synchrotron ... (independent, may run concurrently)
+ *   nb_combine_lnprob_update (nb_combine_lnprob + nb_stretch_update incl. the chain
+ *                         append: every walker's row of step t is written by the warp
+ *                         that decides its proposal)
+ * `step` is read at kernel start by all kernels of a step and incremented by the last
+ * CTA of the split == 1 combine kernel to finish (ticket in `sync`, an int32 scratch
+ * word that must be zero before the first launch). */
+typedef struct nb_stretch {
+  double* coords;      /* [W][P] */
+  double* lp;          /* [W] */
+  double* blobs;       /* [W][nb] or NULL */
+  int nb, W, P, Ns, split;
+  int* step;           /* device int32: current step index t */
+  int* sync;           /* device int32 scratch (ticket counter) */
+  const int* s_idx;    /* [n_steps][2][Ns] */
+  const int* c_idx;
+  const double* zz;
+  const double* lnu;
+  int* n_accepted;     /* [W] */
+  double* chain;       /* [n_steps][W][P] or NULL */
+  double* chain_lp;    /* [n_steps][W] or NULL */
+  double* chain_blobs; /* [n_steps][W][nb] or NULL */
+} nb_stretch;
+int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
+                        const nb_parmap* map_host, int n_map, double* pm,
+                        const nb_prior* priors_host, int n_priors, double* prior_out,
+                        const nb_prep_job* jobs_host, int n_jobs, void* stream);
+/* flux_model (the blob rows, [Ns][N_E] with N_E == mv.nb when mv.nb > 0) and lnp are
+ * required; `pars` holds the proposals published by nb_walker_prep_move. */
+int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
+                             const nb_term* terms_host, int n_terms, int W, int N_E,
+                             const double* unit_fac, const double* data_flux,
+                             const double* err_lo, const double* err_hi, const int* ul,
+                             const double* cl, const double* prior, double* flux_model,
+                             double* lnp, void* stream);
+
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;
  * the caller times it with CUDA events to obtain the fp64 roofline denominator. */

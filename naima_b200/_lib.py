@@ -42,6 +42,13 @@ class nb_prep_job(ctypes.Structure):
                 ("x_to_energy", c_dbl), ("energy_out", vp)]
 
 
+class nb_stretch(ctypes.Structure):
+    _fields_ = [("coords", vp), ("lp", vp), ("blobs", vp), ("nb", c_int), ("W", c_int),
+                ("P", c_int), ("Ns", c_int), ("split", c_int), ("step", vp), ("sync", vp),
+                ("s_idx", vp), ("c_idx", vp), ("zz", vp), ("lnu", vp), ("n_accepted", vp),
+                ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp)]
+
+
 # name -> (argtypes); every function returns int
 PROTOTYPES = {
     "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
@@ -66,6 +73,11 @@ PROTOTYPES = {
                      ctypes.POINTER(nb_prior), c_int, vp, vp],
     "nb_walker_prep": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
                        ctypes.POINTER(nb_prior), c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
+    "nb_walker_prep_move": [ctypes.POINTER(nb_stretch), vp, c_int, c_int,
+                            ctypes.POINTER(nb_parmap), c_int, vp, ctypes.POINTER(nb_prior),
+                            c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
+    "nb_combine_lnprob_update": [ctypes.POINTER(nb_stretch), vp, ctypes.POINTER(nb_term), c_int,
+                                 c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

@@ -415,73 +415,135 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
 // ---------------------------------------------------------------------------
 constexpr int COMBINE_WARPS = 4;
 
+struct CombineKernelArgs {
+  CombineArgs c;
+  int has_mv;  // != 0: accept/reject the proposals and append the chain (nb_stretch)
+  nb_stretch mv;
+  const double* pars;  // [Ns][P] proposals
+};
+
 __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
-    const __grid_constant__ CombineArgs a) {
+    const __grid_constant__ CombineKernelArgs ka) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const CombineArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
-  if (w >= a.W) return;
-  // s_t[k]: Gaussian term of the k-th non-upper-limit point (k ascending with e)
-  double* s_t = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.N_E;
-  int n = 0, nviol = 0, nul = 0;
-  for (int e0 = 0; e0 < a.N_E; e0 += 32) {
-    const int e = e0 + lane;
-    bool is_pt = false;
-    double t = 0.0;
-    if (e < a.N_E) {
-      // issue the data loads before the model (independent; the store below would
-      // otherwise fence them behind the component loads)
-      int ule = 0;
-      double df = 0.0, elo = 0.0, ehi = 0.0;
-      if (a.lnp) {
-        ule = a.ul[e];
-        df = a.data_flux[e];
-        elo = a.err_lo[e];
-        ehi = a.err_hi[e];
+  const int t_step = ka.has_mv ? *ka.mv.step : 0;  // before anybody can increment it
+  if (w < a.W) {
+    // s_t[k]: Gaussian term of the k-th non-upper-limit point (k ascending with e)
+    double* s_t = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.N_E;
+    int n = 0, nviol = 0, nul = 0;
+    for (int e0 = 0; e0 < a.N_E; e0 += 32) {
+      const int e = e0 + lane;
+      bool is_pt = false;
+      double t = 0.0;
+      if (e < a.N_E) {
+        // issue the data loads before the model (independent; the store below would
+        // otherwise fence them behind the component loads)
+        int ule = 0;
+        double df = 0.0, elo = 0.0, ehi = 0.0;
+        if (a.lnp) {
+          ule = a.ul[e];
+          df = a.data_flux[e];
+          elo = a.err_lo[e];
+          ehi = a.err_hi[e];
+        }
+        double m = combine_model(a, w, e);
+        if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+        if (a.lnp) {
+          if (ule) {
+            ++nul;
+            if (m > df) ++nviol;
+          } else {
+            is_pt = true;
+            t = lnprob_term(m, df, elo, ehi);
+          }
+        }
       }
-      double m = combine_model(a, w, e);
-      if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
-      if (a.lnp) {
-        if (ule) {
-          ++nul;
-          if (m > df) ++nviol;
-        } else {
-          is_pt = true;
-          t = lnprob_term(m, df, elo, ehi);
+      unsigned mask = __ballot_sync(0xffffffffu, is_pt);
+      if (is_pt) s_t[n + __popc(mask & ((1u << lane) - 1u))] = t;
+      n += __popc(mask);
+    }
+    if (a.lnp) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
+        nul += __shfl_xor_sync(0xffffffffu, nul, o);
+      }
+      __syncwarp();
+      // numpy's summation order (np.sum of core.py:87; see numpy_order_sum): n < 8
+      // sequential; else 8 strided accumulators r[j] = sum_i t[8 i + j] over the full
+      // blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) -- exactly the
+      // xor-1, xor-2, xor-4 shuffle tree over lanes 0..7 -- then the tail sequentially
+      double seq = 0.0;
+      const int nblk = n - (n % 8);
+      if (n >= 8) {
+        double r = 0.0;
+        if (lane < 8) {
+          r = s_t[lane];
+          for (int i = 8 + lane; i < nblk; i += 8) r += s_t[i];
+        }
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        seq = r;
+      }
+      double lv = 0.0;
+      if (lane == 0) {
+        for (int i = (n >= 8 ? nblk : 0); i < n; ++i) seq = (i == 0) ? s_t[0] : seq + s_t[i];
+        lv = lnprob_finish(a, w, seq, nul, nviol);
+        a.lnp[w] = lv;
+      }
+      if (ka.has_mv) {
+        // emcee's accept step for proposal w of the active half, then this walker's
+        // row of the chain (its state is final for step t once its half is decided)
+        const nb_stretch& mv = ka.mv;
+        const size_t base = ((size_t)t_step * 2 + mv.split) * mv.Ns + w;
+        const int sidx = mv.s_idx[base];
+        int acc = 0;
+        double lp_old = 0.0;
+        if (lane == 0) {
+          lp_old = mv.lp[sidx];
+          double lnpdiff = (mv.P - 1) * log(mv.zz[base]) + lv - lp_old;
+          acc = lnpdiff > mv.lnu[base];
+        }
+        acc = __shfl_sync(0xffffffffu, acc, 0);
+        __syncwarp();  // this warp's flux_model row is visible to all its lanes
+        const size_t W_ = (size_t)mv.W;
+        for (int d = lane; d < mv.P; d += 32) {
+          double v = acc ? ka.pars[(size_t)w * mv.P + d] : mv.coords[(size_t)sidx * mv.P + d];
+          if (acc) mv.coords[(size_t)sidx * mv.P + d] = v;
+          if (mv.chain) mv.chain[((size_t)t_step * W_ + sidx) * mv.P + d] = v;
+        }
+        if (mv.nb > 0) {
+          for (int d = lane; d < mv.nb; d += 32) {
+            double v = acc ? a.flux_model[(size_t)w * a.N_E + d]
+                           : mv.blobs[(size_t)sidx * mv.nb + d];
+            if (acc) mv.blobs[(size_t)sidx * mv.nb + d] = v;
+            if (mv.chain_blobs) mv.chain_blobs[((size_t)t_step * W_ + sidx) * mv.nb + d] = v;
+          }
+        }
+        if (lane == 0) {
+          if (acc) {
+            mv.lp[sidx] = lv;
+            mv.n_accepted[sidx] += 1;
+          }
+          if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
         }
       }
     }
-    unsigned mask = __ballot_sync(0xffffffffu, is_pt);
-    if (is_pt) s_t[n + __popc(mask & ((1u << lane) - 1u))] = t;
-    n += __popc(mask);
   }
-  if (!a.lnp) return;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nviol += __shfl_xor_sync(0xffffffffu, nviol, o);
-    nul += __shfl_xor_sync(0xffffffffu, nul, o);
-  }
-  __syncwarp();
-  // numpy's summation order (np.sum of core.py:87; see numpy_order_sum): n < 8
-  // sequential; else 8 strided accumulators r[j] = sum_i t[8 i + j] over the full
-  // blocks of 8, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) -- exactly the xor-1,
-  // xor-2, xor-4 shuffle tree over lanes 0..7 -- then the tail added sequentially
-  double seq = 0.0;
-  const int nblk = n - (n % 8);
-  if (n >= 8) {
-    double r = 0.0;
-    if (lane < 8) {
-      r = s_t[lane];
-      for (int i = 8 + lane; i < nblk; i += 8) r += s_t[i];
+  if (ka.has_mv && ka.mv.split == 1) {
+    // the last CTA to finish advances the step counter (no CTA reads it any more)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      int ticket = atomicAdd(ka.mv.sync, 1);
+      if (ticket == (int)gridDim.x - 1) {
+        *ka.mv.sync = 0;
+        *ka.mv.step = t_step + 1;
+      }
     }
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    seq = r;
-  }
-  if (lane == 0) {
-    for (int i = (n >= 8 ? nblk : 0); i < n; ++i) seq = (i == 0) ? s_t[0] : seq + s_t[i];
-    a.lnp[w] = lnprob_finish(a, w, seq, nul, nviol);
   }
 }
 
@@ -568,11 +630,15 @@ struct PrepItem {
   int j0;
 };
 constexpr int NB_MAX_PREP_ITEMS = 48;
+constexpr int NB_MAX_MOVE_PAR = 32;
 struct WalkerPrepArgs {
   ParamMapArgs pm;
   nb_prep_job jobs[NB_MAX_PREP_JOBS];
   PrepItem items[NB_MAX_PREP_ITEMS];
   int n_jobs, n_items;
+  int has_mv;        // != 0: parameters are stretch-move proposals computed here
+  nb_stretch mv;
+  double* pars_out;  // where CTA y == 0 publishes the proposals
 };
 
 __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant__ WalkerPrepArgs a) {
@@ -586,6 +652,20 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   const int tid = threadIdx.x;
   const bool publish = blockIdx.y == 0;
   const double* p = a.pm.pars + (size_t)w * a.pm.P;
+  __shared__ double s_q[NB_MAX_MOVE_PAR];
+  if (a.has_mv) {
+    // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
+    if (tid < a.pm.P) {
+      const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + w;
+      double c = a.mv.coords[(size_t)a.mv.c_idx[base] * a.pm.P + tid];
+      double sv = a.mv.coords[(size_t)a.mv.s_idx[base] * a.pm.P + tid];
+      double q = __dsub_rn(c, __dmul_rn(__dsub_rn(c, sv), a.mv.zz[base]));
+      s_q[tid] = q;
+      if (publish) a.pars_out[(size_t)w * a.pm.P + tid] = q;
+    }
+    __syncthreads();
+    p = s_q;
+  }
   if (tid < a.pm.n_out) {
     const nb_parmap& m = a.pm.map[tid];
     double v = m.scale;
@@ -1043,27 +1123,58 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
   return 0;
 }
 
-int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
-                      const double* unit_fac, const double* data_flux, const double* err_lo,
-                      const double* err_hi, const int* ul, const double* cl, const double* prior,
-                      double* flux_model, double* lnp, void* stream) {
+static int launch_combine(const nb_stretch* mv, const double* pars, const nb_term* terms_host,
+                          int n_terms, int W, int N_E, const double* unit_fac,
+                          const double* data_flux, const double* err_lo, const double* err_hi,
+                          const int* ul, const double* cl, const double* prior,
+                          double* flux_model, double* lnp, void* stream) {
   if (!terms_host || n_terms < 1 || n_terms > NB_MAX_TERMS || W < 0 || N_E < 1 || !unit_fac)
     return NB_EINVAL;
   if (lnp && (!data_flux || !err_lo || !err_hi || !ul || !cl)) return NB_EINVAL;
   if (!lnp && !flux_model) return NB_EINVAL;
-  if (W == 0) return 0;
-  CombineArgs a;
+  CombineKernelArgs ka;
+  CombineArgs& a = ka.c;
   for (int t = 0; t < n_terms; ++t) a.terms[t] = terms_host[t];
   if (!a.terms[n_terms - 1].group_end) return NB_EINVAL;
   a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
   a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
   a.prior = prior; a.flux_model = flux_model; a.lnp = lnp;
+  ka.has_mv = mv ? 1 : 0;
+  ka.pars = pars;
+  if (mv) {
+    if (!lnp || !pars || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
+        !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->P < 1 || mv->W < W ||
+        mv->split < 0 || mv->split > 1 || mv->nb < 0 ||
+        (mv->nb > 0 && (!mv->blobs || !flux_model || mv->nb != N_E)))
+      return NB_EINVAL;
+    ka.mv = *mv;
+  }
+  if (W == 0) return 0;
   size_t smem = (size_t)COMBINE_WARPS * N_E * sizeof(double);
   if (smem > 48 * 1024) return NB_ETOOLARGE;
   combine_lnprob_kernel<<<(W + COMBINE_WARPS - 1) / COMBINE_WARPS, COMBINE_WARPS * 32, smem,
-                          as_stream(stream)>>>(a);
+                          as_stream(stream)>>>(ka);
   NB_CHECK_LAUNCH();
   return 0;
+}
+
+int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
+                      const double* unit_fac, const double* data_flux, const double* err_lo,
+                      const double* err_hi, const int* ul, const double* cl, const double* prior,
+                      double* flux_model, double* lnp, void* stream) {
+  return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
+                        err_lo, err_hi, ul, cl, prior, flux_model, lnp, stream);
+}
+
+int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
+                             const nb_term* terms_host, int n_terms, int W, int N_E,
+                             const double* unit_fac, const double* data_flux,
+                             const double* err_lo, const double* err_hi, const int* ul,
+                             const double* cl, const double* prior, double* flux_model,
+                             double* lnp, void* stream) {
+  if (!mv_host) return NB_EINVAL;
+  return launch_combine(mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux, err_lo,
+                        err_hi, ul, cl, prior, flux_model, lnp, stream);
 }
 
 int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
@@ -1142,13 +1253,23 @@ static int fill_param_map(ParamMapArgs& a, const double* pars, int W, int P,
   return 0;
 }
 
-int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
-                   double* pm, const nb_prior* priors_host, int n_priors, double* prior_out,
-                   const nb_prep_job* jobs_host, int n_jobs, void* stream) {
+static int launch_walker_prep(const nb_stretch* mv, double* pars_out, const double* pars, int W,
+                              int P, const nb_parmap* map_host, int n_map, double* pm,
+                              const nb_prior* priors_host, int n_priors, double* prior_out,
+                              const nb_prep_job* jobs_host, int n_jobs, void* stream) {
   WalkerPrepArgs a;
   int rc = fill_param_map(a.pm, pars, W, P, map_host, n_map, pm, priors_host, n_priors,
                           prior_out);
   if (rc) return rc;
+  a.has_mv = mv ? 1 : 0;
+  a.pars_out = pars_out;
+  if (mv) {
+    if (!mv->coords || !mv->step || !mv->s_idx || !mv->c_idx || !mv->zz || mv->P != P ||
+        mv->Ns != W || mv->split < 0 || mv->split > 1 || !pars_out)
+      return NB_EINVAL;
+    if (P > NB_MAX_MOVE_PAR) return NB_ETOOLARGE;
+    a.mv = *mv;
+  }
   if (n_jobs < 0 || n_jobs > NB_MAX_PREP_JOBS || (n_jobs > 0 && (!jobs_host || !pm)))
     return NB_EINVAL;
   for (int k = 0; k < n_jobs; ++k) {
@@ -1175,10 +1296,9 @@ int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, 
     }
   }
   if (W == 0) return 0;
-  if (W > 65535 * 32) return NB_ETOOLARGE;
   size_t smem = (size_t)max_energy_N * sizeof(double);
   if (smem > 200 * 1024) return NB_ETOOLARGE;
-  if (smem > 40 * 1024) {
+  if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(walker_prep_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1187,6 +1307,22 @@ int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, 
   walker_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
   NB_CHECK_LAUNCH();
   return 0;
+}
+
+int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
+                   double* pm, const nb_prior* priors_host, int n_priors, double* prior_out,
+                   const nb_prep_job* jobs_host, int n_jobs, void* stream) {
+  return launch_walker_prep(nullptr, nullptr, pars, W, P, map_host, n_map, pm, priors_host,
+                            n_priors, prior_out, jobs_host, n_jobs, stream);
+}
+
+int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
+                        const nb_parmap* map_host, int n_map, double* pm,
+                        const nb_prior* priors_host, int n_priors, double* prior_out,
+                        const nb_prep_job* jobs_host, int n_jobs, void* stream) {
+  if (!mv_host) return NB_EINVAL;
+  return launch_walker_prep(mv_host, pars, pars, W, P, map_host, n_map, pm, priors_host,
+                            n_priors, prior_out, jobs_host, n_jobs, stream);
 }
 
 int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch,

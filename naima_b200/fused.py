@@ -528,13 +528,22 @@ class LikelihoodPlan:
             walk(s)
         return out
 
-    def _enqueue(self, ex):
-        """The launch sequence of one likelihood evaluation of ex.W walkers."""
+    def _enqueue(self, ex, mv=None):
+        """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
+        (an nb_stretch describing a device-resident ensemble) the parameters are the
+        stretch-move proposals of the active half, computed by the set-up kernel, and the
+        combine kernel also accepts/rejects them and appends the chain."""
         L, st, W = lib(), eng.stream(), ex.W
         n = 0
-        check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map, eng.ptr(ex.pm),
-                               ex.pri, ex.n_pri, eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st),
-              "nb_walker_prep")
+        if mv is None:
+            check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map,
+                                   eng.ptr(ex.pm), ex.pri, ex.n_pri, eng.ptr(ex.prior),
+                                   ex.jobs, ex.n_jobs, st), "nb_walker_prep")
+        else:
+            check(L.nb_walker_prep_move(ctypes.byref(mv), eng.ptr(ex.pars), W, self.P, ex.map,
+                                        ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
+                                        eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st),
+                  "nb_walker_prep_move")
         n += 1
         def launch(c, out):
             p = ex.preps[c["prep"]]
@@ -565,7 +574,8 @@ class LikelihoodPlan:
             main.wait_event(done)
         n += len(comps)
         eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.flux, data=self.ddata,
-                    prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp)
+                    prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
+                    mv=mv, pars_d=ex.pars)
         n += 1
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
             if spec["kind"] != "pdist":

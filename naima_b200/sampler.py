@@ -342,10 +342,11 @@ class DeviceEnsemble:
         self.blobs = eng.zeros(self.W, max(self.nb, 1))
         self.n_acc = eng.zeros(self.W, dtype=torch.int32)
         self.step = eng.zeros(1, dtype=torch.int32)
+        self.sync = eng.zeros(1, dtype=torch.int32)
         self.use_graph = use_graph
         self._graph = None
         self._block = 0
-        self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 2) + 1
+        self.kernel_launches_per_step = 2 * plan.launches_per_eval
 
     def set_state(self, coords):
         """Upload positions and evaluate their log-probability (one batched call)."""
@@ -399,22 +400,26 @@ class DeviceEnsemble:
         self.chain_blobs = eng.zeros(n, W, self.nb) if self.nb else None
         self._graph = None
 
-    def _enqueue_step(self):
-        from . import engine as eng
-        from ._lib import check, lib
+    def _stretch(self, split):
+        """nb_stretch descriptor of the active half `split` over the current buffers."""
+        from ._lib import nb_stretch
 
-        L, ptr, ex = lib(), eng.ptr, self.ex
+        mv = nb_stretch()
+        for name, t in (("coords", self.coords), ("lp", self.lp),
+                        ("blobs", self.blobs if self.nb else None), ("step", self.step),
+                        ("sync", self.sync), ("s_idx", self.s_idx), ("c_idx", self.c_idx),
+                        ("zz", self.zz), ("lnu", self.lnu), ("n_accepted", self.n_acc),
+                        ("chain", self.chain), ("chain_lp", self.chain_lp),
+                        ("chain_blobs", self.chain_blobs if self.nb else None)):
+            setattr(mv, name, t.data_ptr() if t is not None else None)
+        mv.nb, mv.W, mv.P, mv.Ns, mv.split = self.nb, self.W, self.P, self.Ns, split
+        return mv
+
+    def _enqueue_step(self):
+        """One ensemble step: per half, set-up (+ proposal) -> components -> combine
+        (+ accept + chain append)."""
         for split in range(2):
-            check(L.nb_stretch_move(ptr(self.coords), self.P, self.Ns, split, ptr(self.step),
-                                    ptr(self.s_idx), ptr(self.c_idx), ptr(self.zz), ptr(ex.pars),
-                                    eng.stream()), "nb_stretch_move")
-            self.plan._enqueue(ex)
-            check(L.nb_stretch_update(
-                ptr(self.coords), ptr(self.lp), ptr(self.blobs) if self.nb else None, self.nb,
-                self.W, self.P, self.Ns, split, ptr(self.step), ptr(self.s_idx), ptr(self.zz),
-                ptr(self.lnu), ptr(ex.pars), ptr(ex.lnp), ptr(ex.flux) if self.nb else None,
-                ptr(self.n_acc), ptr(self.chain), ptr(self.chain_lp),
-                ptr(self.chain_blobs) if self.nb else None, eng.stream()), "nb_stretch_update")
+            self.plan._enqueue(self.ex, mv=self._stretch(split))
 
     def load_draws(self, nsteps):
         """Draw and upload the random numbers of the next `nsteps` steps."""
