@@ -294,34 +294,60 @@ def run_native(args):
     assert np.all(np.isfinite(lp_final[np.isfinite(lp_final)])) and not np.any(np.isnan(lp_final))
 
     # ---- end-to-end loop through the public API -----------------------------------
+    # naima_b200.PlanSampler is what get_sampler()/run_sampler() build for a traceable
+    # model: the EnsembleSampler API over the device-resident loop.  Every step's random
+    # draws go host->device from pinned memory and its chain row, log-probabilities and
+    # blob records (model flux + We) come back device->host; the host consumes one State
+    # per step.  L2 is flushed before every step here too (inside the wall-clock region,
+    # so `value` below is conservative; `value_excl_flush` subtracts the flushes' device time).
+    flush_ev = []
+
+    def e2e_flush():
+        if args.no_flush:
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        flush_buf.zero_()
+        b.record()
+        flush_ev.append((a, b))
+
     if world == 1:
-        sampler = nb.EnsembleSampler(W, 4, PlanLogProb(plan), vectorize=True, seed=wl.SEED)
+        sampler = nb.PlanSampler(W, 4, plan, seed=wl.SEED)
+        sampler._device().before_step = e2e_flush
+        h2d_step, d2h_step = sampler._device().io_bytes_per_step()
+        api = ("naima_b200.PlanSampler.sample (the sampler get_sampler()/run_sampler() build "
+               "for a traced model; one State per step on the host)")
     else:
         sampler = parallel.ShardedSampler(W, 4, plan, seed=wl.SEED)
+        h2d, d2h = plan.io_bytes((W // world) // 2)
+        h2d_step, d2h_step = 2 * h2d * world, 2 * d2h * world
+        api = "naima_b200.parallel.ShardedSampler.sample over a traced LikelihoodPlan"
     state = sampler.run_mcmc(p0, args.warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_t = 0.0
+    del flush_ev[:]
     gen = sampler.sample(state, iterations=args.steps, store=True)
+    t0 = time.perf_counter()
     for k in range(args.steps):
-        flush()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        if world > 1:
+            flush()
         next(gen)
-        torch.cuda.synchronize()
-        e2e_t += time.perf_counter() - t0
+    torch.cuda.synchronize()
+    e2e_t = time.perf_counter() - t0
+    gen.close()
+    torch.cuda.synchronize()
+    flush_s = 1e-3 * sum(a.elapsed_time(b) for a, b in flush_ev[:args.steps])
     if world > 1:
         t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
     clk = clocks.stop()
     e2e_value = W * args.steps / e2e_t
-    h2d, d2h = plan.io_bytes((W // world) // 2)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * h2d * world,
-           "d2h_bytes_per_step": 2 * d2h * world, "ms_per_step": 1e3 * e2e_t / args.steps,
-           "api": "naima_b200.EnsembleSampler.sample over a traced LikelihoodPlan "
-                  "(what run_sampler drives)"}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
+           "d2h_bytes_per_step": int(d2h_step), "ms_per_step": 1e3 * e2e_t / args.steps,
+           "value_excl_flush": W * args.steps / max(e2e_t - flush_s, 1e-9),
+           "flush_ms_per_step": 1e3 * flush_s / args.steps, "api": api}
     if rank != 0:
         return
 

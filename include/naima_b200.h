@@ -74,6 +74,9 @@ int nb_trapz_loglog(const double* y, int R, int N, int ld, const double* x, int 
  * out[w][i] = PD.eval(e[i], params[w])                     models.py:87-335 */
 int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
                   double* out, void* stream);
+/* same with an output row pitch out_ld >= N (rows inside a wider per-walker record) */
+int nb_pdist_eval_ld(int kind, const double* pd_params, int W, const double* e_eV, int N,
+                     double* out, int out_ld, void* stream);
 
 /* Per-walker integration operands on a particle grid x[N]
  * (BaseElectron._gam/_nelec radiative.py:147-160, BaseProton._Ep/_J :1002-1015):
@@ -178,7 +181,8 @@ typedef struct nb_term {
   double div;           /* 4 pi d^2, or 1 */
 } nb_term;
 
-/* flux_model[W][N_E] (may be NULL) receives the model in data units;
+/* flux_model[W][flux_ld] (may be NULL; flux_ld >= N_E is the row pitch, 0 = N_E) receives
+ * the model in data units in its first N_E columns;
  * lnp[W] (may be NULL) receives lnprob:
  *   sum_{!ul} -(m-f)^2 / (2 s^2), s = err_hi if m > f else err_lo,
  *   + n_viol * ln(1 - cl[n_viol]) when the table has upper limits,
@@ -187,7 +191,8 @@ typedef struct nb_term {
 int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
                       const double* unit_fac, const double* data_flux, const double* err_lo,
                       const double* err_hi, const int* ul, const double* cl,
-                      const double* prior, double* flux_model, double* lnp, void* stream);
+                      const double* prior, double* flux_model, int flux_ld, double* lnp,
+                      void* stream);
 
 /* --- parameter map + priors ------------------------------------------------
  * What the user's model(pars, data) / lnprior(pars) callbacks do on the host in
@@ -248,7 +253,8 @@ typedef struct nb_prep_job {
   int wpitch;
   int pad_;
   double x_to_energy;
-  double* energy_out;   /* [W] or NULL */
+  double* energy_out;   /* element w at energy_out[w * energy_stride], or NULL */
+  long long energy_stride; /* 0 = 1 */
 } nb_prep_job;
 int nb_walker_prep(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
                    double* pm, const nb_prior* priors_host, int n_priors, double* prior_out,
@@ -324,14 +330,17 @@ int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
                         const nb_parmap* map_host, int n_map, double* pm,
                         const nb_prior* priors_host, int n_priors, double* prior_out,
                         const nb_prep_job* jobs_host, int n_jobs, void* stream);
-/* flux_model (the blob rows, [Ns][N_E] with N_E == mv.nb when mv.nb > 0) and lnp are
- * required; `pars` holds the proposals published by nb_walker_prep_move. */
+/* lnp is required; when mv.nb > 0 so is flux_model, whose rows [Ns][flux_ld] are the
+ * per-walker blob records (model flux in the first N_E columns, further blobs written
+ * there by earlier kernels): the first mv.nb columns (N_E <= mv.nb <= flux_ld) of an
+ * accepted proposal's row replace the walker's blob record.  `pars` holds the
+ * proposals published by nb_walker_prep_move. */
 int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
                              const nb_term* terms_host, int n_terms, int W, int N_E,
                              const double* unit_fac, const double* data_flux,
                              const double* err_lo, const double* err_hi, const int* ul,
                              const double* cl, const double* prior, double* flux_model,
-                             double* lnp, void* stream);
+                             int flux_ld, double* lnp, void* stream);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

@@ -12,7 +12,7 @@ from . import models  # noqa: F401
 from .core import (get_sampler, lnprob, lnprobmodel, log_uniform_prior, normal_prior,  # noqa: F401
                    run_sampler, uniform_prior)
 from .fused import LikelihoodPlan, TraceError  # noqa: F401
-from .sampler import DeviceEnsemble, EnsembleSampler, State  # noqa: F401
+from .sampler import DeviceEnsemble, EnsembleSampler, PlanSampler, State  # noqa: F401
 from .utils import (DataTable, build_data_table, generate_energy_edges, read_ipac,  # noqa: F401
                     sed_conversion, trapz_loglog, validate_data_table)
 

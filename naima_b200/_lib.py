@@ -39,7 +39,7 @@ class nb_prep_job(ctypes.Structure):
     _fields_ = [("kind", c_int), ("N", c_int), ("pd_off", c_ll), ("x", vp), ("invdlx", vp),
                 ("e_mul1", c_dbl), ("e_mul2", c_dbl), ("n_scale", c_dbl), ("xn", vp),
                 ("ds1", vp), ("nraw", vp), ("wpitch", c_int), ("pad_", c_int),
-                ("x_to_energy", c_dbl), ("energy_out", vp)]
+                ("x_to_energy", c_dbl), ("energy_out", vp), ("energy_stride", c_ll)]
 
 
 class nb_stretch(ctypes.Structure):
@@ -53,6 +53,7 @@ class nb_stretch(ctypes.Structure):
 PROTOTYPES = {
     "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
     "nb_pdist_eval": [c_int, vp, c_int, vp, c_int, vp, vp],
+    "nb_pdist_eval_ld": [c_int, vp, c_int, vp, c_int, vp, c_int, vp],
     "nb_pd_prep": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, vp, vp, vp, c_int, vp],
     "nb_pd_prep_ex": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, vp, vp, vp, vp, c_int, vp],
     "nb_particle_energy": [c_int, vp, c_int, vp, c_int, c_dbl, c_dbl, c_dbl, c_dbl, vp, vp],
@@ -68,7 +69,7 @@ PROTOTYPES = {
                     c_int, vp],
     "nb_synchrotron": [vp, c_int, vp, vp, c_int, vp, vp, vp, c_int, vp, c_int, vp, vp],
     "nb_combine_lnprob": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp, vp,
-                          vp, vp, vp, vp],
+                          vp, vp, c_int, vp, vp],
     "nb_param_map": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
                      ctypes.POINTER(nb_prior), c_int, vp, vp],
     "nb_walker_prep": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
@@ -77,7 +78,7 @@ PROTOTYPES = {
                             ctypes.POINTER(nb_parmap), c_int, vp, ctypes.POINTER(nb_prior),
                             c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
     "nb_combine_lnprob_update": [ctypes.POINTER(nb_stretch), vp, ctypes.POINTER(nb_term), c_int,
-                                 c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+                                 c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

@@ -26,7 +26,7 @@ from . import engine as eng
 from . import units as u
 from .fused import (PRIOR_LOGUNIFORM, PRIOR_NORMAL, PRIOR_UNIFORM, LikelihoodPlan, SymPrior,
                     TraceError, is_sym)
-from .sampler import BlobBatch, EnsembleSampler, State
+from .sampler import BlobBatch, EnsembleSampler, PlanSampler, State
 from .units import Quantity
 from .utils import sed_conversion, validate_data_table
 
@@ -328,8 +328,8 @@ def get_sampler(data_table=None, p0=None, model=None, prior=None, nwalkers=500, 
         except TraceError as e:
             log.info("model/prior callbacks are not traceable (%s); using batched callbacks", e)
     if plan is not None:
-        sampler = EnsembleSampler(nwalkers, len(p0), PlanLogProb(plan), vectorize=True,
-                                  blobs_dtype=np.dtype(object), seed=seed)
+        # device-resident stepping behind the EnsembleSampler API
+        sampler = PlanSampler(nwalkers, len(p0), plan, blobs_dtype=np.dtype(object), seed=seed)
     elif vectorize:
         sampler = EnsembleSampler(nwalkers, len(p0), BatchedLogProb(data, model, prior),
                                   vectorize=True, blobs_dtype=np.dtype(object), seed=seed)

@@ -38,14 +38,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // particle distribution kernels
 // ---------------------------------------------------------------------------
 __global__ void pdist_eval_kernel(int kind, const double* __restrict__ params, int W,
-                                  const double* __restrict__ e, int N, double* __restrict__ out) {
+                                  const double* __restrict__ e, int N, double* __restrict__ out,
+                                  int out_ld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int w = blockIdx.y;
   if (i >= N || w >= W) return;
   double p[PD_MAXPAR];
 #pragma unroll
   for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
-  out[(size_t)w * N + i] = pd_eval(kind, p, e[i]);
+  out[(size_t)w * out_ld + i] = pd_eval(kind, p, e[i]);
 }
 
 // One chunk of 256 nodes of one walker: n on the grid, x*n and the logarithmic slope
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
           ehi = a.err_hi[e];
         }
         double m = combine_model(a, w, e);
-        if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+        if (a.flux_model) a.flux_model[(size_t)w * a.flux_ld + e] = m;
         if (a.lnp) {
           if (ule) {
             ++nul;
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         }
         if (mv.nb > 0) {
           for (int d = lane; d < mv.nb; d += 32) {
-            double v = acc ? a.flux_model[(size_t)w * a.N_E + d]
+            double v = acc ? a.flux_model[(size_t)w * a.flux_ld + d]
                            : mv.blobs[(size_t)sidx * mv.nb + d];
             if (acc) mv.blobs[(size_t)sidx * mv.nb + d] = v;
             if (mv.chain_blobs) mv.chain_blobs[((size_t)t_step * W_ + sidx) * mv.nb + d] = v;
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
       if (tid < s2) s_red[tid] += s_red[tid + s2];
       __syncthreads();
     }
-    if (tid == 0) J.energy_out[w] = s_red[0];
+    if (tid == 0) J.energy_out[(size_t)w * (J.energy_stride > 0 ? J.energy_stride : 1)] = s_red[0];
   }
 }
 
@@ -907,15 +908,22 @@ int nb_contract_smem_bytes(int N, int rows_per_tile) {
   return b > 227 * 1024 ? 0 : (int)b;
 }
 
-int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
-                  double* out, void* stream) {
-  if (!pd_params || !e_eV || !out || W < 0 || N < 0 || kind < 0 || kind > NB_PD_LOGPAR)
+int nb_pdist_eval_ld(int kind, const double* pd_params, int W, const double* e_eV, int N,
+                     double* out, int out_ld, void* stream) {
+  if (!pd_params || !e_eV || !out || W < 0 || N < 0 || kind < 0 || kind > NB_PD_LOGPAR ||
+      out_ld < N)
     return NB_EINVAL;
   if (W == 0 || N == 0) return 0;
   dim3 grid((N + 255) / 256, W);
-  pdist_eval_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, e_eV, N, out);
+  pdist_eval_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, e_eV, N, out,
+                                                         out_ld);
   NB_CHECK_LAUNCH();
   return 0;
+}
+
+int nb_pdist_eval(int kind, const double* pd_params, int W, const double* e_eV, int N,
+                  double* out, void* stream) {
+  return nb_pdist_eval_ld(kind, pd_params, W, e_eV, N, out, N, stream);
 }
 
 // nraw is an extension used by the exact contraction: n[w][j] itself
@@ -1127,9 +1135,11 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
                           int n_terms, int W, int N_E, const double* unit_fac,
                           const double* data_flux, const double* err_lo, const double* err_hi,
                           const int* ul, const double* cl, const double* prior,
-                          double* flux_model, double* lnp, void* stream) {
+                          double* flux_model, int flux_ld, double* lnp, void* stream) {
   if (!terms_host || n_terms < 1 || n_terms > NB_MAX_TERMS || W < 0 || N_E < 1 || !unit_fac)
     return NB_EINVAL;
+  if (flux_ld == 0) flux_ld = N_E;
+  if (flux_ld < N_E) return NB_EINVAL;
   if (lnp && (!data_flux || !err_lo || !err_hi || !ul || !cl)) return NB_EINVAL;
   if (!lnp && !flux_model) return NB_EINVAL;
   CombineKernelArgs ka;
@@ -1138,14 +1148,14 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
   if (!a.terms[n_terms - 1].group_end) return NB_EINVAL;
   a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
   a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
-  a.prior = prior; a.flux_model = flux_model; a.lnp = lnp;
+  a.prior = prior; a.flux_model = flux_model; a.flux_ld = flux_ld; a.lnp = lnp;
   ka.has_mv = mv ? 1 : 0;
   ka.pars = pars;
   if (mv) {
     if (!lnp || !pars || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
         !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->P < 1 || mv->W < W ||
         mv->split < 0 || mv->split > 1 || mv->nb < 0 ||
-        (mv->nb > 0 && (!mv->blobs || !flux_model || mv->nb != N_E)))
+        (mv->nb > 0 && (!mv->blobs || !flux_model || mv->nb < N_E || mv->nb > flux_ld)))
       return NB_EINVAL;
     ka.mv = *mv;
   }
@@ -1161,9 +1171,9 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
 int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
                       const double* unit_fac, const double* data_flux, const double* err_lo,
                       const double* err_hi, const int* ul, const double* cl, const double* prior,
-                      double* flux_model, double* lnp, void* stream) {
+                      double* flux_model, int flux_ld, double* lnp, void* stream) {
   return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
-                        err_lo, err_hi, ul, cl, prior, flux_model, lnp, stream);
+                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, stream);
 }
 
 int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
@@ -1171,10 +1181,10 @@ int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
                              const double* unit_fac, const double* data_flux,
                              const double* err_lo, const double* err_hi, const int* ul,
                              const double* cl, const double* prior, double* flux_model,
-                             double* lnp, void* stream) {
+                             int flux_ld, double* lnp, void* stream) {
   if (!mv_host) return NB_EINVAL;
   return launch_combine(mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux, err_lo,
-                        err_hi, ul, cl, prior, flux_model, lnp, stream);
+                        err_hi, ul, cl, prior, flux_model, flux_ld, lnp, stream);
 }
 
 int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,

@@ -771,6 +771,7 @@ struct CombineArgs {
   const double* cl;
   const double* prior;
   double* flux_model;
+  int flux_ld;  // row pitch of flux_model (>= N_E)
   double* lnp;
 };
 
@@ -837,13 +838,13 @@ NB_HD double lnprob_finish(const CombineArgs& a, int w, double gauss_sum, int nu
 // serial form (one walker): host emulation and the reference for the warp kernel
 NB_HD void combine_lnprob_walker(const CombineArgs& a, int w) {
   if (!a.lnp) {
-    for (int e = 0; e < a.N_E; ++e) a.flux_model[(size_t)w * a.N_E + e] = combine_model(a, w, e);
+    for (int e = 0; e < a.N_E; ++e) a.flux_model[(size_t)w * a.flux_ld + e] = combine_model(a, w, e);
     return;
   }
   int n = 0, nviol = 0, nul = 0;
   for (int e = 0; e < a.N_E; ++e) {
     double m = combine_model(a, w, e);
-    if (a.flux_model) a.flux_model[(size_t)w * a.N_E + e] = m;
+    if (a.flux_model) a.flux_model[(size_t)w * a.flux_ld + e] = m;
     if (a.ul[e]) {
       ++nul;
       if (m > a.data_flux[e]) ++nviol;

@@ -379,6 +379,14 @@ class LikelihoodPlan:
         self.blob_specs = []
         for b in self.blobs:
             self.blob_specs.append(self._blob_spec(b, pd_index))
+        # columns of the per-walker record: model flux first, then the device-side blobs
+        self.blob_cols = []
+        off = self.N_E
+        for spec in self._flat_blob_specs():
+            width = 1 if spec["kind"] == "W" else int(spec["e_eV"].size)
+            self.blob_cols.append((off, width))
+            off += width
+        self.row_width = off
 
     def _blob_spec(self, b, pd_index):
         if isinstance(b, SymBlob):
@@ -460,15 +468,17 @@ class LikelihoodPlan:
                                   scalar_col(sc) if sc is not None else None))
             ex.outs.append(out)
         ex.terms = eng.make_terms(terms)
-        ex.flux = eng.zeros(W, self.N_E)
+        # one record per walker: [model flux (N_E) | further blobs], so that a sampler
+        # moves a walker's blobs with one row copy (row pitch = self.row_width)
+        ex.row = eng.zeros(W, self.row_width)
+        ex.flux = ex.row[:, :self.N_E]
         ex.lnp = eng.zeros(W)
         ex.E_erg = eng.to_dev(self.E_eV * eng.eV_erg)
         ex.blob_bufs = []
-        for spec in self._flat_blob_specs():
-            if spec["kind"] == "W":
-                ex.blob_bufs.append(eng.zeros(W))
-            elif spec["kind"] == "pdist":
-                ex.blob_bufs.append(eng.zeros(W, spec["e_eV"].size))
+        for spec, (off, width) in zip(self._flat_blob_specs(), self.blob_cols):
+            ex.blob_bufs.append(ex.row[:, off] if spec["kind"] == "W"
+                                else ex.row[:, off:off + width])
+            if spec["kind"] == "pdist":
                 spec["e_d"] = eng.to_dev(spec["e_eV"])
         # jobs of the fused per-walker set-up kernel
         jobs = []
@@ -484,7 +494,8 @@ class LikelihoodPlan:
                 jobs.append(dict(kind=PD_KIND[self.pds[spec["pd"]][0]._kind], N=g.N,
                                  pd_off=spec["pd"] * W * NB_PD_MAXPAR, x=g.x_d,
                                  e_mul1=g.e_mul1, e_mul2=g.e_mul2, n_scale=g.n_scale,
-                                 x_to_energy=g.x_to_erg, energy_out=buf))
+                                 x_to_energy=g.x_to_erg, energy_out=buf,
+                                 energy_stride=self.row_width))
         if len(jobs) > 8:
             raise TraceError("too many particle-distribution jobs in one plan")
         ex.jobs = (nb_prep_job * max(len(jobs), 1))()
@@ -496,9 +507,7 @@ class LikelihoodPlan:
         # pinned staging for the host-facing call
         ex.pars_pin = torch.empty(W, P, dtype=torch.float64).pin_memory()
         ex.lnp_pin = torch.empty(W, dtype=torch.float64).pin_memory()
-        ex.flux_pin = torch.empty(W, self.N_E, dtype=torch.float64).pin_memory()
-        ex.blob_pins = [torch.empty(b.shape, dtype=torch.float64).pin_memory()
-                        for b in ex.blob_bufs]
+        ex.row_pin = torch.empty(W, self.row_width, dtype=torch.float64).pin_memory()
         ex.pd_block, ex.scalar_col = pd_block, scalar_col
         ex.graph = None
         # warm-up launch outside capture (function attributes, lazy module load)
@@ -573,18 +582,19 @@ class LikelihoodPlan:
         for done in joins:
             main.wait_event(done)
         n += len(comps)
-        eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.flux, data=self.ddata,
-                    prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
-                    mv=mv, pars_d=ex.pars)
-        n += 1
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
             if spec["kind"] != "pdist":
                 continue  # particle energies are jobs of nb_walker_prep
             pdobj = self.pds[spec["pd"]][0]
-            check(L.nb_pdist_eval(PD_KIND[pdobj._kind], eng.ptr(ex.pd_block(spec["pd"])), W,
-                                  eng.ptr(spec["e_d"]), spec["e_eV"].size, eng.ptr(buf), st),
-                  "nb_pdist_eval")
+            check(L.nb_pdist_eval_ld(PD_KIND[pdobj._kind], eng.ptr(ex.pd_block(spec["pd"])), W,
+                                     eng.ptr(spec["e_d"]), spec["e_eV"].size, eng.ptr(buf),
+                                     self.row_width, st), "nb_pdist_eval_ld")
             n += 1
+        # last: with `mv` the combine kernel also moves the accepted walkers' records
+        eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
+                    prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
+                    mv=mv, pars_d=ex.pars, flux_ld=self.row_width)
+        n += 1
         self.launches_per_eval = n
         return n
 
@@ -614,21 +624,38 @@ class LikelihoodPlan:
         self.run(ex)
         ex.lnp_pin.copy_(ex.lnp, non_blocking=True)
         if want_blobs:
-            ex.flux_pin.copy_(ex.flux, non_blocking=True)
-            for pin, buf in zip(ex.blob_pins, ex.blob_bufs):
-                pin.copy_(buf, non_blocking=True)
+            ex.row_pin.copy_(ex.row, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         lnp = ex.lnp_pin.numpy().copy()
         if not want_blobs:
             return lnp, None, None
-        return lnp, ex.flux_pin.numpy().copy(), [p.numpy().copy() for p in ex.blob_pins]
+        flux, blob_arrays = self.split_rows(ex.row_pin.numpy().copy())
+        return lnp, flux, blob_arrays
+
+    def eval_rows(self, pars):
+        """pars: host array [W][P] -> (lnp[W], per-walker records [W][row_width])."""
+        pars = np.ascontiguousarray(pars, dtype=float)
+        ex = self.executable(pars.shape[0])
+        ex.pars_pin.numpy()[...] = pars
+        ex.pars.copy_(ex.pars_pin, non_blocking=True)
+        self.run(ex)
+        ex.lnp_pin.copy_(ex.lnp, non_blocking=True)
+        ex.row_pin.copy_(ex.row, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return ex.lnp_pin.numpy().copy(), ex.row_pin.numpy().copy()
+
+    def split_rows(self, rows):
+        """Per-walker records [..., row_width] -> (flux [..., N_E], [blob arrays])."""
+        out = []
+        for spec, (off, width) in zip(self._flat_blob_specs(), self.blob_cols):
+            out.append(rows[..., off] if spec["kind"] == "W" else rows[..., off:off + width])
+        return rows[..., :self.N_E], out
 
     def io_bytes(self, W, want_blobs=True):
         """(host->device, device->host) bytes of one host-facing evaluation."""
-        ex = self.executable(W)
         d2h = 8 * W
         if want_blobs:
-            d2h += 8 * W * self.N_E + sum(8 * b.numel() for b in ex.blob_bufs)
+            d2h += 8 * W * self.row_width
         return 8 * W * self.P, d2h
 
     # -- blob reconstruction -----------------------------------------------------------

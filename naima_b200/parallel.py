@@ -135,8 +135,8 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         if per * self.world != W:
             raise ValueError("walkers must divide evenly over ranks")
         lo, hi = bounds[self.rank]
-        lnp, flux, _ = self.plan(coords[lo:hi])
-        pack = np.concatenate([lnp[:, None], flux], axis=1)
+        lnp, rows = self.plan.eval_rows(coords[lo:hi])
+        pack = np.concatenate([lnp[:, None], rows], axis=1)
         if self.world > 1:
             dist = _dist()
             local = eng.to_dev(pack)
@@ -166,7 +166,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             if self.world > 1:
                 self.pack_local[:, 0].copy_(ex.lnp)
                 if self.nb:
-                    self.pack_local[:, 1:].copy_(ex.flux)
+                    self.pack_local[:, 1:].copy_(ex.row)
                 _dist().all_gather_into_tensor(self.pack_full, self.pack_local, group=self.group)
                 self.collectives += 1
                 self.lnp_full.copy_(self.pack_full[:, 0])
@@ -174,7 +174,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
                     self.flux_full.copy_(self.pack_full[:, 1:])
                 new_lp, new_bl = self.lnp_full, self.flux_full
             else:
-                new_lp, new_bl = ex.lnp, ex.flux
+                new_lp, new_bl = ex.lnp, ex.row
             check(L.nb_stretch_update(
                 ptr(self.coords), ptr(self.lp), ptr(self.blobs) if self.nb else None, self.nb,
                 self.W, self.P, self.Ns, split, ptr(self.step), ptr(self.s_idx), ptr(self.zz),

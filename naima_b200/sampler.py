@@ -22,7 +22,7 @@ Two execution modes:
 """
 import numpy as np
 
-__all__ = ["EnsembleSampler", "State", "DeviceEnsemble"]
+__all__ = ["EnsembleSampler", "State", "DeviceEnsemble", "PlanSampler"]
 
 
 class State:
@@ -235,8 +235,9 @@ class EnsembleSampler:
             self._grow(int(iterations))
         all_inds = np.arange(self.nwalkers)
         for _ in range(int(iterations)):
-            # emcee draws the move with random.choice(moves, p=weights) every iteration
-            self._random.choice(1, p=[1.0])
+            # emcee draws the move with random.choice(moves, p=weights) every iteration,
+            # which consumes exactly one uniform of the stream
+            self._random.random_sample()
             inds = all_inds % 2
             self._random.shuffle(inds)
             for split in range(2):
@@ -334,7 +335,7 @@ class DeviceEnsemble:
                              "twice the number of dimensions.")
         self.plan, self.W, self.P, self.a = plan, int(nwalkers), plan.P, float(a)
         self.Ns = self.W // 2
-        self.nb = plan.N_E if store_blobs else 0
+        self.nb = plan.row_width if store_blobs else 0  # [model flux | further blobs]
         self._random = np.random.mtrand.RandomState(seed)
         self.ex = plan.executable(self.Ns)
         self.coords = eng.zeros(self.W, self.P)
@@ -343,23 +344,26 @@ class DeviceEnsemble:
         self.n_acc = eng.zeros(self.W, dtype=torch.int32)
         self.step = eng.zeros(1, dtype=torch.int32)
         self.sync = eng.zeros(1, dtype=torch.int32)
+        self.before_step = None
         self.use_graph = use_graph
         self._graph = None
         self._block = 0
         self.kernel_launches_per_step = 2 * plan.launches_per_eval
 
-    def set_state(self, coords):
-        """Upload positions and evaluate their log-probability (one batched call)."""
+    def set_state(self, coords, log_prob=None, rows=None):
+        """Upload positions; their log-probabilities and blob records are evaluated in
+        one batched call unless given."""
         from . import engine as eng
 
         coords = np.ascontiguousarray(coords, dtype=float)
-        lnp, flux, _ = self.plan(coords)
-        if np.any(np.isnan(lnp)):
+        if log_prob is None or (self.nb and rows is None):
+            log_prob, rows = self.plan.eval_rows(coords)
+        if np.any(np.isnan(log_prob)):
             raise ValueError("The initial log_prob was NaN")
         self.coords.copy_(eng.to_dev(coords))
-        self.lp.copy_(eng.to_dev(lnp))
+        self.lp.copy_(eng.to_dev(np.ascontiguousarray(log_prob, dtype=float)))
         if self.nb:
-            self.blobs.copy_(eng.to_dev(flux))
+            self.blobs.copy_(eng.to_dev(np.ascontiguousarray(rows, dtype=float)))
         self.n_acc.zero_()
 
     def _draw_block(self, n):
@@ -370,7 +374,8 @@ class DeviceEnsemble:
         lnu = np.empty((n, 2, Ns))
         all_inds = np.arange(W)
         for t in range(n):
-            self._random.choice(1, p=[1.0])
+            # emcee draws the move with random.choice(moves, p=weights): one uniform
+            self._random.random_sample()
             inds = all_inds % 2
             self._random.shuffle(inds)
             for split in range(2):
@@ -441,8 +446,8 @@ class DeviceEnsemble:
 
         if self.use_graph and self._graph is None:
             # warm-up outside capture, then rewind the step counter and state
-            c0, l0, b0, a0 = (self.coords.clone(), self.lp.clone(), self.blobs.clone(),
-                              self.n_acc.clone())
+            c0, l0, b0, a0, s0 = (self.coords.clone(), self.lp.clone(), self.blobs.clone(),
+                                  self.n_acc.clone(), self.step.clone())
             self._enqueue_step()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -457,16 +462,70 @@ class DeviceEnsemble:
             self.lp.copy_(l0)
             self.blobs.copy_(b0)
             self.n_acc.copy_(a0)
-            self.step.zero_()
+            self.step.copy_(s0)
         for _ in range(nsteps):
+            if self.before_step is not None:
+                self.before_step()  # measurement hook (bench.py flushes L2 here)
             if self._graph is not None:
                 self._graph.replay()
             else:
                 self._enqueue_step()
 
+    # -- pipelined execution for the host-facing sampler ------------------------------
+    def begin_chunk(self, n):
+        """Prepare buffers (device + pinned host mirrors) for a chunk of up to n steps and
+        rewind the step counter.  The caller must have consumed the previous chunk."""
+        import torch
+
+        first = self._block < n or not hasattr(self, "_pin")
+        self._alloc_block(n)
+        if first:
+            nn, W, Ns = self._block, self.W, self.Ns
+            pin = lambda *shape, dtype=torch.float64: torch.empty(*shape, dtype=dtype).pin_memory()
+            self._pin = dict(
+                s_idx=pin(nn, 2, Ns, dtype=torch.int32), c_idx=pin(nn, 2, Ns, dtype=torch.int32),
+                zz=pin(nn, 2, Ns), lnu=pin(nn, 2, Ns), chain=pin(nn, W, self.P),
+                lp=pin(nn, W), rows=pin(nn, W, max(self.nb, 1)))
+            self._pin_np = {k: v.numpy() for k, v in self._pin.items()}
+        self.step.zero_()
+
+    def enqueue_steps(self, t0, t1):
+        """Steps [t0, t1) of the current chunk: draw on the host, upload from pinned
+        memory, replay, read the chain rows back into pinned memory -- all asynchronous.
+        Returns (event, rng_states) with the generator state after each step."""
+        import torch
+
+        n = t1 - t0
+        states = []
+        pn = self._pin
+        for t in range(t0, t1):
+            s_idx, c_idx, zz, lnu = self._draw_block(1)
+            hp = self._pin_np
+            hp["s_idx"][t], hp["c_idx"][t], hp["zz"][t], hp["lnu"][t] = (s_idx[0], c_idx[0],
+                                                                         zz[0], lnu[0])
+            states.append(self._random.get_state())
+        for name, dev in (("s_idx", self.s_idx), ("c_idx", self.c_idx), ("zz", self.zz),
+                          ("lnu", self.lnu)):
+            dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
+        self.run_loaded(n)
+        pn["chain"][t0:t1].copy_(self.chain[t0:t1], non_blocking=True)
+        pn["lp"][t0:t1].copy_(self.chain_lp[t0:t1], non_blocking=True)
+        if self.nb:
+            pn["rows"][t0:t1].copy_(self.chain_blobs[t0:t1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev, states
+
+    def io_bytes_per_step(self):
+        """(host->device, device->host) bytes moved per ensemble step by enqueue_steps."""
+        h2d = 2 * self.Ns * (4 + 4 + 8 + 8)
+        d2h = 8 * self.W * (self.P + 1 + self.nb)
+        return h2d, d2h
+
     def run(self, nsteps):
         """Draw, upload, run and read back `nsteps` steps: returns (chain, log_prob,
-        blobs|None) as host arrays [nsteps, W, ...]."""
+        records|None) as host arrays [nsteps, W, ...]; plan.split_rows(records) gives
+        the model flux and the further blobs."""
         import torch
 
         self.load_draws(nsteps)
@@ -482,3 +541,117 @@ class DeviceEnsemble:
     @property
     def acceptance_counts(self):
         return self.n_acc.cpu().numpy()
+
+
+class PlanSampler(EnsembleSampler):
+    """The EnsembleSampler API (what naima's run_sampler drives, core.py:127-160) over the
+    device-resident stretch-move loop of a LikelihoodPlan.
+
+    Per ensemble step the host draws the random numbers with the same NumPy stream and
+    draw order as the host-driven sampler, uploads them from pinned memory, replays one
+    CUDA graph (2 x [set-up + proposal -> components -> combine + accept + chain append])
+    and reads the step's chain row, log-probabilities and blob records back.  Steps are
+    enqueued `block` at a time so that the host's drawing overlaps the device's stepping;
+    the chain is identical to the host-driven sampler's for the same seed."""
+
+    def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=16, chunk=256,
+                 blobs_dtype=None, **kwargs):
+        self.plan = plan
+        self.block, self.chunk = int(block), int(chunk)
+        self._de = None
+        super().__init__(nwalkers, ndim, self._log_prob, a=a, vectorize=True,
+                         blobs_dtype=blobs_dtype, seed=seed, **kwargs)
+
+    def _log_prob(self, p):
+        lnp, rows = self.plan.eval_rows(p)
+        flux, arrays = self.plan.split_rows(rows)
+        return lnp, BlobBatch(self.plan, flux, arrays)
+
+    def _device(self):
+        if self._de is None:
+            self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
+            self._de._random = self._random  # one stream, shared with the host-side API
+        return self._de
+
+    def sample(self, initial_state, log_prob0=None, rstate0=None, blobs0=None, iterations=1,
+               tune=False, skip_initial_state_check=False, thin_by=1, thin=None, store=True,
+               progress=False):
+        if self.nwalkers % 2 or self.nwalkers < 2 * self.ndim:
+            # odd ensembles / live_dangerously: the host-driven loop handles them
+            yield from super().sample(initial_state, log_prob0=log_prob0, rstate0=rstate0,
+                                      blobs0=blobs0, iterations=iterations,
+                                      skip_initial_state_check=skip_initial_state_check,
+                                      store=store)
+            return
+        state = State(initial_state, copy=True)
+        if np.shape(state.coords) != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions {0}".format(np.shape(state.coords)))
+        if not skip_initial_state_check and not walkers_independent(state.coords):
+            raise ValueError("Initial state has a large condition number. Make sure that your "
+                             "walkers are linearly independent for the best performance")
+        if np.any(~np.isfinite(state.coords)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        if rstate0 is not None:
+            self.random_state = rstate0
+        if log_prob0 is not None:
+            state.log_prob = np.asarray(log_prob0, dtype=float)
+        # the device loop needs the walkers' blob records: evaluate the ensemble once
+        lnp, rows = self.plan.eval_rows(state.coords)
+        if state.log_prob is None:
+            state.log_prob = lnp
+        if np.shape(state.log_prob) != (self.nwalkers,):
+            raise ValueError("incompatible input dimensions")
+        if np.any(np.isnan(state.log_prob)):
+            raise ValueError("The initial log_prob was NaN")
+        de = self._device()
+        de.set_state(state.coords, state.log_prob, rows)
+        iterations = int(iterations)
+        if store:
+            self._grow(iterations)
+        prev = state.coords
+        done = 0
+        while done < iterations:
+            nchunk = min(self.chunk, iterations - done)
+            de.begin_chunk(nchunk)
+            pending = []  # (t0, t1, event, rng_states), in flight on the device
+            t_enq = 0
+            t_out = 0
+            while t_out < nchunk:
+                while t_enq < nchunk and len(pending) < 2:
+                    t1 = min(t_enq + self.block, nchunk)
+                    ev, states = de.enqueue_steps(t_enq, t1)
+                    pending.append((t_enq, t1, ev, states))
+                    t_enq = t1
+                t0, t1, ev, states = pending.pop(0)
+                ev.synchronize()
+                pn = de._pin
+                chain = pn["chain"][t0:t1].numpy().copy()
+                lps = pn["lp"][t0:t1].numpy().copy()
+                recs = pn["rows"][t0:t1].numpy().copy() if de.nb else None
+                if np.any(np.isnan(lps)):
+                    raise ValueError("Probability function returned NaN")
+                for k in range(t1 - t0):
+                    coords = chain[k]
+                    self._accepted += np.any(coords != prev, axis=1)
+                    prev = coords
+                    blobs = None
+                    if recs is not None:
+                        flux, arrays = self.plan.split_rows(recs[k])
+                        blobs = BlobBatch(self.plan, flux, arrays)
+                    if store:
+                        self._chain[self.iteration] = coords
+                        self._log_prob[self.iteration] = lps[k]
+                        if blobs is not None:
+                            self._blobs.append(blobs)
+                    self.iteration += 1
+                    out = State(coords, log_prob=lps[k], blobs=blobs, random_state=states[k],
+                                copy=False)
+                    self._previous_state = out
+                    try:
+                        yield State(out, copy=True)
+                    except GeneratorExit:
+                        # the consumer stopped here: rewind the stream to this step
+                        self._random.set_state(states[k])
+                        raise
+                t_out = t1
+            done += nchunk

@@ -611,6 +611,29 @@ def test_sampler_chain_parity(nb):
     s.run_mcmc(None, 3)
     dchain2, _, _ = de.run(3)
     assert_allclose(dchain2, s.get_chain()[nsteps:], rtol=1e-13)
+    # the public-API sampler over the device loop (what get_sampler builds): same chain,
+    # same blobs, same acceptance counts, for block sizes that do / do not divide nsteps
+    for block in (4, 16):
+        ps = nb.PlanSampler(W, P, plan, seed=seed, block=block, chunk=5)
+        st = ps.run_mcmc(p0, nsteps)
+        assert_allclose(ps.get_chain(), s.get_chain()[:nsteps], rtol=1e-13)
+        assert_allclose(ps.get_log_prob(), s.get_log_prob()[:nsteps], rtol=1e-13)
+        assert_allclose(st.coords, s.get_chain()[nsteps - 1], rtol=1e-13)
+        bp, bs = ps.get_blobs()[-1, 5], s.get_blobs()[nsteps - 1, 5]
+        assert len(bp) == len(bs) == 2
+        assert_allclose(bp[0].value, bs[0].value, rtol=1e-13)
+        assert_allclose(bp[1].value, bs[1].value, rtol=1e-13)
+        ps.run_mcmc(None, 3)
+        assert_allclose(ps.get_chain()[nsteps:], s.get_chain()[nsteps:], rtol=1e-13)
+        assert np.array_equal(ps.acceptance_fraction, s.acceptance_fraction)
+    # stopping the generator early rewinds the random stream to the last yielded step
+    ps = nb.PlanSampler(W, P, plan, seed=seed, block=4)
+    gen = ps.sample(p0, iterations=nsteps)
+    for _ in range(2):
+        state = next(gen)
+    gen.close()
+    ps.run_mcmc(state, nsteps - 2)
+    assert_allclose(ps.get_chain()[:nsteps], s.get_chain()[:nsteps], rtol=1e-13)
 
 
 def test_get_sampler_run_sampler(nb):
