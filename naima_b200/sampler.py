@@ -335,6 +335,7 @@ class DeviceEnsemble:
                              "twice the number of dimensions.")
         self.plan, self.W, self.P, self.a = plan, int(nwalkers), plan.P, float(a)
         self.Ns = self.W // 2
+        self._all_inds = np.arange(self.W)
         self.nb = plan.row_width if store_blobs else 0  # [model flux | further blobs]
         self._random = np.random.mtrand.RandomState(seed)
         self.ex = plan.executable(self.Ns)
@@ -345,6 +346,7 @@ class DeviceEnsemble:
         self.step = eng.zeros(1, dtype=torch.int32)
         self.sync = eng.zeros(1, dtype=torch.int32)
         self.before_step = None
+        self.min_block = 0
         self.use_graph = use_graph
         self._graph = None
         self._block = 0
@@ -366,25 +368,30 @@ class DeviceEnsemble:
             self.blobs.copy_(eng.to_dev(np.ascontiguousarray(rows, dtype=float)))
         self.n_acc.zero_()
 
+    def _draw_step(self, s_idx, c_idx, zz, lnu):
+        """Draws of one ensemble step into [2][Ns] views, in emcee's order: the move
+        choice (one uniform), the shuffle of the red-blue split, then per half zz, the
+        partner index and the accept uniform."""
+        rs, Ns = self._random, self.Ns
+        rs.random_sample()  # random.choice(moves, p=weights)
+        inds = self._all_inds % 2
+        rs.shuffle(inds)
+        half = (np.flatnonzero(inds == 0), np.flatnonzero(inds == 1))
+        for split in range(2):
+            s_idx[split] = half[split]
+            t = (self.a - 1.0) * rs.rand(Ns) + 1
+            zz[split] = t * t / self.a  # == t ** 2.0 / a (numpy squares for exponent 2)
+            c_idx[split] = half[1 - split][rs.randint(Ns, size=(Ns,))]
+            lnu[split] = np.log(rs.rand(Ns))
+
     def _draw_block(self, n):
-        W, Ns = self.W, self.Ns
+        Ns = self.Ns
         s_idx = np.empty((n, 2, Ns), dtype=np.int32)
         c_idx = np.empty((n, 2, Ns), dtype=np.int32)
         zz = np.empty((n, 2, Ns))
         lnu = np.empty((n, 2, Ns))
-        all_inds = np.arange(W)
         for t in range(n):
-            # emcee draws the move with random.choice(moves, p=weights): one uniform
-            self._random.random_sample()
-            inds = all_inds % 2
-            self._random.shuffle(inds)
-            for split in range(2):
-                S1 = inds == split
-                s_idx[t, split] = np.flatnonzero(S1)
-                comp = np.flatnonzero(~S1)
-                zz[t, split] = ((self.a - 1.0) * self._random.rand(Ns) + 1) ** 2.0 / self.a
-                c_idx[t, split] = comp[self._random.randint(Ns, size=(Ns,))]
-                lnu[t, split] = np.log(self._random.rand(Ns))
+            self._draw_step(s_idx[t], c_idx[t], zz[t], lnu[t])
         return s_idx, c_idx, zz, lnu
 
     def _alloc_block(self, n):
@@ -477,6 +484,7 @@ class DeviceEnsemble:
         rewind the step counter.  The caller must have consumed the previous chunk."""
         import torch
 
+        n = max(n, self.min_block)  # full-size once: no reallocation / recapture later
         first = self._block < n or not hasattr(self, "_pin")
         self._alloc_block(n)
         if first:
@@ -492,18 +500,14 @@ class DeviceEnsemble:
     def enqueue_steps(self, t0, t1):
         """Steps [t0, t1) of the current chunk: draw on the host, upload from pinned
         memory, replay, read the chain rows back into pinned memory -- all asynchronous.
-        Returns (event, rng_states) with the generator state after each step."""
+        Returns (event, rng0) with the generator state before the block."""
         import torch
 
         n = t1 - t0
-        states = []
-        pn = self._pin
+        pn, hp = self._pin, self._pin_np
+        rng0 = self._random.get_state()  # generator state before the block
         for t in range(t0, t1):
-            s_idx, c_idx, zz, lnu = self._draw_block(1)
-            hp = self._pin_np
-            hp["s_idx"][t], hp["c_idx"][t], hp["zz"][t], hp["lnu"][t] = (s_idx[0], c_idx[0],
-                                                                         zz[0], lnu[0])
-            states.append(self._random.get_state())
+            self._draw_step(hp["s_idx"][t], hp["c_idx"][t], hp["zz"][t], hp["lnu"][t])
         for name, dev in (("s_idx", self.s_idx), ("c_idx", self.c_idx), ("zz", self.zz),
                           ("lnu", self.lnu)):
             dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
@@ -514,7 +518,19 @@ class DeviceEnsemble:
             pn["rows"][t0:t1].copy_(self.chain_blobs[t0:t1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return ev, states
+        return ev, rng0
+
+    def rng_state_after(self, rng0, k):
+        """Generator state after k steps drawn from state rng0 (replays the draws)."""
+        keep = self._random.get_state()
+        self._random.set_state(rng0)
+        scratch = (np.empty((2, self.Ns), dtype=np.int32), np.empty((2, self.Ns), dtype=np.int32),
+                   np.empty((2, self.Ns)), np.empty((2, self.Ns)))
+        for _ in range(k):
+            self._draw_step(*scratch)
+        out = self._random.get_state()
+        self._random.set_state(keep)
+        return out
 
     def io_bytes_per_step(self):
         """(host->device, device->host) bytes moved per ensemble step by enqueue_steps."""
@@ -562,6 +578,10 @@ class PlanSampler(EnsembleSampler):
         super().__init__(nwalkers, ndim, self._log_prob, a=a, vectorize=True,
                          blobs_dtype=blobs_dtype, seed=seed, **kwargs)
 
+    def reset(self):
+        super().reset()
+        self._rows = None
+
     def _log_prob(self, p):
         lnp, rows = self.plan.eval_rows(p)
         flux, arrays = self.plan.split_rows(rows)
@@ -571,6 +591,7 @@ class PlanSampler(EnsembleSampler):
         if self._de is None:
             self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
             self._de._random = self._random  # one stream, shared with the host-side API
+            self._de.min_block = self.chunk
         return self._de
 
     def sample(self, initial_state, log_prob0=None, rstate0=None, blobs0=None, iterations=1,
@@ -608,26 +629,40 @@ class PlanSampler(EnsembleSampler):
         iterations = int(iterations)
         if store:
             self._grow(iterations)
+            keep = getattr(self, "_rows", None)
+            self._rows = np.empty((self.iteration + iterations, self.nwalkers, max(de.nb, 1)))
+            if keep is not None and self.iteration:
+                self._rows[:self.iteration] = keep[:self.iteration]
         prev = state.coords
         done = 0
         while done < iterations:
             nchunk = min(self.chunk, iterations - done)
             de.begin_chunk(nchunk)
-            pending = []  # (t0, t1, event, rng_states), in flight on the device
+            pending = []  # (t0, t1, event, rng state before the block), in flight
             t_enq = 0
             t_out = 0
             while t_out < nchunk:
                 while t_enq < nchunk and len(pending) < 2:
                     t1 = min(t_enq + self.block, nchunk)
-                    ev, states = de.enqueue_steps(t_enq, t1)
-                    pending.append((t_enq, t1, ev, states))
+                    ev, rng0 = de.enqueue_steps(t_enq, t1)
+                    pending.append((t_enq, t1, ev, rng0))
                     t_enq = t1
-                t0, t1, ev, states = pending.pop(0)
+                t0, t1, ev, rng0 = pending.pop(0)
                 ev.synchronize()
-                pn = de._pin
-                chain = pn["chain"][t0:t1].numpy().copy()
-                lps = pn["lp"][t0:t1].numpy().copy()
-                recs = pn["rows"][t0:t1].numpy().copy() if de.nb else None
+                hp = de._pin_np
+                nblk = t1 - t0
+                if store:  # straight into the sampler's storage, no temporaries
+                    it0 = self.iteration
+                    self._chain[it0:it0 + nblk] = hp["chain"][t0:t1]
+                    self._log_prob[it0:it0 + nblk] = hp["lp"][t0:t1]
+                    chain, lps = self._chain[it0:it0 + nblk], self._log_prob[it0:it0 + nblk]
+                    recs = None
+                    if de.nb:
+                        self._rows[it0:it0 + nblk] = hp["rows"][t0:t1]
+                        recs = self._rows[it0:it0 + nblk]
+                else:
+                    chain, lps = hp["chain"][t0:t1].copy(), hp["lp"][t0:t1].copy()
+                    recs = hp["rows"][t0:t1].copy() if de.nb else None
                 if np.any(np.isnan(lps)):
                     raise ValueError("Probability function returned NaN")
                 for k in range(t1 - t0):
@@ -638,20 +673,18 @@ class PlanSampler(EnsembleSampler):
                     if recs is not None:
                         flux, arrays = self.plan.split_rows(recs[k])
                         blobs = BlobBatch(self.plan, flux, arrays)
-                    if store:
-                        self._chain[self.iteration] = coords
-                        self._log_prob[self.iteration] = lps[k]
-                        if blobs is not None:
-                            self._blobs.append(blobs)
+                    if store and blobs is not None:
+                        self._blobs.append(blobs)
                     self.iteration += 1
-                    out = State(coords, log_prob=lps[k], blobs=blobs, random_state=states[k],
-                                copy=False)
+                    last = done + t0 + k + 1 == iterations
+                    out = State(coords, log_prob=lps[k], blobs=blobs, copy=False,
+                                random_state=self._random.get_state() if last else None)
                     self._previous_state = out
                     try:
                         yield State(out, copy=True)
                     except GeneratorExit:
                         # the consumer stopped here: rewind the stream to this step
-                        self._random.set_state(states[k])
+                        self._random.set_state(de.rng_state_after(rng0, k + 1))
                         raise
                 t_out = t1
             done += nchunk
