@@ -53,7 +53,8 @@ __global__ void pdist_eval_kernel(int kind, const double* __restrict__ params, i
 // term ds1 per interval.  nraw != NULL selects the reference-order evaluation (pd_eval
 // with pow, slope from log(n2/n1)) that the exact contraction consumes; otherwise the
 // log-space form (pd_log_*).  s_n / s_nd: 257 entries of scratch shared memory.
-__device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const double* x, int N,
+__device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const PdLog& S,
+                                              const double* x, int N,
                                               double e_mul1, double e_mul2, double n_scale,
                                               const double* invdlx, double* xn, double* ds1,
                                               double* nraw, size_t row, int j0, double* s_n,
@@ -79,7 +80,6 @@ __device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const 
       ds1[row + j] = (j < N - 1) ? log(s_n[tid + 1] / nj) * invdlx[j] + 1.0 : 0.0;
     }
   } else {
-    const PdLog S = pd_log_setup(kind, pp, n_scale);
     if (j < N) {
       xj = x[j];
       double e = (xj * e_mul1) * e_mul2;
@@ -105,11 +105,14 @@ __global__ void __launch_bounds__(256) pd_prep_kernel(
     double* __restrict__ xn, double* __restrict__ ds1, double* __restrict__ nraw, int wpitch) {
   __shared__ double s_n[257];
   __shared__ PdNode s_nd[257];
+  __shared__ PdLog s_S;
   int w = blockIdx.y;
   double p[PD_MAXPAR];
 #pragma unroll
   for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
-  pd_prep_chunk(kind, p, x, N, e_mul1, e_mul2, n_scale, invdlx, xn, ds1, nraw,
+  if (threadIdx.x == 0) s_S = pd_log_setup(kind, p, n_scale);
+  __syncthreads();
+  pd_prep_chunk(kind, p, s_S, x, N, e_mul1, e_mul2, n_scale, invdlx, xn, ds1, nraw,
                 (size_t)w * wpitch, blockIdx.x * 256, s_n, s_nd);
 }
 
@@ -393,19 +396,29 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
   }
   __syncthreads();
 
-  for (int e = ebeg + warp; e < eend; e += 8) {
+  // each photon energy is integrated by a pair of warps (64 lanes, ~5 intervals per lane
+  // on the default grids): the per-lane chains are serial, so short chains and many warps
+  // are what keeps the fp64 pipe busy.  The two partial sums meet in shared memory.
+  double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
+  const int pair = warp >> 1, half = warp & 1;
+  for (int e = ebeg + pair; e < eend; e += 4) {
     const double E = a.E_erg[e];
     const int js = s_js[e - ebeg];
     const int len = nint - js;
     double acc = 0.0;
     if (len > 0) {
-      const int m = odd_chunk(len);
-      const int i0 = js + lane * m;
+      const int m = odd_chunk2(len);
+      const int i0 = js + (half * 32 + lane) * m;
       const int i1 = min(i0 + m, nint);
       if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
       acc = warp_sum(acc);
     }
-    if (lane == 0) a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, E, acc);
+    if (lane == 0) s_part[2 * (e - ebeg) + half] = acc;
+  }
+  __syncthreads();
+  for (int e = ebeg + threadIdx.x; e < eend; e += blockDim.x) {
+    const double acc = s_part[2 * (e - ebeg)] + s_part[2 * (e - ebeg) + 1];
+    a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, a.E_erg[e], acc);
   }
 }
 
@@ -430,6 +443,18 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
   const int t_step = ka.has_mv ? *ka.mv.step : 0;  // before anybody can increment it
+  // the accept step's operands do not depend on the model: fetch them up front so that
+  // their (cold) latency overlaps the component loads
+  int sidx = 0;
+  double mv_zz = 1.0, mv_lnu = 0.0, lp_old = 0.0;
+  size_t mv_base = 0;
+  if (ka.has_mv && w < a.W) {
+    mv_base = ((size_t)t_step * 2 + ka.mv.split) * ka.mv.Ns + w;
+    sidx = ka.mv.s_idx[mv_base];
+    mv_zz = ka.mv.zz[mv_base];
+    mv_lnu = ka.mv.lnu[mv_base];
+    lp_old = ka.mv.lp[sidx];
+  }
   if (w < a.W) {
     // s_t[k]: Gaussian term of the k-th non-upper-limit point (k ascending with e)
     double* s_t = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.N_E;
@@ -499,14 +524,10 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         // emcee's accept step for proposal w of the active half, then this walker's
         // row of the chain (its state is final for step t once its half is decided)
         const nb_stretch& mv = ka.mv;
-        const size_t base = ((size_t)t_step * 2 + mv.split) * mv.Ns + w;
-        const int sidx = mv.s_idx[base];
         int acc = 0;
-        double lp_old = 0.0;
         if (lane == 0) {
-          lp_old = mv.lp[sidx];
-          double lnpdiff = (mv.P - 1) * log(mv.zz[base]) + lv - lp_old;
-          acc = lnpdiff > mv.lnu[base];
+          double lnpdiff = (mv.P - 1) * log(mv_zz) + lv - lp_old;
+          acc = lnpdiff > mv_lnu;
         }
         acc = __shfl_sync(0xffffffffu, acc, 0);
         __syncwarp();  // this warp's flux_model row is visible to all its lanes
@@ -689,22 +710,26 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   __syncthreads();
   const PrepItem it = a.items[blockIdx.y];
   const nb_prep_job& J = a.jobs[it.job];
-  double pp[PD_MAXPAR];
-#pragma unroll
-  for (int k = 0; k < PD_MAXPAR; ++k) pp[k] = 0.0;
-  for (int k = 0; k < a.pm.n_out; ++k) {
-    long long d = a.pm.map[k].dst_off - J.pd_off;
-    if (a.pm.map[k].dst_stride == PD_MAXPAR && d >= 0 && d < PD_MAXPAR) {
-#pragma unroll
-      for (int q = 0; q < PD_MAXPAR; ++q)
-        if (q == (int)d) pp[q] = s_pm[k];
-    }
+  // this item's distribution parameters: lane q < 8 of warp 0 finds parameter q among the
+  // mapped entries, thread 0 derives the log-space constants once for the whole CTA
+  __shared__ double s_pp[PD_MAXPAR];
+  __shared__ PdLog s_S;
+  if (tid < PD_MAXPAR) {
+    double v = 0.0;
+    for (int k = 0; k < a.pm.n_out; ++k)
+      if (a.pm.map[k].dst_stride == PD_MAXPAR && a.pm.map[k].dst_off - J.pd_off == tid)
+        v = s_pm[k];
+    s_pp[tid] = v;
   }
+  __syncthreads();
+  if (tid == 0) s_S = pd_log_setup(J.kind, s_pp, J.n_scale);
+  __syncthreads();
+  const double* pp = s_pp;
+  const PdLog& S = s_S;
   if (!it.energy) {
-    pd_prep_chunk(J.kind, pp, J.x, J.N, J.e_mul1, J.e_mul2, J.n_scale, J.invdlx, J.xn, J.ds1,
+    pd_prep_chunk(J.kind, pp, S, J.x, J.N, J.e_mul1, J.e_mul2, J.n_scale, J.invdlx, J.xn, J.ds1,
                   J.nraw, (size_t)w * J.wpitch, it.j0, s_n, s_nd);
   } else {
-    const PdLog S = pd_log_setup(J.kind, pp, J.n_scale);
     for (int i = tid; i < J.N; i += 256) {
       double e = (J.x[i] * J.e_mul1) * J.e_mul2;
       s_node[i] = pd_log_value(S, pd_log_node(S, e));
@@ -1116,7 +1141,7 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
   int epc = (N_E + 7) & ~7;
   while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
   a.e_per_cta = epc;
-  long long smem = 6LL * N * 8 + 4LL * epc;
+  long long smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
   if (smem > 226 * 1024) return NB_ETOOLARGE;
   static bool attr_set = false;
   if (!attr_set) {

@@ -19,6 +19,7 @@
 #pragma once
 #include <math.h>
 #include <stddef.h>
+#include <string.h>
 
 #include "../../include/naima_b200.h"
 
@@ -83,6 +84,85 @@ NB_HD double pd_eval(int kind, const double* p, double e) {
     }
   }
   return NAN;
+}
+
+// ---------------------------------------------------------------------------
+// constants of the per-cell math.  On the device they live in constant memory so that
+// DFMA/DMUL take them straight from the constant bank; as literals every use costs two
+// extra moves per 64-bit constant, which was a third of the synchrotron kernel's
+// instructions.
+// ---------------------------------------------------------------------------
+#define NB_CONST_TABLE                                                                      \
+  { /* 0..12: 1/k!, k = 0..12 (exp) */                                                      \
+    1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664,                  \
+    0.008333333333333333, 0.001388888888888889, 0.0001984126984126984, 2.48015873015873e-05,             \
+    2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08, 2.08767569878681e-09,                                                                                     \
+    /* 13..16: log2(e), 2^52 + 2^51, ln2 hi, ln2 lo */                                      \
+    1.4426950408889634, 6755399441055744.0, 6.93147180369123816490e-01,                     \
+    1.90821492927058770002e-10,                                                             \
+    /* 17..22: AKP10 Gtilde: 1.808, 3.4, 2.210, 0.347, 1.353, 0.217 */                      \
+    1.808, 3.4, 2.210, 0.347, 1.353, 0.217,                                                 \
+    /* 23..27: atanh series 1/3, 1/5, 1/7, 1/9, 1/11 */                                     \
+    1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0                                  \
+  }
+#if defined(__CUDACC__)
+__constant__ double NB_C_DEV[28] = NB_CONST_TABLE;
+#endif
+static const double NB_C_HOST[28] = NB_CONST_TABLE;
+#if defined(__CUDA_ARCH__)
+#define NB_K(i) NB_C_DEV[i]
+#else
+#define NB_K(i) NB_C_HOST[i]
+#endif
+
+// exp(-x) for x >= 0 (NaN propagates): k = round(-x log2 e), r = -x - k ln2 in two
+// pieces, degree-12 Taylor polynomial on |r| <= ln2/2 (max error 3.7e-16 incl.
+// rounding), scaling by 2^k in two factors so that the result underflows gradually.
+NB_HD int nb_loword(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(v);
+#else
+  long long b;
+  memcpy(&b, &v, 8);
+  return (int)(b & 0xffffffffLL);
+#endif
+}
+
+NB_HD double nb_pow2(int k) {  // 2^k, -1022 <= k <= 1023
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((k + 1023) << 20, 0);
+#else
+  long long b = (long long)(k + 1023) << 52;
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+#endif
+}
+
+NB_HD double exp_neg(double x) {
+  const bool ovf = x < -709.0;  // exp(-x) overflows (only reachable with B < 0)
+  x = (x > 1100.0) ? 1100.0 : x;
+  x = ovf ? -709.0 : x;
+  double t = fma(-x, NB_K(13), NB_K(14));
+  int k = nb_loword(t);
+  double kd = t - NB_K(14);
+  double r = fma(kd, -NB_K(15), -x);
+  r = fma(kd, -NB_K(16), r);
+  double p = fma(NB_K(12), r, NB_K(11));
+  p = fma(p, r, NB_K(10));
+  p = fma(p, r, NB_K(9));
+  p = fma(p, r, NB_K(8));
+  p = fma(p, r, NB_K(7));
+  p = fma(p, r, NB_K(6));
+  p = fma(p, r, NB_K(5));
+  p = fma(p, r, NB_K(4));
+  p = fma(p, r, NB_K(3));
+  p = fma(p, r, NB_K(2));
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  int k1 = k >> 1, k2 = k - k1;
+  double v = (p * nb_pow2(k1)) * nb_pow2(k2);
+  return ovf ? INFINITY : v;
 }
 
 // ---------------------------------------------------------------------------
@@ -625,6 +705,14 @@ NB_HD int odd_chunk(int nint) {
   return m;
 }
 
+// odd chunk length for 64 lanes (a pair of warps per row)
+NB_HD int odd_chunk2(int nint) {
+  int m = (nint + 63) / 64;
+  if (m < 1) m = 1;
+  if ((m & 1) == 0) ++m;
+  return m;
+}
+
 // fast contraction: RT table rows (sK/sL, row pitch `pitch`) against one walker
 template <int RT>
 NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double* dlx,
@@ -634,10 +722,12 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
   double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
+  // walker operands come from global memory: fetch those of interval i + 1 before the
+  // RT cells of interval i so that their latency hides behind ~250 instructions
+  double n2 = xnw[i0 + 1], d = dsw[i0], dl = dlx[i0];
   for (int i = i0; i < i1; ++i) {
-    double n2 = xnw[i + 1];
-    double d = dsw[i];
-    double dl = dlx[i];
+    const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
+    const double n2n = xnw[in + 1], dn = dsw[in], dln = dlx[in];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       double xy2 = n2 * sK[r * pitch + i + 1];
@@ -645,6 +735,9 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
       acc[r] += interval_fast(prev[r], xy2, bp1, dl);
       prev[r] = xy2;
     }
+    n2 = n2n;
+    d = dn;
+    dl = dln;
   }
 }
 
@@ -683,13 +776,13 @@ NB_HD void syn_node(double g, double B, double* iec, double* cb) {
 NB_HD double gtilde_rational_fast(double cb) {
   double cb2 = cb * cb;
   double cb4 = cb2 * cb2;
-  double gt2 = fma(0.347, cb4, fma(2.210, cb2, 1.0));
-  double gt3 = fma(0.217, cb4, fma(1.353, cb2, 1.0));
-  double d = (gt3 * gt3) * fma(3.4, cb2, 1.0);
+  double gt2 = fma(NB_K(20), cb4, fma(NB_K(19), cb2, 1.0));
+  double gt3 = fma(NB_K(22), cb4, fma(NB_K(21), cb2, 1.0));
+  double d = (gt3 * gt3) * fma(NB_K(18), cb2, 1.0);
 #if defined(__CUDA_ARCH__)
-  return (1.808 * cb) * gt2 * rsqrt(d);
+  return (NB_K(17) * cb) * gt2 * rsqrt(d);
 #else
-  return (1.808 * cb) * gt2 / sqrt(d);
+  return (NB_K(17) * cb) * gt2 / sqrt(d);
 #endif
 }
 
@@ -698,10 +791,10 @@ NB_HD double gtilde_rational_fast(double cb) {
 NB_HD double log_ratio(double R1, double R2) {
   double s = (R2 - R1) * fast_rcp(R2 + R1);
   double s2 = s * s;
-  double p = fma(s2, 1.0 / 11.0, 1.0 / 9.0);
-  p = fma(p, s2, 1.0 / 7.0);
-  p = fma(p, s2, 1.0 / 5.0);
-  p = fma(p, s2, 1.0 / 3.0);
+  double p = fma(s2, NB_K(27), NB_K(26));
+  p = fma(p, s2, NB_K(25));
+  p = fma(p, s2, NB_K(24));
+  p = fma(p, s2, NB_K(23));
   p = fma(p, s2, 1.0);
   double v = (2.0 * s) * p;
   if (!(fabs(s) <= 0.05)) v = log(R2 / R1);
@@ -734,11 +827,11 @@ NB_HD double syn_lane(double E, double cbE, const double* s_iec, const double* s
   double acc = 0.0;
   double x1 = E * s_iec[i0];
   double R1 = gtilde_rational_fast(cbE * s_cb[i0]);
-  double xy1 = s_xn[i0] * (R1 * exp(-x1));
+  double xy1 = s_xn[i0] * (R1 * exp_neg(x1));
   for (int i = i0; i < i1; ++i) {
     double x2 = E * s_iec[i + 1];
     double R2 = gtilde_rational_fast(cbE * s_cb[i + 1]);
-    double xy2 = s_xn[i + 1] * (R2 * exp(-x2));
+    double xy2 = s_xn[i + 1] * (R2 * exp_neg(x2));
     double bp1 = s_ds[i] + (log_ratio(R1, R2) - (x2 - x1)) * s_idl[i];
     acc += interval_fast(xy1, xy2, bp1, s_dl[i]);
     x1 = x2;

@@ -88,6 +88,10 @@ void emu_bspl(const double* tx, int nx, const double* ty, int ny, const double* 
   for (int i = 0; i < n; ++i) out[i] = bspl_eval2d(tx, nx, ty, ny, c, x[i], y);
 }
 
+void emu_exp_neg(const double* x, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = exp_neg(x[i]);
+}
+
 // pd_prep_chunk, reference-order branch (nraw != NULL): feeds the exact contraction
 void emu_pd_prep(int kind, const double* p, const double* x, int N, double m1, double m2,
                  double ns, const double* invdlx, double* xn, double* ds1, double* nraw) {
@@ -155,17 +159,25 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
   for (int j = 0; j < N; ++j) syn_node(gam[j], B, &iec[j], &cb[j]);
   int nint = N - 1;
   for (int e = 0; e < N_E; ++e) {
-    double part[32];
+    double tot = 0.0;
     int js = syn_first_node(gam, N, B, E_erg[e]);
     int len = nint - js;
-    int m = odd_chunk(len > 0 ? len : 1);
-    for (int lane = 0; lane < 32; ++lane) {
-      int i0 = js + lane * m, i1 = i0 + m < nint ? i0 + m : nint;
-      part[lane] = (len > 0 && i0 < nint)
-                       ? syn_lane(E_erg[e], cbrt(E_erg[e]), iec, cb, xn, ds1, invdlx, dlx, i0, i1)
-                       : 0.0;
+    if (len > 0) {
+      int m = odd_chunk2(len);
+      double halves[2];
+      for (int half = 0; half < 2; ++half) {
+        double part[32];
+        for (int lane = 0; lane < 32; ++lane) {
+          int i0 = js + (half * 32 + lane) * m, i1 = i0 + m < nint ? i0 + m : nint;
+          part[lane] = (i0 < nint) ? syn_lane(E_erg[e], cbrt(E_erg[e]), iec, cb, xn, ds1, invdlx,
+                                              dlx, i0, i1)
+                                   : 0.0;
+        }
+        halves[half] = tree32(part);
+      }
+      tot = halves[0] + halves[1];
     }
-    out[e] = syn_finish(B, E_erg[e], len > 0 ? tree32(part) : 0.0);
+    out[e] = syn_finish(B, E_erg[e], tot);
   }
   free(iec);
   free(cb);

@@ -160,6 +160,26 @@ def test_bspline(emu, lut_probe):
         assert_allclose(out, lut_probe["ds"][k], rtol=1e-12, atol=1e-45)
 
 
+def test_exp_neg(emu):
+    """The device exp(-x) (range reduction + degree-12 polynomial + two-step scaling):
+    <= 2 ulp over the whole range incl. the subnormal tail, exact zero beyond, NaN kept."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 760, 200000), 10 ** rng.uniform(-300, 3, 50000),
+                        [0.0, 1e-320, 708.39, 744.4, 745.2, 746.0, 1e4, 1e300, np.inf]])
+    out = np.empty(x.size)
+    emu.emu_exp_neg(P(x), x.size, P(out))
+    ref = np.exp(-x)
+    normal = ref > 2.3e-308
+    assert_allclose(out[normal], ref[normal], rtol=4.5e-16)
+    assert_allclose(out[~normal], ref[~normal], rtol=0, atol=2e-323)
+    assert np.all(out[x > 746] == 0)
+    y = np.array([np.nan, -1.0, -800.0])
+    out = np.empty(3)
+    with np.errstate(all="ignore"):
+        emu.emu_exp_neg(P(y), 3, P(out))
+        assert np.isnan(out[0]) and out[1] == np.exp(1.0) and out[2] == np.inf
+
+
 def _prep(emu, pd, x, m1, m2, ns, exact=True):
     """exact: reference-order operands (pow, log of the ratio); else the log-space form
     the hoisted kernels consume."""
