@@ -49,10 +49,13 @@ __global__ void pdist_eval_kernel(int kind, const double* __restrict__ params, i
   out[(size_t)w * out_ld + i] = pd_eval(kind, p, e[i]);
 }
 
-// One chunk of 256 nodes of one walker: n on the grid, x*n and the logarithmic slope
-// term ds1 per interval.  nraw != NULL selects the reference-order evaluation (pd_eval
-// with pow, slope from log(n2/n1)) that the exact contraction consumes; otherwise the
-// log-space form (pd_log_*).  s_n / s_nd: 257 entries of scratch shared memory.
+// One chunk of PREP_CHUNK = 512 nodes of one walker (two per thread: the transcendental
+// chains of the two nodes interleave): n on the grid, x*n and the logarithmic slope term
+// ds1 per interval.  nraw != NULL selects the reference-order evaluation (pd_eval with
+// pow, slope from log(n2/n1)) that the exact contraction consumes; otherwise the
+// log-space form (pd_log_*).  s_n / s_nd: PREP_CHUNK + 1 entries of scratch shared memory.
+constexpr int PREP_CHUNK = 512;
+
 __device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const PdLog& S,
                                               const double* x, int N,
                                               double e_mul1, double e_mul2, double n_scale,
@@ -60,41 +63,53 @@ __device__ __forceinline__ void pd_prep_chunk(int kind, const double* pp, const 
                                               double* nraw, size_t row, int j0, double* s_n,
                                               PdNode* s_nd) {
   const int tid = threadIdx.x;
-  const int j = j0 + tid;
-  const bool next = (tid == 255 && j0 + 256 < N);  // first node of the next chunk
-  double xj = 0.0, nj = 0.0;
-  PdNode nd;
-  nd.P = nd.c = nd.L = 0.0;
-  nd.side = 0;
+  const bool next = (tid == 255 && j0 + PREP_CHUNK < N);  // first node of the next chunk
+  double xj[2] = {0.0, 0.0}, nj[2] = {0.0, 0.0};
+  PdNode nd[2];
   if (nraw) {
-    if (j < N) {
-      xj = x[j];
-      nj = pd_eval(kind, pp, (xj * e_mul1) * e_mul2) * n_scale;
-      s_n[tid] = nj;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = tid + 256 * u, j = j0 + l;
+      if (j < N) {
+        xj[u] = x[j];
+        nj[u] = pd_eval(kind, pp, (xj[u] * e_mul1) * e_mul2) * n_scale;
+        s_n[l] = nj[u];
+      }
     }
-    if (next) s_n[256] = pd_eval(kind, pp, (x[j0 + 256] * e_mul1) * e_mul2) * n_scale;
+    if (next)
+      s_n[PREP_CHUNK] = pd_eval(kind, pp, (x[j0 + PREP_CHUNK] * e_mul1) * e_mul2) * n_scale;
     __syncthreads();
-    if (j < N) {
-      xn[row + j] = xj * nj;
-      nraw[row + j] = nj;
-      ds1[row + j] = (j < N - 1) ? log(s_n[tid + 1] / nj) * invdlx[j] + 1.0 : 0.0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = tid + 256 * u, j = j0 + l;
+      if (j < N) {
+        xn[row + j] = xj[u] * nj[u];
+        nraw[row + j] = nj[u];
+        ds1[row + j] = (j < N - 1) ? log(s_n[l + 1] / nj[u]) * invdlx[j] + 1.0 : 0.0;
+      }
     }
   } else {
-    if (j < N) {
-      xj = x[j];
-      double e = (xj * e_mul1) * e_mul2;
-      nd = pd_log_node(S, e);
-      nj = pd_log_value(S, nd);
-      s_nd[tid] = nd;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = tid + 256 * u, j = j0 + l;
+      nd[u].P = nd[u].c = nd[u].L = 0.0;
+      nd[u].side = 0;
+      if (j < N) {
+        xj[u] = x[j];
+        nd[u] = pd_log_node(S, (xj[u] * e_mul1) * e_mul2);
+        nj[u] = pd_log_value(S, nd[u]);
+        s_nd[l] = nd[u];
+      }
     }
-    if (next) {
-      double e = (x[j0 + 256] * e_mul1) * e_mul2;
-      s_nd[256] = pd_log_node(S, e);
-    }
+    if (next) s_nd[PREP_CHUNK] = pd_log_node(S, (x[j0 + PREP_CHUNK] * e_mul1) * e_mul2);
     __syncthreads();
-    if (j < N) {
-      xn[row + j] = xj * nj;
-      ds1[row + j] = (j < N - 1) ? pd_log_ds1(S, nd, s_nd[tid + 1], invdlx[j]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = tid + 256 * u, j = j0 + l;
+      if (j < N) {
+        xn[row + j] = xj[u] * nj[u];
+        ds1[row + j] = (j < N - 1) ? pd_log_ds1(S, nd[u], s_nd[l + 1], invdlx[j]) : 0.0;
+      }
     }
   }
 }
@@ -103,8 +118,8 @@ __global__ void __launch_bounds__(256) pd_prep_kernel(
     int kind, const double* __restrict__ params, int W, const double* __restrict__ x, int N,
     double e_mul1, double e_mul2, double n_scale, const double* __restrict__ invdlx,
     double* __restrict__ xn, double* __restrict__ ds1, double* __restrict__ nraw, int wpitch) {
-  __shared__ double s_n[257];
-  __shared__ PdNode s_nd[257];
+  __shared__ double s_n[PREP_CHUNK + 1];
+  __shared__ PdNode s_nd[PREP_CHUNK + 1];
   __shared__ PdLog s_S;
   int w = blockIdx.y;
   double p[PD_MAXPAR];
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(256) pd_prep_kernel(
   if (threadIdx.x == 0) s_S = pd_log_setup(kind, p, n_scale);
   __syncthreads();
   pd_prep_chunk(kind, p, s_S, x, N, e_mul1, e_mul2, n_scale, invdlx, xn, ds1, nraw,
-                (size_t)w * wpitch, blockIdx.x * 256, s_n, s_nd);
+                (size_t)w * wpitch, blockIdx.x * PREP_CHUNK, s_n, s_nd);
 }
 
 // W = trapz_loglog(x*n, x*x_to_energy) in reference operation order; one CTA
@@ -370,17 +385,19 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
   const double Bw = a.B[w];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nint = a.N - 1;
-  const int ebeg = blockIdx.y * a.e_per_cta;
-  const int eend = min(ebeg + a.e_per_cta, a.N_E);
+  // this CTA's photon energies: e = blockIdx.y + k * gridDim.y, k < ne (strided, so that
+  // every slice gets the same mix of cheap and expensive energies)
+  const int nsl = gridDim.y;
+  const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
 
   // nodes whose exp(-E/Ec) underflows to zero contribute nothing: find, per photon
   // energy, the first node that can be non-zero, and only set up nodes from the
   // smallest of them on
   if (threadIdx.x == 0) s_jmin = a.N;
   __syncthreads();
-  for (int e = ebeg + threadIdx.x; e < eend; e += blockDim.x) {
-    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[e]);
-    s_js[e - ebeg] = js;
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[blockIdx.y + k * nsl]);
+    s_js[k] = js;
     atomicMin(&s_jmin, js);
   }
   __syncthreads();
@@ -401,9 +418,9 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
   // are what keeps the fp64 pipe busy.  The two partial sums meet in shared memory.
   double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
   const int pair = warp >> 1, half = warp & 1;
-  for (int e = ebeg + pair; e < eend; e += 4) {
-    const double E = a.E_erg[e];
-    const int js = s_js[e - ebeg];
+  for (int k = pair; k < ne; k += 4) {
+    const double E = a.E_erg[blockIdx.y + k * nsl];
+    const int js = s_js[k];
     const int len = nint - js;
     double acc = 0.0;
     if (len > 0) {
@@ -413,11 +430,12 @@ __global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
       if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
       acc = warp_sum(acc);
     }
-    if (lane == 0) s_part[2 * (e - ebeg) + half] = acc;
+    if (lane == 0) s_part[2 * k + half] = acc;
   }
   __syncthreads();
-  for (int e = ebeg + threadIdx.x; e < eend; e += blockDim.x) {
-    const double acc = s_part[2 * (e - ebeg)] + s_part[2 * (e - ebeg) + 1];
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    const int e = blockIdx.y + k * nsl;
+    const double acc = s_part[2 * k] + s_part[2 * k + 1];
     a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, a.E_erg[e], acc);
   }
 }
@@ -667,8 +685,8 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_node = reinterpret_cast<double*>(smem_raw);  // energy items: n at every node
   __shared__ double s_pm[NB_MAX_MAP];
-  __shared__ double s_n[257];
-  __shared__ PdNode s_nd[257];
+  __shared__ double s_n[PREP_CHUNK + 1];
+  __shared__ PdNode s_nd[PREP_CHUNK + 1];
   __shared__ double s_red[256];
   const int w = blockIdx.x;
   const int tid = threadIdx.x;
@@ -959,7 +977,7 @@ int nb_pd_prep_ex(int kind, const double* pd_params, int W, const double* x, int
       kind < 0 || kind > NB_PD_LOGPAR)
     return NB_EINVAL;
   if (W == 0) return 0;
-  dim3 grid((N + 255) / 256, W);
+  dim3 grid((N + PREP_CHUNK - 1) / PREP_CHUNK, W);
   pd_prep_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, x, N, e_mul1, e_mul2,
                                                       n_scale, invdlx, xn, ds1, nraw, wpitch);
   NB_CHECK_LAUNCH();
@@ -1320,7 +1338,7 @@ static int launch_walker_prep(const nb_stretch* mv, double* pars_out, const doub
   for (int k = 0; k < n_jobs; ++k) {
     const nb_prep_job& J = a.jobs[k];
     if (J.xn)
-      for (int j0 = 0; j0 < J.N; j0 += 256) {
+      for (int j0 = 0; j0 < J.N; j0 += PREP_CHUNK) {
         if (a.n_items == NB_MAX_PREP_ITEMS) return NB_ETOOLARGE;
         a.items[a.n_items++] = PrepItem{(short)k, 0, j0};
       }

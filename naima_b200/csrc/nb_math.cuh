@@ -289,6 +289,20 @@ NB_HD double fast_rcp(double b) {
 #endif
 }
 
+// 1/sqrt(d) to ~1 ulp for normal positive d: hardware seed (MUFU.RSQ64H, <= 2^-23) and
+// one cubically convergent step, y (1 + e/2 + 3 e^2/8) with e = 1 - d y^2.
+NB_HD double fast_rsqrt(double d) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-(d * y), y, 1.0);
+  double t = fma(e, 0.375, 0.5) * e;
+  return fma(y, t, y);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
 // hoisted form: xy = x*y at both nodes, bp1 = b + 1 with
 // b = ln(y2/y1)/ln(x2/x1), dlx = ln(x2/x1).  (x2/x1)^b == y2/y1, so
 // y1 (x2 (x2/x1)^b - x1) == x2 y2 - x1 y1.
@@ -779,11 +793,7 @@ NB_HD double gtilde_rational_fast(double cb) {
   double gt2 = fma(NB_K(20), cb4, fma(NB_K(19), cb2, 1.0));
   double gt3 = fma(NB_K(22), cb4, fma(NB_K(21), cb2, 1.0));
   double d = (gt3 * gt3) * fma(NB_K(18), cb2, 1.0);
-#if defined(__CUDA_ARCH__)
-  return (NB_K(17) * cb) * gt2 * rsqrt(d);
-#else
-  return (NB_K(17) * cb) * gt2 / sqrt(d);
-#endif
+  return (NB_K(17) * cb) * gt2 * fast_rsqrt(d);
 }
 
 // ln(R2/R1) for neighbouring nodes: 2 atanh((R2-R1)/(R2+R1)) by its series while
@@ -869,23 +879,38 @@ struct CombineArgs {
 };
 
 NB_HD double combine_model(const CombineArgs& a, int w, int e) {
-  double total = 0.0, g = 0.0;
-  bool first_in_group = true, first_group = true;
-#pragma unroll 4
-  for (int t = 0; t < a.n_terms; ++t) {
-    const nb_term& T = a.terms[t];
-    double v = T.src[(size_t)w * T.ld + T.off + e];
-    if (T.wscale) v *= T.wscale[w];
-    g = first_in_group ? v : g + v;
-    first_in_group = false;
-    if (T.group_end) {
-      if (T.div != 1.0) g = g / T.div;
-      total = first_group ? g : total + g;
-      first_group = false;
-      first_in_group = true;
+  // all loads first (independent: they overlap instead of queueing behind the
+  // data-dependent group logic), then the sums in the order given
+  double v[NB_MAX_TERMS], ws[NB_MAX_TERMS];
+#pragma unroll
+  for (int t = 0; t < NB_MAX_TERMS; ++t) {
+    v[t] = 0.0;
+    ws[t] = 1.0;
+    if (t < a.n_terms) {
+      const nb_term& T = a.terms[t];
+      v[t] = T.src[(size_t)w * T.ld + T.off + e];
+      if (T.wscale) ws[t] = T.wscale[w];
     }
   }
-  return total * a.unit_fac[e];
+  const double uf = a.unit_fac[e];
+  double total = 0.0, g = 0.0;
+  bool first_in_group = true, first_group = true;
+#pragma unroll
+  for (int t = 0; t < NB_MAX_TERMS; ++t) {
+    if (t < a.n_terms) {
+      const nb_term& T = a.terms[t];
+      double x = T.wscale ? v[t] * ws[t] : v[t];
+      g = first_in_group ? x : g + x;
+      first_in_group = false;
+      if (T.group_end) {
+        if (T.div != 1.0) g = g / T.div;
+        total = first_group ? g : total + g;
+        first_group = false;
+        first_in_group = true;
+      }
+    }
+  }
+  return total * uf;
 }
 
 // Sum of the n non-upper-limit terms get(e), e ascending, in numpy's pairwise
