@@ -311,17 +311,12 @@ def run_native(args):
         b.record()
         flush_ev.append((a, b))
 
-    if world == 1:
-        sampler = nb.PlanSampler(W, 4, plan, seed=wl.SEED)
-        sampler._device().before_step = e2e_flush
-        h2d_step, d2h_step = sampler._device().io_bytes_per_step()
-        api = ("naima_b200.PlanSampler.sample (the sampler get_sampler()/run_sampler() build "
-               "for a traced model; one State per step on the host)")
-    else:
-        sampler = parallel.ShardedSampler(W, 4, plan, seed=wl.SEED)
-        h2d, d2h = plan.io_bytes((W // world) // 2)
-        h2d_step, d2h_step = 2 * h2d * world, 2 * d2h * world
-        api = "naima_b200.parallel.ShardedSampler.sample over a traced LikelihoodPlan"
+    sampler = nb.PlanSampler(W, 4, plan, seed=wl.SEED)  # sharded over the ranks when N > 1
+    sampler._device().before_step = e2e_flush
+    h2d_step, d2h_step = sampler._device().io_bytes_per_step()
+    h2d_step, d2h_step = h2d_step * world, d2h_step * world  # every rank keeps the chain
+    api = ("naima_b200.PlanSampler.sample (the sampler get_sampler()/run_sampler() build "
+           "for a traced model; one State per step on the host)")
     state = sampler.run_mcmc(p0, args.warmup)
     torch.cuda.synchronize()
     if world > 1:
@@ -330,8 +325,6 @@ def run_native(args):
     gen = sampler.sample(state, iterations=args.steps, store=True)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        if world > 1:
-            flush()
         next(gen)
     torch.cuda.synchronize()
     e2e_t = time.perf_counter() - t0
@@ -349,6 +342,19 @@ def run_native(args):
            "value_excl_flush": W * args.steps / max(e2e_t - flush_s, 1e-9),
            "flush_ms_per_step": 1e3 * flush_s / args.steps, "api": api}
     if rank != 0:
+        return
+    if world > 1:  # roofline and CPU baseline are N = 1 measurements
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world, W), "clocks": clk, "e2e": e2e,
+            "gpu_launches": int(gpu_launches),
+            "collectives_per_step": 2, "roofline": None, "cpu_baseline": None,
+            "acceptance_fraction": float(np.mean(ens.acceptance_counts)
+                                         / (args.steps + args.warmup)),
+        }
+        print(json.dumps(line))
         return
 
     # ---- roofline of the dominant kernel (rank 0, N = 1 shapes) ------------------------
@@ -435,14 +441,18 @@ def main():
         run_reference(args)
     else:
         run_native(args)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        try:
-            import torch.distributed as dist
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.impl != "reference":
+        # CUDA graphs that captured NCCL collectives are still alive: tearing the process
+        # group down under them can dead-lock, so synchronise and leave without it
+        import torch
+        import torch.distributed as dist
 
-            if dist.is_initialized():
-                dist.destroy_process_group()
-        except Exception:
-            pass
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -315,6 +315,10 @@ typedef struct nb_stretch {
   double* lp;          /* [W] */
   double* blobs;       /* [W][nb] or NULL */
   int nb, W, P, Ns, split;
+  int i0;              /* first proposal of the half handled by this launch (walker sharding:
+                          a rank evaluates proposals [i0, i0 + W_launch) of the Ns) */
+  int pars_ld;         /* row pitch of the published proposals `pars` (0 = P) */
+  int pad_;
   int* step;           /* device int32: current step index t */
   int* sync;           /* device int32 scratch (ticket counter) */
   const int* s_idx;    /* [n_steps][2][Ns] */
@@ -341,6 +345,22 @@ int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
                              const double* err_lo, const double* err_hi, const int* ul,
                              const double* cl, const double* prior, double* flux_model,
                              int flux_ld, double* lnp, void* stream);
+/* nb_combine_lnprob with a stride between consecutive walkers' lnp (lnp[w * lnp_ld]), for
+ * writing straight into packed per-proposal records */
+int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
+                         const double* unit_fac, const double* data_flux, const double* err_lo,
+                         const double* err_hi, const int* ul, const double* cl,
+                         const double* prior, double* flux_model, int flux_ld, double* lnp,
+                         int lnp_ld, void* stream);
+
+/* Walker sharding: every rank evaluates a slice of the half-ensemble's proposals into
+ * packed records  pack[i][0..nb) = blob record, pack[i][nb] = lnprob,
+ * pack[i][nb+1 .. nb+1+P) = proposal  (row pitch ld >= nb + 1 + P), the slices are
+ * all-gathered, and this kernel then runs the accept step + chain append for ALL Ns
+ * proposals of the half identically on every rank (mv.i0 is ignored).  Step counter
+ * protocol as for nb_combine_lnprob_update. */
+int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int ld,
+                             void* stream);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

@@ -44,7 +44,8 @@ class nb_prep_job(ctypes.Structure):
 
 class nb_stretch(ctypes.Structure):
     _fields_ = [("coords", vp), ("lp", vp), ("blobs", vp), ("nb", c_int), ("W", c_int),
-                ("P", c_int), ("Ns", c_int), ("split", c_int), ("step", vp), ("sync", vp),
+                ("P", c_int), ("Ns", c_int), ("split", c_int), ("i0", c_int),
+                ("pars_ld", c_int), ("pad_", c_int), ("step", vp), ("sync", vp),
                 ("s_idx", vp), ("c_idx", vp), ("zz", vp), ("lnu", vp), ("n_accepted", vp),
                 ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp)]
 
@@ -79,6 +80,9 @@ PROTOTYPES = {
                             c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
     "nb_combine_lnprob_update": [ctypes.POINTER(nb_stretch), vp, ctypes.POINTER(nb_term), c_int,
                                  c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp, vp],
+    "nb_combine_lnprob_ld": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp,
+                             vp, vp, vp, c_int, vp, c_int, vp],
+    "nb_stretch_update_packed": [ctypes.POINTER(nb_stretch), vp, c_int, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
       if (lane == 0) {
         for (int i = (n >= 8 ? nblk : 0); i < n; ++i) seq = (i == 0) ? s_t[0] : seq + s_t[i];
         lv = lnprob_finish(a, w, seq, nul, nviol);
-        a.lnp[w] = lv;
+        a.lnp[(size_t)w * a.lnp_ld] = lv;
       }
       if (ka.has_mv) {
         // emcee's accept step for proposal w of the active half, then this walker's
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         __syncwarp();  // this warp's flux_model row is visible to all its lanes
         const size_t W_ = (size_t)mv.W;
         for (int d = lane; d < mv.P; d += 32) {
-          double v = acc ? ka.pars[(size_t)w * mv.P + d] : mv.coords[(size_t)sidx * mv.P + d];
+          double v = acc ? ka.pars[(size_t)w * mv.pars_ld + d] : mv.coords[(size_t)sidx * mv.P + d];
           if (acc) mv.coords[(size_t)sidx * mv.P + d] = v;
           if (mv.chain) mv.chain[((size_t)t_step * W_ + sidx) * mv.P + d] = v;
         }
@@ -696,12 +696,12 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   if (a.has_mv) {
     // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
     if (tid < a.pm.P) {
-      const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + w;
+      const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + a.mv.i0 + w;
       double c = a.mv.coords[(size_t)a.mv.c_idx[base] * a.pm.P + tid];
       double sv = a.mv.coords[(size_t)a.mv.s_idx[base] * a.pm.P + tid];
       double q = __dsub_rn(c, __dmul_rn(__dsub_rn(c, sv), a.mv.zz[base]));
       s_q[tid] = q;
-      if (publish) a.pars_out[(size_t)w * a.pm.P + tid] = q;
+      if (publish) a.pars_out[(size_t)w * a.mv.pars_ld + tid] = q;
     }
     __syncthreads();
     p = s_q;
@@ -886,6 +886,56 @@ __global__ void stretch_store_kernel(const double* __restrict__ coords,
       chain_blobs[t * W * nb + k] = blobs[k];
   __syncthreads();
   if (threadIdx.x == 0) *step = (int)t + 1;
+}
+
+// ---------------------------------------------------------------------------
+// accept step + chain append from all-gathered packed records (walker sharding): one
+// warp per proposal of the active half, identical on every rank
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stretch_update_packed_kernel(
+    const __grid_constant__ nb_stretch mv, const double* __restrict__ pack, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  const int t_step = *mv.step;
+  if (i < mv.Ns) {
+    const size_t base = ((size_t)t_step * 2 + mv.split) * mv.Ns + i;
+    const int sidx = mv.s_idx[base];
+    const double* rec = pack + (size_t)i * ld;
+    const double lv = rec[mv.nb];
+    const double lp_old = mv.lp[sidx];
+    const double lnpdiff = (mv.P - 1) * log(mv.zz[base]) + lv - lp_old;
+    const int acc = lnpdiff > mv.lnu[base];
+    const size_t W_ = (size_t)mv.W;
+    for (int d = lane; d < mv.P; d += 32) {
+      double v = acc ? rec[mv.nb + 1 + d] : mv.coords[(size_t)sidx * mv.P + d];
+      if (acc) mv.coords[(size_t)sidx * mv.P + d] = v;
+      if (mv.chain) mv.chain[((size_t)t_step * W_ + sidx) * mv.P + d] = v;
+    }
+    for (int d = lane; d < mv.nb; d += 32) {
+      double v = acc ? rec[d] : mv.blobs[(size_t)sidx * mv.nb + d];
+      if (acc) mv.blobs[(size_t)sidx * mv.nb + d] = v;
+      if (mv.chain_blobs) mv.chain_blobs[((size_t)t_step * W_ + sidx) * mv.nb + d] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (acc) {
+        mv.lp[sidx] = lv;
+        mv.n_accepted[sidx] += 1;
+      }
+      if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
+    }
+  }
+  if (mv.split == 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      int ticket = atomicAdd(mv.sync, 1);
+      if (ticket == (int)gridDim.x - 1) {
+        *mv.sync = 0;
+        *mv.step = t_step + 1;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1178,7 +1228,8 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
                           int n_terms, int W, int N_E, const double* unit_fac,
                           const double* data_flux, const double* err_lo, const double* err_hi,
                           const int* ul, const double* cl, const double* prior,
-                          double* flux_model, int flux_ld, double* lnp, void* stream) {
+                          double* flux_model, int flux_ld, double* lnp, int lnp_ld,
+                          void* stream) {
   if (!terms_host || n_terms < 1 || n_terms > NB_MAX_TERMS || W < 0 || N_E < 1 || !unit_fac)
     return NB_EINVAL;
   if (flux_ld == 0) flux_ld = N_E;
@@ -1192,15 +1243,18 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
   a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
   a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
   a.prior = prior; a.flux_model = flux_model; a.flux_ld = flux_ld; a.lnp = lnp;
+  a.lnp_ld = lnp_ld > 0 ? lnp_ld : 1;
   ka.has_mv = mv ? 1 : 0;
   ka.pars = pars;
   if (mv) {
     if (!lnp || !pars || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
-        !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->P < 1 || mv->W < W ||
+        !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->i0 != 0 || mv->P < 1 ||
+        mv->W < W || (mv->pars_ld != 0 && mv->pars_ld < mv->P) ||
         mv->split < 0 || mv->split > 1 || mv->nb < 0 ||
         (mv->nb > 0 && (!mv->blobs || !flux_model || mv->nb < N_E || mv->nb > flux_ld)))
       return NB_EINVAL;
     ka.mv = *mv;
+    if (ka.mv.pars_ld == 0) ka.mv.pars_ld = mv->P;
   }
   if (W == 0) return 0;
   size_t smem = (size_t)COMBINE_WARPS * N_E * sizeof(double);
@@ -1216,7 +1270,17 @@ int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
                       const double* err_hi, const int* ul, const double* cl, const double* prior,
                       double* flux_model, int flux_ld, double* lnp, void* stream) {
   return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
-                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, stream);
+                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
+}
+
+int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
+                         const double* unit_fac, const double* data_flux, const double* err_lo,
+                         const double* err_hi, const int* ul, const double* cl,
+                         const double* prior, double* flux_model, int flux_ld, double* lnp,
+                         int lnp_ld, void* stream) {
+  if (lnp_ld < 1) return NB_EINVAL;
+  return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
+                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, lnp_ld, stream);
 }
 
 int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
@@ -1227,7 +1291,7 @@ int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
                              int flux_ld, double* lnp, void* stream) {
   if (!mv_host) return NB_EINVAL;
   return launch_combine(mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux, err_lo,
-                        err_hi, ul, cl, prior, flux_model, flux_ld, lnp, stream);
+                        err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
 }
 
 int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
@@ -1318,10 +1382,12 @@ static int launch_walker_prep(const nb_stretch* mv, double* pars_out, const doub
   a.pars_out = pars_out;
   if (mv) {
     if (!mv->coords || !mv->step || !mv->s_idx || !mv->c_idx || !mv->zz || mv->P != P ||
-        mv->Ns != W || mv->split < 0 || mv->split > 1 || !pars_out)
+        mv->i0 < 0 || mv->i0 + W > mv->Ns || mv->split < 0 || mv->split > 1 || !pars_out ||
+        (mv->pars_ld != 0 && mv->pars_ld < P))
       return NB_EINVAL;
     if (P > NB_MAX_MOVE_PAR) return NB_ETOOLARGE;
     a.mv = *mv;
+    if (a.mv.pars_ld == 0) a.mv.pars_ld = P;
   }
   if (n_jobs < 0 || n_jobs > NB_MAX_PREP_JOBS || (n_jobs > 0 && (!jobs_host || !pm)))
     return NB_EINVAL;
@@ -1439,6 +1505,18 @@ int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, 
                                              nb > 0 ? chain_blobs : nullptr);
     NB_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+int nb_stretch_update_packed(const nb_stretch* mv, const double* pack, int ld, void* stream) {
+  if (!mv || !pack || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
+      !mv->zz || !mv->lnu || !mv->n_accepted || mv->P < 1 || mv->Ns < 0 || mv->W < mv->Ns ||
+      mv->split < 0 || mv->split > 1 || mv->nb < 0 || (mv->nb > 0 && !mv->blobs) ||
+      ld < mv->nb + 1 + mv->P)
+    return NB_EINVAL;
+  if (mv->Ns == 0) return 0;
+  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(*mv, pack, ld);
+  NB_CHECK_LAUNCH();
   return 0;
 }
 

@@ -876,6 +876,7 @@ struct CombineArgs {
   double* flux_model;
   int flux_ld;  // row pitch of flux_model (>= N_E)
   double* lnp;
+  int lnp_ld;  // stride between consecutive walkers' lnp (1 = dense)
 };
 
 NB_HD double combine_model(const CombineArgs& a, int w, int e) {
@@ -973,7 +974,7 @@ NB_HD void combine_lnprob_walker(const CombineArgs& a, int w) {
   double seq = numpy_order_sum(a.N_E, a.ul, n, [&](int e) {
     return lnprob_term(combine_model(a, w, e), a.data_flux[e], a.err_lo[e], a.err_hi[e]);
   });
-  a.lnp[w] = lnprob_finish(a, w, seq, nul, nviol);
+  a.lnp[(size_t)w * a.lnp_ld] = lnprob_finish(a, w, seq, nul, nviol);
 }
 
 // FITPACK bispev at one point with clamping to the knot range

@@ -375,7 +375,7 @@ def make_terms(terms):
 
 
 def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, lnp_out=None,
-            mv=None, pars_d=None, flux_ld=0):
+            mv=None, pars_d=None, flux_ld=0, lnp_ld=1):
     """flux model (radiative.py:102-111) and, with `data`, lnprob (core.py:64-121); with
     `mv` (an nb_stretch) also the accept step and chain append of the half-step."""
     arr = make_terms(terms) if not isinstance(terms, ctypes.Array) else terms
@@ -386,11 +386,11 @@ def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, l
             ptr(d.flux), ptr(d.err_lo), ptr(d.err_hi), ptr(d.ul), ptr(d.cl), ptr(prior_d),
             ptr(flux_out), flux_ld, ptr(lnp_out), stream()), "nb_combine_lnprob_update")
         return
-    check(lib().nb_combine_lnprob(
+    check(lib().nb_combine_lnprob_ld(
         arr, len(arr), W, N_E, ptr(unit_fac_d),
         ptr(d.flux) if d else None, ptr(d.err_lo) if d else None, ptr(d.err_hi) if d else None,
         ptr(d.ul) if d else None, ptr(d.cl) if d else None, ptr(prior_d), ptr(flux_out),
-        flux_ld, ptr(lnp_out), stream()), "nb_combine_lnprob")
+        flux_ld, ptr(lnp_out), max(int(lnp_ld), 1), stream()), "nb_combine_lnprob")
 
 
 def trapz_loglog(y, x, intervals=False):

@@ -404,11 +404,19 @@ class LikelihoodPlan:
         return {"kind": "const", "value": b}
 
     # -- per-W executable -------------------------------------------------------------
-    def _build(self, W):
+    def pack_width(self):
+        """Columns of a packed per-proposal record [blob record | lnprob | proposal]."""
+        return self.row_width + 1 + self.P
+
+    def _build(self, W, pack=None):
+        """pack: optional device tensor [W][>= pack_width()] whose rows receive the packed
+        per-proposal records (walker sharding: the all-gather buffer's local slice)."""
         ex = _Exec()
         ex.W = W
         P = self.P
-        ex.pars = eng.zeros(W, P)
+        ex.pack = pack
+        ex.pars = eng.zeros(W, P) if pack is None else \
+            pack[:, self.row_width + 1:self.row_width + 1 + P]
         n_pd, n_sc = len(self.pds), len(self.scalars)
         ex.pm = eng.zeros(n_pd * W * NB_PD_MAXPAR + max(n_sc, 1) * W)
         entries = []
@@ -470,9 +478,10 @@ class LikelihoodPlan:
         ex.terms = eng.make_terms(terms)
         # one record per walker: [model flux (N_E) | further blobs], so that a sampler
         # moves a walker's blobs with one row copy (row pitch = self.row_width)
-        ex.row = eng.zeros(W, self.row_width)
+        ex.row = eng.zeros(W, self.row_width) if pack is None else pack[:, :self.row_width]
+        ex.row_ld = ex.row.stride(0)
         ex.flux = ex.row[:, :self.N_E]
-        ex.lnp = eng.zeros(W)
+        ex.lnp = eng.zeros(W) if pack is None else pack[:, self.row_width]
         ex.E_erg = eng.to_dev(self.E_eV * eng.eV_erg)
         ex.blob_bufs = []
         for spec, (off, width) in zip(self._flat_blob_specs(), self.blob_cols):
@@ -495,7 +504,7 @@ class LikelihoodPlan:
                                  pd_off=spec["pd"] * W * NB_PD_MAXPAR, x=g.x_d,
                                  e_mul1=g.e_mul1, e_mul2=g.e_mul2, n_scale=g.n_scale,
                                  x_to_energy=g.x_to_erg, energy_out=buf,
-                                 energy_stride=self.row_width))
+                                 energy_stride=ex.row_ld))
         if len(jobs) > 8:
             raise TraceError("too many particle-distribution jobs in one plan")
         ex.jobs = (nb_prep_job * max(len(jobs), 1))()
@@ -510,6 +519,8 @@ class LikelihoodPlan:
         ex.row_pin = torch.empty(W, self.row_width, dtype=torch.float64).pin_memory()
         ex.pd_block, ex.scalar_col = pd_block, scalar_col
         ex.graph = None
+        if pack is not None:
+            return ex  # driven by a sharded ensemble step (proposals computed on the device)
         # warm-up launch outside capture (function attributes, lazy module load)
         self._enqueue(ex)
         torch.cuda.synchronize()
@@ -537,13 +548,15 @@ class LikelihoodPlan:
             walk(s)
         return out
 
-    def _enqueue(self, ex, mv=None):
+    def _enqueue(self, ex, mv=None, fuse_update=True):
         """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
         (an nb_stretch describing a device-resident ensemble) the parameters are the
-        stretch-move proposals of the active half, computed by the set-up kernel, and the
-        combine kernel also accepts/rejects them and appends the chain."""
+        stretch-move proposals of the active half, computed by the set-up kernel, and
+        (fuse_update) the combine kernel also accepts/rejects them and appends the chain."""
         L, st, W = lib(), eng.stream(), ex.W
         n = 0
+        if mv is None and ex.pack is not None:
+            raise ValueError("a packed executable is driven by device-side proposals only")
         if mv is None:
             check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map,
                                    eng.ptr(ex.pm), ex.pri, ex.n_pri, eng.ptr(ex.prior),
@@ -588,20 +601,22 @@ class LikelihoodPlan:
             pdobj = self.pds[spec["pd"]][0]
             check(L.nb_pdist_eval_ld(PD_KIND[pdobj._kind], eng.ptr(ex.pd_block(spec["pd"])), W,
                                      eng.ptr(spec["e_d"]), spec["e_eV"].size, eng.ptr(buf),
-                                     self.row_width, st), "nb_pdist_eval_ld")
+                                     ex.row_ld, st), "nb_pdist_eval_ld")
             n += 1
         # last: with `mv` the combine kernel also moves the accepted walkers' records
         eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
                     prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
-                    mv=mv, pars_d=ex.pars, flux_ld=self.row_width)
+                    mv=mv if fuse_update else None, pars_d=ex.pars, flux_ld=ex.row_ld,
+                    lnp_ld=ex.lnp.stride(0))
         n += 1
         self.launches_per_eval = n
         return n
 
-    def executable(self, W):
-        if W not in self._exec:
-            self._exec[W] = self._build(W)
-        return self._exec[W]
+    def executable(self, W, pack=None):
+        key = W if pack is None else (W, pack.data_ptr())
+        if key not in self._exec:
+            self._exec[key] = self._build(W, pack)
+        return self._exec[key]
 
     # -- device-resident evaluation ---------------------------------------------------
     def run(self, ex):

@@ -13,6 +13,8 @@ rank with identical code, chains are bitwise identical for any world size.
 Backends: NCCL on device tensors (product), gloo on CPU tensors (host-logic
 tests with a stand-in evaluator; the product path has no CPU compute).
 """
+import ctypes
+
 import numpy as np
 
 from .sampler import DeviceEnsemble, EnsembleSampler
@@ -95,89 +97,71 @@ class ShardedSampler(EnsembleSampler):
 
 
 class ShardedDeviceEnsemble(DeviceEnsemble):
-    """Device-resident ensemble step with the likelihood plan sharded over ranks:
-    per half-step  propose (replicated) -> plan on this rank's rows -> all-gather
-    of [lnp | flux] rows over NCCL -> accept (replicated)."""
+    """Device-resident ensemble step with the half-ensemble's proposals sharded over ranks.
 
-    def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None):
-        import torch
+    Per half-step, on every rank:
+      set-up kernel (+ the proposals [lo, lo + per) of the half, computed in place)
+      -> radiative components -> combine, writing packed records
+         [blob record | lnprob | proposal] straight into this rank's slice of the gather buffer
+      -> ONE in-place all-gather of the slices (NCCL over NVLink)
+      -> accept step + chain append for all proposals (replicated, identical on every rank).
+    The whole ensemble step (both halves, both collectives) is one CUDA-graph replay."""
 
+    def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
+                 use_graph=True):
         from . import engine as eng
 
         if seed is None:
             raise ValueError("ShardedDeviceEnsemble needs an explicit seed shared by all ranks")
         self.group = group
         self.rank, self.world = world_info(group)
-        super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=store_blobs,
-                         use_graph=False)
+        super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=True, use_graph=use_graph)
         self.per, self.bounds = shard_bounds(self.Ns, self.world)
-        self.ex = plan.executable(self.per)
-        self.q_full = eng.zeros(self.per * self.world, self.P)
-        self.ncol = 1 + self.nb
-        self.pack_local = eng.zeros(self.per, self.ncol)
-        self.pack_full = eng.zeros(self.per * self.world, self.ncol)
-        self.lnp_full = eng.zeros(self.per * self.world)
-        self.flux_full = eng.zeros(self.per * self.world, max(self.nb, 1))
-        self.collectives = 0
         if self.per * self.world != self.Ns:
             raise ValueError("the half-ensemble (%d) must divide evenly over %d ranks"
                              % (self.Ns, self.world))
-        self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 2) + 1
-        self._torch = torch
+        self.ld = plan.pack_width()
+        self.pack_full = eng.zeros(self.Ns, self.ld)
+        lo = self.rank * self.per
+        self.pack_local = self.pack_full[lo:lo + self.per]
+        self.ex = plan.executable(self.per, pack=self.pack_local)
+        self.collectives = 0
+        self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 1)
 
-    def set_state(self, coords):
-        """Evaluate the initial ensemble sharded, then replicate."""
+    def set_state(self, coords, log_prob=None, rows=None):
+        """Evaluate the initial ensemble sharded (unless given), then replicate."""
         from . import engine as eng
 
         coords = np.ascontiguousarray(coords, dtype=float)
-        W = coords.shape[0]
-        per, bounds = shard_bounds(W, self.world)
-        if per * self.world != W:
-            raise ValueError("walkers must divide evenly over ranks")
-        lo, hi = bounds[self.rank]
-        lnp, rows = self.plan.eval_rows(coords[lo:hi])
-        pack = np.concatenate([lnp[:, None], rows], axis=1)
-        if self.world > 1:
-            dist = _dist()
-            local = eng.to_dev(pack)
-            full = eng.zeros(W, pack.shape[1])
-            dist.all_gather_into_tensor(full, local, group=self.group)
-            pack = full.cpu().numpy()
-        if np.any(np.isnan(pack[:, 0])):
-            raise ValueError("The initial log_prob was NaN")
-        self.coords.copy_(eng.to_dev(coords))
-        self.lp.copy_(eng.to_dev(pack[:, 0].copy()))
-        if self.nb:
-            self.blobs.copy_(eng.to_dev(np.ascontiguousarray(pack[:, 1:])))
-        self.n_acc.zero_()
+        if log_prob is None or rows is None:
+            W = coords.shape[0]
+            per, bounds = shard_bounds(W, self.world)
+            if per * self.world != W:
+                raise ValueError("walkers must divide evenly over ranks")
+            lo, hi = bounds[self.rank]
+            lnp, rws = self.plan.eval_rows(coords[lo:hi])
+            pack = np.concatenate([lnp[:, None], rws], axis=1)
+            if self.world > 1:
+                dist = _dist()
+                local = eng.to_dev(pack)
+                full = eng.zeros(W, pack.shape[1])
+                dist.all_gather_into_tensor(full, local, group=self.group)
+                pack = full.cpu().numpy()
+            log_prob, rows = pack[:, 0].copy(), np.ascontiguousarray(pack[:, 1:])
+        super().set_state(coords, log_prob, rows)
 
     def _enqueue_step(self):
         from . import engine as eng
         from ._lib import check, lib
 
-        L, ptr, ex = lib(), eng.ptr, self.ex
-        lo = self.rank * self.per
+        L = lib()
         for split in range(2):
-            check(L.nb_stretch_move(ptr(self.coords), self.P, self.Ns, split, ptr(self.step),
-                                    ptr(self.s_idx), ptr(self.c_idx), ptr(self.zz),
-                                    ptr(self.q_full), eng.stream()), "nb_stretch_move")
-            ex.pars.copy_(self.q_full[lo:lo + self.per])
-            self.plan._enqueue(ex)
+            mv = self._stretch(split)
+            mv.i0, mv.pars_ld = self.rank * self.per, self.ld
+            self.plan._enqueue(self.ex, mv=mv, fuse_update=False)
             if self.world > 1:
-                self.pack_local[:, 0].copy_(ex.lnp)
-                if self.nb:
-                    self.pack_local[:, 1:].copy_(ex.row)
                 _dist().all_gather_into_tensor(self.pack_full, self.pack_local, group=self.group)
                 self.collectives += 1
-                self.lnp_full.copy_(self.pack_full[:, 0])
-                if self.nb:
-                    self.flux_full.copy_(self.pack_full[:, 1:])
-                new_lp, new_bl = self.lnp_full, self.flux_full
-            else:
-                new_lp, new_bl = ex.lnp, ex.row
-            check(L.nb_stretch_update(
-                ptr(self.coords), ptr(self.lp), ptr(self.blobs) if self.nb else None, self.nb,
-                self.W, self.P, self.Ns, split, ptr(self.step), ptr(self.s_idx), ptr(self.zz),
-                ptr(self.lnu), ptr(self.q_full), ptr(new_lp), ptr(new_bl) if self.nb else None,
-                ptr(self.n_acc), ptr(self.chain), ptr(self.chain_lp),
-                ptr(self.chain_blobs) if self.nb else None, eng.stream()), "nb_stretch_update")
+            check(L.nb_stretch_update_packed(ctypes.byref(self._stretch(split)),
+                                             eng.ptr(self.pack_full), self.ld, eng.stream()),
+                  "nb_stretch_update_packed")

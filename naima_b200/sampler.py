@@ -571,10 +571,19 @@ class PlanSampler(EnsembleSampler):
     the chain is identical to the host-driven sampler's for the same seed."""
 
     def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=16, chunk=256,
-                 blobs_dtype=None, **kwargs):
+                 blobs_dtype=None, group=None, sharded=None, **kwargs):
         self.plan = plan
         self.block, self.chunk = int(block), int(chunk)
         self._de = None
+        self.group = group
+        if sharded is None:
+            import torch.distributed as dist
+
+            sharded = dist.is_available() and dist.is_initialized() and \
+                dist.get_world_size(group) > 1
+        if sharded and seed is None:
+            raise ValueError("a sharded PlanSampler needs an explicit seed shared by all ranks")
+        self.sharded = bool(sharded)
         super().__init__(nwalkers, ndim, self._log_prob, a=a, vectorize=True,
                          blobs_dtype=blobs_dtype, seed=seed, **kwargs)
 
@@ -589,7 +598,13 @@ class PlanSampler(EnsembleSampler):
 
     def _device(self):
         if self._de is None:
-            self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
+            if self.sharded:  # proposals of each half-ensemble sharded over the ranks
+                from .parallel import ShardedDeviceEnsemble
+
+                self._de = ShardedDeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0,
+                                                 group=self.group)
+            else:
+                self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
             self._de._random = self._random  # one stream, shared with the host-side API
             self._de.min_block = self.chunk
         return self._de

@@ -192,7 +192,7 @@ void emu_combine_lnprob(const nb_term* terms, int n_terms, int W, int N_E,
   for (int t = 0; t < n_terms; ++t) a.terms[t] = terms[t];
   a.n_terms = n_terms; a.W = W; a.N_E = N_E; a.unit_fac = unit_fac;
   a.data_flux = data_flux; a.err_lo = err_lo; a.err_hi = err_hi; a.ul = ul; a.cl = cl;
-  a.prior = prior; a.flux_model = flux_model; a.flux_ld = N_E; a.lnp = lnp;
+  a.prior = prior; a.flux_model = flux_model; a.flux_ld = N_E; a.lnp = lnp; a.lnp_ld = 1;
   for (int w = 0; w < W; ++w) combine_lnprob_walker(a, w);
 }
 
