@@ -360,48 +360,67 @@ def run_native(args):
     # ---- roofline of the dominant kernel (rank 0, N = 1 shapes) ------------------------
     ex = plan.executable(W_PER_GPU // 2)
     comps = {c["kind"] + str(i): (c, out) for i, (c, out) in enumerate(zip(plan.comps, ex.outs))}
-    kt = {}
-    for name, (c, out) in comps.items():
-        p = ex.preps[c["prep"]]
-        if c["kind"] == "syn":
-            fn = (lambda c=c, p=p, out=out:
-                  eng.synchrotron(p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=out))
-        else:
-            fn = (lambda c=c, p=p, out=out: eng.contract(c["table"], p, out=out))
-        kt[name] = time_kernel(fn, flush=flush)
+    # per-kernel device times IN SEQUENCE (set-up -> components -> combine), CUDA events
+    # between the launches; the L2 flush in front doubles as a blocker that keeps the GPU
+    # busy while the host enqueues, so host launch latency does not leak into the numbers
+    kt, reps_k = {}, 40
+    stages = plan.stages(ex)
+    for it in range(reps_k + 5):
+        flush_buf.zero_()
+        flush_buf.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
+        evs[0].record()
+        for k, (name, fn) in enumerate(stages):
+            fn()
+            evs[k + 1].record()
+        torch.cuda.synchronize()
+        if it >= 5:
+            for k, (name, fn) in enumerate(stages):
+                kt[name] = kt.get(name, 0.0) + evs[k].elapsed_time(evs[k + 1]) / reps_k
     t_eval = time_kernel(lambda: plan.run(ex), flush=flush)
-    dom = max(kt, key=kt.get)
-    c, out = comps[dom]
-    p = ex.preps[c["prep"]]
-    g = p.grid
-    Wh = ex.W
-    if c["kind"] == "syn":
-        kname = "synchrotron_kernel"
-        bytes_alg = 8 * (2 * Wh * g.N + 3 * g.N + Wh + plan.N_E + Wh * plan.N_E)
-        cells = Wh * plan.N_E * g.N
-        flops_cell = 320
-    else:
-        kname = "contract_kernel (IC, 3 seeds)"
-        R = c["table"].R
-        bytes_alg = 8 * (2 * R * g.N + 2 * Wh * g.N + g.N + R + Wh * R)
-        cells = Wh * R * g.N
-        flops_cell = 164
+    # The roofline object is for the IC integration kernel (BASELINE.json names it); the
+    # synchrotron kernel's figures ride along in roofline_fp64.
     peak, peak_src = measured_peaks()
-    t_dom = kt[dom] * 1e-3
     fp64_peak = eng.fp64_peak_tflops()
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": bytes_alg / t_dom / 1e9,
-                "peak": peak, "unit": "GB/s", "frac": bytes_alg / t_dom / 1e9 / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_alg, "launch_us": 1e6 * t_dom,
-                "note": "fp64-pipe bound by construction (arithmetic intensity >> 1e3 flop/B): "
-                        "see roofline_fp64 and DESIGN.md"}
-    roofline_fp64 = {"kernel": kname, "cells_per_launch": cells,
-                     "ref_order_flops_per_cell": flops_cell,
-                     "achieved_ref_order_tflops": cells * flops_cell / t_dom / 1e12,
-                     "peak_tflops_measured_dfma": fp64_peak,
-                     "frac_ref_order": cells * flops_cell / t_dom / 1e12 / fp64_peak,
-                     "cells_per_s": cells / t_dom,
-                     "kernel_us": {k: 1e3 * v for k, v in kt.items()},
+    Wh = ex.W
+    per_kernel = {}
+    for name, (c, out) in comps.items():
+        g = ex.preps[c["prep"]].grid
+        if c["kind"] == "syn":
+            kname = "synchrotron_kernel"
+            bytes_alg = 8 * (2 * Wh * g.N + 3 * g.N + Wh + plan.N_E + Wh * plan.N_E)
+            cells, flops_cell = Wh * plan.N_E * (g.N - 1), 320
+        else:
+            kname = "contract_kernel (IC, %d seed fields)" % c["table"].n_comp
+            R = c["table"].R
+            bytes_alg = 8 * (2 * R * g.N + 2 * Wh * g.N + g.N + R + Wh * R)
+            cells, flops_cell = Wh * R * (g.N - 1), 164
+        t = kt[name] * 1e-3
+        per_kernel[name] = {"kernel": kname, "launch_us": 1e6 * t, "cells_per_launch": cells,
+                            "algorithmic_bytes_per_launch": bytes_alg,
+                            "achieved_GBps": bytes_alg / t / 1e9,
+                            "ref_order_flops_per_cell": flops_cell,
+                            "achieved_ref_order_tflops": cells * flops_cell / t / 1e12,
+                            "frac_of_measured_dfma_peak": cells * flops_cell / t / 1e12 / fp64_peak,
+                            "cells_per_s": cells / t}
+    ic = next(v for k, v in per_kernel.items() if k.startswith("table"))
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "ncu_contract.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            pj = json.load(f)
+        traffic = pj["launches"][-1]["dram_bytes_per_launch"]
+        traffic_src = "profiles/ncu_contract.json (ncu --set full, same shapes, cold L2)"
+    roofline = {"bound": "hbm", "kernel": ic["kernel"], "achieved": ic["achieved_GBps"],
+                "peak": peak, "unit": "GB/s", "frac": ic["achieved_GBps"] / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ic["algorithmic_bytes_per_launch"],
+                "launch_us": ic["launch_us"],
+                "note": "the path is fp64-pipe / latency bound by construction (arithmetic "
+                        "intensity > 1e3 flop/B, everything L2 resident): the HBM fraction is "
+                        "small on purpose; see roofline_fp64 and DESIGN.md section 4"}
+    roofline_fp64 = {"peak_tflops_measured_dfma": fp64_peak, "kernels": per_kernel,
+                     "stage_us": {k: 1e3 * v for k, v in kt.items()},
                      "plan_eval_us": 1e3 * t_eval, "walkers_per_launch": Wh}
 
     # ---- CPU baseline (oracle port on the host cores; bounded sample) -----------------

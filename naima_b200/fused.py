@@ -612,6 +612,26 @@ class LikelihoodPlan:
         self.launches_per_eval = n
         return n
 
+    def stages(self, ex):
+        """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
+        stream (no forking): measurement aid for bench.py / tools/timeline.py."""
+        L, W = lib(), ex.W
+        out = [("walker_prep", lambda: check(L.nb_walker_prep(
+            eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
+            eng.ptr(ex.prior), ex.jobs, ex.n_jobs, eng.stream()), "nb_walker_prep"))]
+        for i, (c, o) in enumerate(zip(self.comps, ex.outs)):
+            p = ex.preps[c["prep"]]
+            if c["kind"] == "syn":
+                out.append(("syn%d" % i, lambda c=c, p=p, o=o: eng.synchrotron(
+                    p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=o)))
+            else:
+                out.append(("table%d" % i, lambda c=c, p=p, o=o: eng.contract(c["table"], p, out=o)))
+        out.append(("combine", lambda: eng.combine(
+            ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
+            prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
+            flux_ld=ex.row_ld, lnp_ld=ex.lnp.stride(0))))
+        return out
+
     def executable(self, W, pack=None):
         key = W if pack is None else (W, pack.data_ptr())
         if key not in self._exec:

@@ -26,20 +26,7 @@ L = lib()
 
 
 def stages():
-    st = eng.stream()
-    yield "walker_prep", lambda: check(L.nb_walker_prep(
-        eng.ptr(ex.pars), ex.W, plan.P, ex.map, ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
-        eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st))
-    for c, out in zip(plan.comps, ex.outs):
-        p = ex.preps[c["prep"]]
-        if c["kind"] == "syn":
-            yield "synchrotron", (lambda c=c, p=p, out=out: eng.synchrotron(
-                p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=out))
-        else:
-            yield "contract", (lambda c=c, p=p, out=out: eng.contract(c["table"], p, out=out))
-    yield "combine", lambda: eng.combine(
-        ex.terms, ex.W, plan.N_E, plan.unit_fac_d, flux_out=ex.row, data=plan.ddata,
-        prior_d=ex.prior, lnp_out=ex.lnp, flux_ld=plan.row_width)
+    return plan.stages(ex)
 
 
 for cold in (True, False):
