@@ -362,6 +362,41 @@ int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
 int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int ld,
                              void* stream);
 
+/* --- self-contained component kernels -------------------------------------------
+ * nb_contract / nb_synchrotron with the walker's operands derived INSIDE the kernel from
+ * the raw parameters (each warp / CTA repeats the few-hundred-instruction parameter map
+ * and evaluates the particle distribution at the nodes it integrates), so that a
+ * likelihood evaluation needs no set-up launch in front of its components.
+ *   src: where the parameters come from -- pars[W][P] (dense), or, with mv != NULL, the
+ *        stretch-move proposals of the active half (as nb_walker_prep_move);
+ *        map_host/n_map as nb_param_map (dst_off / dst_stride identify the entries:
+ *        parameter k of the distribution is the entry with dst_off == pd_off + k and
+ *        dst_stride == NB_PD_MAXPAR).  P <= 32 and n_map <= 32.
+ *   pd:  the particle distribution and the grid's walker-independent tables
+ *        (lnx[j] = ln x[j]). */
+typedef struct nb_walker_src {
+  const double* pars;
+  int P;
+  int n_map;
+  const nb_parmap* map_host;
+  const nb_stretch* mv_host; /* NULL: parameters from `pars` */
+} nb_walker_src;
+typedef struct nb_pd_desc {
+  int kind;          /* NB_PD_* */
+  int pad_;
+  long long pd_off;
+  double e_mul1, e_mul2, n_scale;
+  const double* lnx;    /* [N] */
+  const double* invdlx; /* [N-1] */
+} nb_pd_desc;
+int nb_contract_fused(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
+                      const double* lrs, int R, int N, int pitch, int W, const double* dlx,
+                      const double* xgrid, const double* coef, double* out, void* stream);
+/* b_entry: index of the map entry holding B [G] */
+int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
+                         const double* gam, int N, const double* dlx, int W,
+                         const double* E_erg, int N_E, double* out, void* stream);
+
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;
  * the caller times it with CUDA events to obtain the fp64 roofline denominator. */

@@ -50,6 +50,16 @@ class nb_stretch(ctypes.Structure):
                 ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp)]
 
 
+class nb_walker_src(ctypes.Structure):
+    _fields_ = [("pars", vp), ("P", c_int), ("n_map", c_int),
+                ("map_host", ctypes.POINTER(nb_parmap)), ("mv_host", ctypes.POINTER(nb_stretch))]
+
+
+class nb_pd_desc(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("pad_", c_int), ("pd_off", c_ll), ("e_mul1", c_dbl),
+                ("e_mul2", c_dbl), ("n_scale", c_dbl), ("lnx", vp), ("invdlx", vp)]
+
+
 # name -> (argtypes); every function returns int
 PROTOTYPES = {
     "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
@@ -83,6 +93,10 @@ PROTOTYPES = {
     "nb_combine_lnprob_ld": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp,
                              vp, vp, vp, c_int, vp, c_int, vp],
     "nb_stretch_update_packed": [ctypes.POINTER(nb_stretch), vp, c_int, vp],
+    "nb_contract_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), vp, vp, c_int,
+                          c_int, c_int, c_int, vp, vp, vp, vp, vp],
+    "nb_synchrotron_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), c_int, vp,
+                             c_int, vp, c_int, vp, c_int, vp, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

@@ -770,6 +770,240 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------
+// self-contained component kernels: walker parameters derived per warp
+// ---------------------------------------------------------------------------
+struct WalkerSrc {
+  ParamMapArgs pm;  // pars / P / map / n_out (out, priors unused)
+  int has_mv;
+  nb_stretch mv;
+};
+
+struct PdDesc {
+  int kind;
+  long long pd_off;
+  double e_mul1, e_mul2, n_scale;
+  const double* lnx;
+  const double* invdlx;
+};
+
+// All 32 lanes of a warp cooperate and all receive: the NB_PD_MAXPAR parameters of the
+// distribution block at pd_off and the mapped value of entry scalar_entry, for walker w.
+__device__ __forceinline__ void warp_walker_params(const WalkerSrc& s, int w, long long pd_off,
+                                                   int scalar_entry, double* pp,
+                                                   double* scalar) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int P = s.pm.P;
+  double qv = 0.0;
+  if (lane < P) {
+    if (s.has_mv) {
+      const size_t base = ((size_t)(*s.mv.step) * 2 + s.mv.split) * s.mv.Ns + s.mv.i0 + w;
+      double c = s.mv.coords[(size_t)s.mv.c_idx[base] * P + lane];
+      double sv = s.mv.coords[(size_t)s.mv.s_idx[base] * P + lane];
+      qv = __dsub_rn(c, __dmul_rn(__dsub_rn(c, sv), s.mv.zz[base]));
+    } else {
+      qv = s.pm.pars[(size_t)w * P + lane];
+    }
+  }
+  const bool active = lane < s.pm.n_out;
+  int src = 0, fn = 0, stride = 0;
+  long long off = -1;
+  double scale = 0.0;
+  if (active) {
+    const nb_parmap& m = s.pm.map[lane];
+    src = m.src;
+    fn = m.fn;
+    scale = m.scale;
+    off = m.dst_off;
+    stride = m.dst_stride;
+  }
+  double x = __shfl_sync(FULL, qv, src >= 0 ? src : 0);
+  double v = scale;
+  if (active && src >= 0) {
+    if (fn == NB_FN_POW10) x = exp10(x);
+    else if (fn == NB_FN_EXP) x = exp(x);
+    v = x * scale;
+  }
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) {
+    const bool mine = active && stride == PD_MAXPAR && off == pd_off + k;
+    const unsigned b = __ballot_sync(FULL, mine);
+    const double t = __shfl_sync(FULL, v, b ? (__ffs(b) - 1) : 0);
+    pp[k] = b ? t : 0.0;
+  }
+  const double sc = __shfl_sync(FULL, v, scalar_entry >= 0 ? scalar_entry : 0);
+  *scalar = scalar_entry >= 0 ? sc : 0.0;
+}
+
+struct ContractFusedArgs {
+  ContractArgs a;  // xn / ds1 / wpitch unused
+  WalkerSrc src;
+  PdDesc pd;
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256, 3) contract_fused_kernel(
+    const __grid_constant__ ContractFusedArgs fa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ PdLog s_S[8];  // per warp: keeps the distribution constants out of registers
+  const ContractArgs& a = fa.a;
+  double* sK = reinterpret_cast<double*>(smem_raw);
+  double* sL = sK + (size_t)RT * a.pitch;
+  double* sX = sL + (size_t)RT * a.pitch;  // grid tables: x, ln x, dlx, invdlx
+  double* sLX = sX + a.pitch;
+  double* sDL = sLX + a.pitch;
+  double* sIDL = sDL + a.pitch;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sIDL + a.pitch);
+
+  const int row0 = blockIdx.x * RT;
+  const int nrows = min(RT, a.R - row0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbarrier_init(bar, 1);
+    ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = (uint32_t)nrows * (uint32_t)a.pitch * 8u;
+    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar,
+                                   2u * bytes);
+    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK,
+                       a.K + (size_t)row0 * a.pitch, bytes, bar);
+    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL,
+                       a.lrs + (size_t)row0 * a.pitch, bytes, bar);
+  }
+  for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
+    sX[j] = a.xgrid[j];
+    sLX[j] = fa.pd.lnx[j];
+    if (j < a.N - 1) {
+      sDL[j] = a.dlx[j];
+      sIDL[j] = fa.pd.invdlx[j];
+    }
+  }
+  __syncthreads();
+  while (!ptx::mbarrier_try_wait_parity(bar, 0)) {
+  }
+
+  const int nint = a.N - 1;
+  const int i0 = lane * a.m;
+  const int i1 = min(i0 + a.m, nint);
+  const int wbeg = blockIdx.y * a.w_per_cta;
+  const int wend = min(wbeg + a.w_per_cta, a.W);
+  const int nwarps = blockDim.x >> 5;
+  for (int w = wbeg + warp; w < wend; w += nwarps) {
+    double pp[PD_MAXPAR], unused;
+    warp_walker_params(fa.src, w, fa.pd.pd_off, -1, pp, &unused);
+    if (lane == 0) {
+      PdLog S = pd_log_setup(fa.pd.kind, pp, fa.pd.n_scale);
+      pd_log_setup_grid(S, fa.pd.e_mul1, fa.pd.e_mul2);
+      s_S[warp] = S;
+    }
+    __syncwarp();
+    double acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+    if (i0 < nint)
+      contract_lane_selfprep<RT>(s_S[warp], sX, sLX, sDL, sIDL, sK, sL, a.pitch, i0, i1, acc);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      double v = warp_sum(acc[r]);
+      if (lane == 0 && r < nrows) {
+        int row = row0 + r;
+        if (a.coef) v *= a.coef[row];
+        a.out[(size_t)w * a.R + row] = v;
+      }
+    }
+  }
+}
+
+struct SynFusedArgs {
+  SynArgs a;  // xn / ds1 / wpitch / B / invdlx unused
+  WalkerSrc src;
+  PdDesc pd;
+  int b_entry;
+};
+
+__global__ void __launch_bounds__(256) synchrotron_fused_kernel(
+    const __grid_constant__ SynFusedArgs fa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SynArgs& a = fa.a;
+  double* s_iec = reinterpret_cast<double*>(smem_raw);
+  double* s_cb = s_iec + a.N;
+  double* s_xn = s_cb + a.N;
+  double* s_ds = s_xn + a.N;
+  double* s_idl = s_ds + a.N;
+  double* s_dl = s_idl + a.N;
+  int* s_js = reinterpret_cast<int*>(s_dl + a.N);  // [e_per_cta]
+  __shared__ int s_jmin;
+  __shared__ double s_B;
+  __shared__ PdLog s_S;
+
+  const int w = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nint = a.N - 1;
+  const int nsl = gridDim.y;
+  const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
+  if (warp == 0) {
+    double pp[PD_MAXPAR], Bv;
+    warp_walker_params(fa.src, w, fa.pd.pd_off, fa.b_entry, pp, &Bv);
+    if (lane == 0) {
+      PdLog S = pd_log_setup(fa.pd.kind, pp, fa.pd.n_scale);
+      pd_log_setup_grid(S, fa.pd.e_mul1, fa.pd.e_mul2);
+      s_S = S;
+      s_B = Bv;
+      s_jmin = a.N;
+    }
+  }
+  __syncthreads();
+  const double Bw = s_B;
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[blockIdx.y + k * nsl]);
+    s_js[k] = js;
+    atomicMin(&s_jmin, js);
+  }
+  __syncthreads();
+  const int jmin = s_jmin;
+  for (int j = jmin + threadIdx.x; j < a.N; j += blockDim.x) {
+    const double g = a.gam[j];
+    syn_node(g, Bw, &s_iec[j], &s_cb[j]);
+    const PdNode nd = pd_log_node_tab(s_S, g, fa.pd.lnx[j]);
+    s_xn[j] = g * pd_log_value_fast(s_S, nd);
+    if (j < nint) {
+      const double idl = fa.pd.invdlx[j];
+      const PdNode nd2 = pd_log_node_tab(s_S, a.gam[j + 1], fa.pd.lnx[j + 1]);
+      s_ds[j] = pd_log_ds1(s_S, nd, nd2, idl);
+      s_idl[j] = idl;
+      s_dl[j] = a.dlx[j];
+    }
+  }
+  __syncthreads();
+
+  double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
+  const int pair = warp >> 1, half = warp & 1;
+  for (int k = pair; k < ne; k += 4) {
+    const double E = a.E_erg[blockIdx.y + k * nsl];
+    const int js = s_js[k];
+    const int len = nint - js;
+    double acc = 0.0;
+    if (len > 0) {
+      const int m = odd_chunk2(len);
+      const int i0 = js + (half * 32 + lane) * m;
+      const int i1 = min(i0 + m, nint);
+      if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) s_part[2 * k + half] = acc;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+    const int e = blockIdx.y + k * nsl;
+    const double acc = s_part[2 * k] + s_part[2 * k + 1];
+    a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, a.E_erg[e], acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // IC on a tabulated seed, fused: CTA = (photon energy e, walker w)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ic_seed_spectrum_kernel(
@@ -1220,6 +1454,133 @@ int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1
   }
   dim3 grid(W, (N_E + epc - 1) / epc);
   synchrotron_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill_walker_src(WalkerSrc& s, const nb_walker_src* src, int W) {
+  if (!src || src->P < 1 || src->P > 32 || src->n_map < 0 || src->n_map > 32 ||
+      (src->n_map > 0 && !src->map_host) || (!src->mv_host && !src->pars))
+    return NB_EINVAL;
+  for (int k = 0; k < src->n_map; ++k) {
+    s.pm.map[k] = src->map_host[k];
+    if (s.pm.map[k].src >= src->P || s.pm.map[k].fn < 0 || s.pm.map[k].fn > NB_FN_EXP)
+      return NB_EINVAL;
+  }
+  s.pm.n_out = src->n_map;
+  s.pm.n_pri = 0;
+  s.pm.W = W;
+  s.pm.P = src->P;
+  s.pm.pars = src->pars;
+  s.pm.out = nullptr;
+  s.pm.prior_out = nullptr;
+  s.has_mv = src->mv_host ? 1 : 0;
+  if (src->mv_host) {
+    const nb_stretch* mv = src->mv_host;
+    if (!mv->coords || !mv->step || !mv->s_idx || !mv->c_idx || !mv->zz || mv->P != src->P ||
+        mv->i0 < 0 || mv->i0 + W > mv->Ns || mv->split < 0 || mv->split > 1)
+      return NB_EINVAL;
+    s.mv = *mv;
+  }
+  return 0;
+}
+
+static int fill_pd_desc(PdDesc& d, const nb_pd_desc* pd) {
+  if (!pd || pd->kind < 0 || pd->kind > NB_PD_LOGPAR || pd->pd_off < 0 || !pd->lnx || !pd->invdlx)
+    return NB_EINVAL;
+  d.kind = pd->kind;
+  d.pd_off = pd->pd_off;
+  d.e_mul1 = pd->e_mul1;
+  d.e_mul2 = pd->e_mul2;
+  d.n_scale = pd->n_scale;
+  d.lnx = pd->lnx;
+  d.invdlx = pd->invdlx;
+  return 0;
+}
+
+}  // extern "C"
+
+template <int RT>
+static int launch_contract_fused(const ContractFusedArgs& fa, int smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(contract_fused_kernel<RT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const ContractArgs& a = fa.a;
+  dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
+  contract_fused_kernel<RT><<<grid, 256, smem, st>>>(fa);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" {
+
+int nb_contract_fused(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
+                      const double* lrs, int R, int N, int pitch, int W, const double* dlx,
+                      const double* xgrid, const double* coef, double* out, void* stream) {
+  if (!K || !lrs || !dlx || !xgrid || !out || R < 1 || N < 2 || pitch < N || W < 0)
+    return NB_EINVAL;
+  if ((pitch & 1) || ((uintptr_t)K & 15) || ((uintptr_t)lrs & 15)) return NB_EALIGN;
+  ContractFusedArgs fa;
+  int rc = fill_walker_src(fa.src, src, W);
+  if (rc) return rc;
+  rc = fill_pd_desc(fa.pd, pd);
+  if (rc) return rc;
+  if (W == 0) return 0;
+  ContractArgs& a = fa.a;
+  a.K = K; a.lrs = lrs; a.R = R; a.N = N; a.pitch = pitch;
+  a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0; a.W = W;
+  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out;
+  a.m = odd_chunk(N - 1);
+  long long row_bytes = 2LL * pitch * 8, grid_bytes = 4LL * pitch * 8;
+  int RT = 8;
+  while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
+  if (RT * row_bytes + grid_bytes + 16 > 224 * 1024) return NB_ETOOLARGE;
+  int smem = (int)(RT * row_bytes + grid_bytes + 16);
+  int row_tiles = (R + RT - 1) / RT;
+  int wpc = 8;
+  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 4 * 148) wpc <<= 1;
+  a.w_per_cta = wpc;
+  cudaStream_t st = as_stream(stream);
+  if (RT == 8) return launch_contract_fused<8>(fa, smem, st);
+  if (RT == 4) return launch_contract_fused<4>(fa, smem, st);
+  return launch_contract_fused<2>(fa, smem, st);
+}
+
+int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
+                         const double* gam, int N, const double* dlx, int W,
+                         const double* E_erg, int N_E, double* out, void* stream) {
+  if (!gam || !dlx || !E_erg || !out || N < 2 || W < 0 || N_E < 1 || b_entry < 0)
+    return NB_EINVAL;
+  SynFusedArgs fa;
+  int rc = fill_walker_src(fa.src, src, W);
+  if (rc) return rc;
+  if (b_entry >= fa.src.pm.n_out) return NB_EINVAL;
+  rc = fill_pd_desc(fa.pd, pd);
+  if (rc) return rc;
+  if (W == 0) return 0;
+  fa.b_entry = b_entry;
+  SynArgs& a = fa.a;
+  a.gam = gam; a.N = N; a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0;
+  a.invdlx = pd->invdlx; a.dlx = dlx; a.B = nullptr; a.W = W; a.E_erg = E_erg; a.N_E = N_E;
+  a.out = out;
+  int epc = (N_E + 7) & ~7;
+  while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
+  a.e_per_cta = epc;
+  long long smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
+  if (smem > 224 * 1024) return NB_ETOOLARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(synchrotron_fused_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(W, (N_E + epc - 1) / epc);
+  synchrotron_fused_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(fa);
   NB_CHECK_LAUNCH();
   return 0;
 }

@@ -185,6 +185,8 @@ struct PdLog {
   double ec;     // e_cutoff
   double beta;   // cutoff exponent, or LogParabola curvature
   bool cutoff, broken;
+  // grid-relative constants for pd_log_node_tab (e = x * m with m = e_mul1 * e_mul2)
+  double m, lnme0, mec, lnmec;  // m, ln(m / e_0), m / e_c, ln(m / e_c)
 };
 
 struct PdNode {
@@ -224,6 +226,31 @@ NB_HD PdLog pd_log_setup(int kind, const double* p, double n_scale) {
   return s;
 }
 
+// grid-relative constants: with them a node costs no log (ln x comes from the grid's
+// walker-independent table) and, for beta == 1, a single exp
+NB_HD void pd_log_setup_grid(PdLog& s, double e_mul1, double e_mul2) {
+  s.m = e_mul1 * e_mul2;
+  s.lnme0 = log(s.m / s.e0);
+  s.mec = s.m / s.ec;
+  s.lnmec = log(s.mec);
+}
+
+// node x of a grid whose ln(x) is tabulated
+NB_HD PdNode pd_log_node_tab(const PdLog& s, double x, double lnx) {
+  PdNode nd;
+  nd.L = lnx + s.lnme0;
+  nd.side = (s.broken && !(x * s.m < s.eb)) ? 1 : 0;
+  nd.c = 0.0;
+  if (s.cutoff) nd.c = (s.beta == 1.0) ? x * s.mec : exp(s.beta * (lnx + s.lnmec));
+  if (s.kind == PD_LOGPAR)
+    nd.P = s.lnA - (s.a1 + s.beta * nd.L) * nd.L;
+  else if (nd.side)
+    nd.P = (s.lnA + s.lnK) - s.a2 * nd.L;
+  else
+    nd.P = s.lnA - s.a1 * nd.L;
+  return nd;
+}
+
 // e: node energy [eV]
 NB_HD PdNode pd_log_node(const PdLog& s, double e) {
   PdNode nd;
@@ -244,6 +271,11 @@ NB_HD PdNode pd_log_node(const PdLog& s, double e) {
 }
 
 NB_HD double pd_log_value(const PdLog& s, const PdNode& nd) { return s.sgn * exp(nd.P - nd.c); }
+
+// same through exp_neg (no libm call in the hot loops)
+NB_HD double pd_log_value_fast(const PdLog& s, const PdNode& nd) {
+  return s.sgn * exp_neg(nd.c - nd.P);
+}
 
 // d ln n / d ln x + 1 over the interval (a, b); invdlx = 1/ln(x_b/x_a)
 NB_HD double pd_log_ds1(const PdLog& s, const PdNode& a, const PdNode& b, double invdlx) {
@@ -752,6 +784,36 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
     n2 = n2n;
     d = dn;
     dl = dln;
+  }
+}
+
+// fast contraction with the walker's operands evaluated on the fly from the log-space
+// distribution (no set-up kernel, no operand arrays): xg / lnx / dlx / invdlx are the
+// grid's tables
+template <int RT>
+NB_HD void contract_lane_selfprep(const PdLog& S, const double* xg, const double* lnx,
+                                  const double* dlx, const double* invdlx, const double* sK,
+                                  const double* sL, int pitch, int i0, int i1, double* acc) {
+  double prev[RT];
+  double x1 = xg[i0];
+  PdNode nd1 = pd_log_node_tab(S, x1, lnx[i0]);
+  double n1 = x1 * pd_log_value_fast(S, nd1);
+#pragma unroll
+  for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
+  for (int i = i0; i < i1; ++i) {
+    const double x2 = xg[i + 1];
+    const PdNode nd2 = pd_log_node_tab(S, x2, lnx[i + 1]);
+    const double n2 = x2 * pd_log_value_fast(S, nd2);
+    const double d = pd_log_ds1(S, nd1, nd2, invdlx[i]);
+    const double dl = dlx[i];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      double xy2 = n2 * sK[r * pitch + i + 1];
+      double bp1 = d + sL[r * pitch + i];
+      acc[r] += interval_fast(prev[r], xy2, bp1, dl);
+      prev[r] = xy2;
+    }
+    nd1 = nd2;
   }
 }
 

@@ -92,7 +92,9 @@ class Grid:
         dlx[: self.N - 1] = np.log(self.x[1:] / self.x[:-1])
         inv = np.zeros(self.pitch)
         inv[: self.N - 1] = 1.0 / dlx[: self.N - 1]
-        self._host = (pad, dlx, inv)
+        lnx = np.zeros(self.pitch)
+        lnx[: self.N] = np.log(self.x)
+        self._host = (pad, dlx, inv, lnx)
         self._dev = None
         if species == "electron":  # e = (gam * mec2[erg]) * (erg -> eV); n per unit gam
             self.e_mul1, self.e_mul2, self.n_scale = mec2_erg, erg_eV, mec2_eV
@@ -110,6 +112,7 @@ class Grid:
     x_d = property(lambda self: self._device()[0])
     dlx_d = property(lambda self: self._device()[1])
     invdlx_d = property(lambda self: self._device()[2])
+    lnx_d = property(lambda self: self._device()[3])
 
 
 _GRIDS = OrderedDict()

@@ -23,7 +23,8 @@ import torch
 
 from . import engine as eng
 from . import units as u
-from ._lib import NB_PD_MAXPAR, PD_KIND, check, lib, nb_parmap, nb_prep_job, nb_prior
+from ._lib import (NB_PD_MAXPAR, PD_KIND, check, lib, nb_parmap, nb_pd_desc, nb_prep_job, nb_prior,
+                   nb_walker_src)
 from .units import Quantity, Unit
 
 FN_ID, FN_POW10, FN_EXP = 0, 1, 2
@@ -260,10 +261,12 @@ class _Exec:
 
 
 class LikelihoodPlan:
-    def __init__(self, model, prior, data, P, use_graph=True):
+    def __init__(self, model, prior, data, P, use_graph=True, selfprep=True):
         self.P = int(P)
         self.data = data
         self.use_graph = use_graph
+        self.selfprep = selfprep
+        self.selfprep_kinds = ("syn",)
         flux, blobs, sp = trace(model, prior, data, self.P)
         self.flux, self.blobs, self.prior = flux, blobs, sp
         E = Quantity(data["energy"])
@@ -375,6 +378,14 @@ class LikelihoodPlan:
             else:
                 raise TraceError("unsupported radiative class %r" % type(comp).__name__)
             self.comps.append(c)
+        # components whose kernels derive the walker's operands themselves (no set-up
+        # launch in front of them); the reference-order (exact) mode keeps the operand arrays
+        # Synchrotron only: its CTAs own one walker, so the operands cost one pass over the
+        # nodes; the contraction would repeat them in every row-tile CTA (+30 % work,
+        # measured slower than reading the arrays of the set-up kernel)
+        for c in self.comps:
+            c["selfprep"] = (self.selfprep and not exact and self.P <= 32
+                             and c["kind"] in self.selfprep_kinds)
         # blobs
         self.blob_specs = []
         for b in self.blobs:
@@ -428,6 +439,8 @@ class LikelihoodPlan:
             entries.append((v, sc_base + j * W, 1))
         if len(entries) > 32:
             raise TraceError("too many mapped parameters")
+        n_pd_entries = sum(len(vals) for _, vals in self.pds)
+        ex.scalar_entry = [n_pd_entries + j for j in range(len(self.scalars))]
         ex.map = (nb_parmap * max(len(entries), 1))()
         for k, (v, off, stride) in enumerate(entries):
             m = ex.map[k]
@@ -489,9 +502,26 @@ class LikelihoodPlan:
                                 else ex.row[:, off:off + width])
             if spec["kind"] == "pdist":
                 spec["e_d"] = eng.to_dev(spec["e_eV"])
+        # descriptors for the self-contained component kernels
+        ex.src = nb_walker_src()
+        ex.src.pars, ex.src.P, ex.src.n_map = ex.pars.data_ptr(), P, ex.n_map
+        ex.src.map_host = ctypes.cast(ex.map, ctypes.POINTER(nb_parmap))
+        ex.pd_desc = []
+        for prd in self.preps:
+            g = prd["grid"]
+            d = nb_pd_desc()
+            d.kind = PD_KIND[self.pds[prd["pd"]][0]._kind]
+            d.pd_off = prd["pd"] * W * NB_PD_MAXPAR
+            d.e_mul1, d.e_mul2, d.n_scale = g.e_mul1, g.e_mul2, g.n_scale
+            d.lnx, d.invdlx = g.lnx_d.data_ptr(), g.invdlx_d.data_ptr()
+            ex.pd_desc.append(d)
+        # operand arrays are only needed by components that do not prepare their own
+        needed = set(c["prep"] for c in self.comps if not c["selfprep"])
         # jobs of the fused per-walker set-up kernel
         jobs = []
-        for prd, p in zip(self.preps, ex.preps):
+        for ip, (prd, p) in enumerate(zip(self.preps, ex.preps)):
+            if ip not in needed:
+                continue
             g = prd["grid"]
             jobs.append(dict(kind=PD_KIND[self.pds[prd["pd"]][0]._kind], N=g.N,
                              pd_off=prd["pd"] * W * NB_PD_MAXPAR, x=g.x_d, invdlx=g.invdlx_d,
@@ -548,53 +578,109 @@ class LikelihoodPlan:
             walk(s)
         return out
 
-    def _enqueue(self, ex, mv=None, fuse_update=True):
-        """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
-        (an nb_stretch describing a device-resident ensemble) the parameters are the
-        stretch-move proposals of the active half, computed by the set-up kernel, and
-        (fuse_update) the combine kernel also accepts/rejects them and appends the chain."""
-        L, st, W = lib(), eng.stream(), ex.W
-        n = 0
-        if mv is None and ex.pack is not None:
-            raise ValueError("a packed executable is driven by device-side proposals only")
+    def _src(self, ex, mv):
+        """nb_walker_src of ex: dense parameters, or the proposals described by mv."""
+        if mv is None:
+            return ex.src
+        src = nb_walker_src()
+        src.pars, src.P, src.n_map, src.map_host = None, ex.src.P, ex.src.n_map, ex.src.map_host
+        src.mv_host = ctypes.pointer(mv)
+        return src
+
+    def _launch_prep(self, ex, mv):
+        """Parameter map + priors (+ proposals) published for the combine kernel, the
+        total-energy blobs, and the operand arrays of components that need them."""
+        L, W, st = lib(), ex.W, eng.stream()
         if mv is None:
             check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map,
                                    eng.ptr(ex.pm), ex.pri, ex.n_pri, eng.ptr(ex.prior),
                                    ex.jobs, ex.n_jobs, st), "nb_walker_prep")
         else:
-            check(L.nb_walker_prep_move(ctypes.byref(mv), eng.ptr(ex.pars), W, self.P, ex.map,
-                                        ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
+            check(L.nb_walker_prep_move(ctypes.byref(mv), eng.ptr(ex.pars), W, self.P,
+                                        ex.map, ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
                                         eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st),
                   "nb_walker_prep_move")
-        n += 1
-        def launch(c, out):
-            p = ex.preps[c["prep"]]
-            if c["kind"] == "syn":
-                eng.synchrotron(p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=out)
-            else:
-                eng.contract(c["table"], p, out=out)
 
-        # the radiative components are independent: fork them onto side streams (they
-        # become parallel branches of the captured graph) and join before the combine
+    def _launch_comp(self, ex, c, out, src):
+        L, W = lib(), ex.W
+        p = ex.preps[c["prep"]]
+        g = p.grid
+        if c["selfprep"]:
+            d = ex.pd_desc[c["prep"]]
+            if c["kind"] == "syn":
+                check(L.nb_synchrotron_fused(
+                    ctypes.byref(src), ctypes.byref(d), ex.scalar_entry[c["B"]],
+                    eng.ptr(g.x_d), g.N, eng.ptr(g.dlx_d), W, eng.ptr(ex.E_erg), self.N_E,
+                    eng.ptr(out), eng.stream()), "nb_synchrotron_fused")
+            else:
+                tb = c["table"]
+                check(L.nb_contract_fused(
+                    ctypes.byref(src), ctypes.byref(d), eng.ptr(tb.K), eng.ptr(tb.lrs), tb.R,
+                    g.N, g.pitch, W, eng.ptr(g.dlx_d), eng.ptr(g.x_d), eng.ptr(tb.coef),
+                    eng.ptr(out), eng.stream()), "nb_contract_fused")
+        elif c["kind"] == "syn":
+            eng.synchrotron(g, p, ex.scalar_col(c["B"]), ex.E_erg, out=out)
+        else:
+            eng.contract(c["table"], p, out=out)
+
+    def _enqueue(self, ex, mv=None, fuse_update=True):
+        """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
+        (an nb_stretch describing a device-resident ensemble) the parameters are the
+        stretch-move proposals of the active half, computed by the set-up kernel, and
+        (fuse_update) the combine kernel also accepts/rejects them and appends the chain."""
+        L, W = lib(), ex.W
+        n = 0
+        if mv is None and ex.pack is not None:
+            raise ValueError("a packed executable is driven by device-side proposals only")
+
+        src = self._src(ex, mv)
+
+        def prep():
+            self._launch_prep(ex, mv)
+
+        def launch(c, out):
+            self._launch_comp(ex, c, out, src)
+
+        # The set-up kernel and the radiative components fork onto side streams (parallel
+        # branches of the captured graph) and join before the combine.  Components that
+        # still consume operand arrays must follow the set-up kernel.
         comps = list(zip(self.comps, ex.outs))
         main = torch.cuda.current_stream()
+        dependent = [x for x in comps if not x[0]["selfprep"]]
+        free = [x for x in comps if x[0]["selfprep"]]
+        branches = [[prep] + [lambda c=c, o=o: launch(c, o) for c, o in dependent[:1]]]
+        branches += [[lambda c=c, o=o: launch(c, o)] for c, o in free]
+        extra_dep = dependent[1:]
         joins = []
-        if len(comps) > 1:
+        if len(branches) > 1 or extra_dep:
+            while len(self._side) < len(branches) + len(extra_dep):
+                self._side.append(torch.cuda.Stream())
             fork = torch.cuda.Event()
             fork.record(main)
-            while len(self._side) < len(comps) - 1:
-                self._side.append(torch.cuda.Stream())
-            for (c, out), side in zip(comps[1:], self._side):
+            for br, side in zip(branches[1:], self._side):
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
-                    launch(c, out)
+                    for f in br:
+                        f()
                     done = torch.cuda.Event()
                     done.record(side)
                 joins.append(done)
-        launch(*comps[0])
+        for f in branches[0]:
+            f()
+        if extra_dep:  # further operand-consuming components: fork after the set-up
+            after = torch.cuda.Event()
+            after.record(main)
+            for (c, o), side in zip(extra_dep, self._side[len(branches) - 1:]):
+                side.wait_event(after)
+                with torch.cuda.stream(side):
+                    launch(c, o)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                joins.append(done)
         for done in joins:
             main.wait_event(done)
-        n += len(comps)
+        n += 1 + len(comps)
+        L, st = lib(), eng.stream()
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
             if spec["kind"] != "pdist":
                 continue  # particle energies are jobs of nb_walker_prep
@@ -615,19 +701,12 @@ class LikelihoodPlan:
     def stages(self, ex):
         """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
         stream (no forking): measurement aid for bench.py / tools/timeline.py."""
-        L, W = lib(), ex.W
-        out = [("walker_prep", lambda: check(L.nb_walker_prep(
-            eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map, eng.ptr(ex.pm), ex.pri, ex.n_pri,
-            eng.ptr(ex.prior), ex.jobs, ex.n_jobs, eng.stream()), "nb_walker_prep"))]
+        out = [("walker_prep", lambda: self._launch_prep(ex, None))]
         for i, (c, o) in enumerate(zip(self.comps, ex.outs)):
-            p = ex.preps[c["prep"]]
-            if c["kind"] == "syn":
-                out.append(("syn%d" % i, lambda c=c, p=p, o=o: eng.synchrotron(
-                    p.grid, p, ex.scalar_col(c["B"]), ex.E_erg, out=o)))
-            else:
-                out.append(("table%d" % i, lambda c=c, p=p, o=o: eng.contract(c["table"], p, out=o)))
+            name = ("syn%d" if c["kind"] == "syn" else "table%d") % i
+            out.append((name, lambda c=c, o=o: self._launch_comp(ex, c, o, ex.src)))
         out.append(("combine", lambda: eng.combine(
-            ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
+            ex.terms, ex.W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
             prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
             flux_ld=ex.row_ld, lnp_ld=ex.lnp.stride(0))))
         return out

@@ -495,9 +495,12 @@ def test_lnprob_parity_paths(nb, mode, case):
             assert_allclose(r[0], want[w], rtol=LNP_RTOL)
         else:
             assert r[0] == -np.inf
-        # blob parity between the three paths: model flux and We
+        # blob parity between the three paths: model flux and We.  The plan's
+        # self-contained synchrotron kernel derives ln(e/e0) from the grid's ln x table, the
+        # class path from log(e/e0): few-ulp operand differences, amplified by 1/|b + 1|
+        # where the integrand slope b -> -1 (conditioning note)
         b_plan = plan.blobs_for(flux, blob_arrays, w)
-        assert_allclose(b_plan[0].value, r[1].value, rtol=1e-12)
+        assert_allclose(b_plan[0].value, r[1].value, rtol=1e-10)
         assert_allclose(blobs2[w][0].value, r[1].value, rtol=1e-12)
         assert_allclose(b_plan[-1].value, r[-1].value, rtol=1e-12)
         if case == "IC":
@@ -571,6 +574,58 @@ def test_priors(nb):
     fin = np.isfinite(want)
     assert np.array_equal(np.isfinite(lnp), fin)
     assert_allclose(lnp[fin], want[fin], rtol=LNP_RTOL)
+
+
+@pytest.mark.parametrize("kinds", [(), ("syn",), ("syn", "table")],
+                         ids=["operand-arrays", "syn-selfprep", "all-selfprep"])
+def test_selfprep_kernels_vs_oracle(nb, kinds):
+    """nb_contract_fused / nb_synchrotron_fused (operands derived inside the component
+    kernels) against the oracle, for every launch configuration of the plan."""
+    suz, hess = rxj_tables()
+    data = nb.validate_data_table([suz, hess])
+    rng = np.random.default_rng(11)
+    p_true = np.array([33.0, 2.5, np.log10(48.0), 20.0])
+    P = p_true * (1 + 0.1 * rng.normal(size=(24, 4)))
+    plan = nb.LikelihoodPlan(ElectronSynIC, lnprior_SynIC, data, 4)
+    for c in plan.comps:
+        c["selfprep"] = c["kind"] in kinds
+    lnp, flux, blobs = plan(P)
+    omodel, oprior = oracle_SynIC()
+    want, wflux = oracle_lnprob_batch(P, oracle_data(data), omodel, oprior)
+    assert_allclose(lnp, want, rtol=LNP_RTOL)
+    assert_allclose(flux, wflux, rtol=FLUX_RTOL)
+    # broken power law with cutoff + log-parabola through the same kernels
+    from naima_b200 import units as u
+    from naima_b200.models import (ExponentialCutoffBrokenPowerLaw, InverseCompton, LogParabola,
+                                   Synchrotron)
+
+    def model_bpl(pars, data):
+        pd = ExponentialCutoffBrokenPowerLaw(10 ** pars[0] / u.eV, 1 * u.TeV, 3 * u.TeV, pars[1],
+                                             3.2, (10 ** pars[2]) * u.TeV, 2.0)
+        return (InverseCompton(pd, seed_photon_fields=["CMB"], Eemin=100 * u.GeV).flux(data)
+                + Synchrotron(pd, B=pars[3] * u.uG).flux(data))
+
+    def model_lp(pars, data):
+        pd = LogParabola(10 ** pars[0] / u.eV, 10 * u.TeV, pars[1], 0.15)
+        return (InverseCompton(pd, seed_photon_fields=["CMB"], Eemin=100 * u.GeV).flux(data)
+                + Synchrotron(pd, B=pars[3] * u.uG).flux(data))
+
+    od = oracle_data(data)
+    for model, kind, args in (
+            (model_bpl, "ExponentialCutoffBrokenPowerLaw",
+             lambda p: (10 ** p[0], 1 * TeV, 3 * TeV, p[1], 3.2, 10 ** p[2] * TeV, 2.0)),
+            (model_lp, "LogParabola", lambda p: (10 ** p[0], 10 * TeV, p[1], 0.15))):
+        plan2 = nb.LikelihoodPlan(model, None, data, 4)
+        for c in plan2.comps:
+            c["selfprep"] = c["kind"] in kinds
+        _, f2, _ = plan2(P[:6])
+        for w in range(6):
+            pd = o.PDist(kind, *args(P[w]))
+            ref = (o.flux_from_spectrum(o.ic_spectrum(pd, od["E_eV"], ["CMB"], Eemin_eV=100e9),
+                                        o.kpc_cm)
+                   + o.flux_from_spectrum(o.synchrotron_spectrum(pd, od["E_eV"], P[w, 3] * 1e-6),
+                                          o.kpc_cm)) * od["unit_fac"]
+            assert_allclose(f2[w], ref, rtol=FLUX_RTOL)
 
 
 # ------------------------------------------------------------------------------
