@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = "walker-steps/sec (ensemble lnprob evals/s)"
 UNIT = "walker-steps/s"
 W_PER_GPU = 256
+FLUSH_MIB = 160  # > the 126 MB L2 of a B200
 
 
 def parse():
@@ -148,7 +149,7 @@ def workload_config(n_gpus, W):
                         "IC grid 370 nodes, synchrotron grid 570 nodes, P=4",
             "walkers": W, "walkers_per_gpu": W_PER_GPU, "n_photon_energies": 64,
             "parallelism": "walkers sharded over %d GPU(s)" % n_gpus,
-            "l2": "flushed between timed steps (256 MiB memset)"}
+            "l2": "flushed between timed steps (%d MiB memset > 126 MB L2)" % FLUSH_MIB}
 
 
 # ------------------------------------------------------------------------------------
@@ -251,7 +252,7 @@ def run_native(args):
     data = nb.validate_data_table([xt, gt])
     plan = nb.LikelihoodPlan(wl.c3_model, wl.c3_prior, data, 4)
     p0 = wl.walkers(wl.C3_PTRUE, W)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush_buf = torch.empty(FLUSH_MIB << 20, dtype=torch.uint8, device="cuda")
 
     def flush():
         if not args.no_flush:

@@ -535,14 +535,22 @@ class LikelihoodPlan:
                                  e_mul1=g.e_mul1, e_mul2=g.e_mul2, n_scale=g.n_scale,
                                  x_to_energy=g.x_to_erg, energy_out=buf,
                                  energy_stride=ex.row_ld))
-        if len(jobs) > 8:
-            raise TraceError("too many particle-distribution jobs in one plan")
-        ex.jobs = (nb_prep_job * max(len(jobs), 1))()
-        for k, jd in enumerate(jobs):
-            J = ex.jobs[k]
-            for name, v in jd.items():
-                setattr(J, name, v.data_ptr() if hasattr(v, "data_ptr") else v)
-        ex.n_jobs = len(jobs)
+        # two launches of the set-up kernel: the operand jobs (and the published parameter
+        # map / priors / proposals) gate the contraction; the total-energy blobs (reference-
+        # order log10/pow integration, the slowest CTAs by far) only gate the combine and run
+        # on a side branch with scratch outputs for the duplicate parameter map
+        def job_array(js):
+            if len(js) > 8:
+                raise TraceError("too many particle-distribution jobs in one plan")
+            arr = (nb_prep_job * max(len(js), 1))()
+            for k, jd in enumerate(js):
+                for name, v in jd.items():
+                    setattr(arr[k], name, v.data_ptr() if hasattr(v, "data_ptr") else v)
+            return arr, len(js)
+        ex.jobs, ex.n_jobs = job_array([j for j in jobs if "xn" in j])
+        ex.blob_jobs, ex.n_blob_jobs = job_array([j for j in jobs if "xn" not in j])
+        ex.pm2 = torch.empty_like(ex.pm) if ex.n_blob_jobs else None
+        ex.pars2 = eng.zeros(W, P) if ex.n_blob_jobs else None
         # pinned staging for the host-facing call
         ex.pars_pin = torch.empty(W, P, dtype=torch.float64).pin_memory()
         ex.lnp_pin = torch.empty(W, dtype=torch.float64).pin_memory()
@@ -601,6 +609,20 @@ class LikelihoodPlan:
                                         eng.ptr(ex.prior), ex.jobs, ex.n_jobs, st),
                   "nb_walker_prep_move")
 
+    def _launch_blob_prep(self, ex, mv):
+        """The total-energy blobs (same kernel, scratch parameter-map outputs)."""
+        L, W, st = lib(), ex.W, eng.stream()
+        if mv is None:
+            check(L.nb_walker_prep(eng.ptr(ex.pars), W, self.P, ex.map, ex.n_map,
+                                   eng.ptr(ex.pm2), ex.pri, 0, None, ex.blob_jobs,
+                                   ex.n_blob_jobs, st), "nb_walker_prep")
+        else:
+            mv2 = type(mv).from_buffer_copy(mv)
+            mv2.pars_ld = 0
+            check(L.nb_walker_prep_move(ctypes.byref(mv2), eng.ptr(ex.pars2), W, self.P,
+                                        ex.map, ex.n_map, eng.ptr(ex.pm2), ex.pri, 0, None,
+                                        ex.blob_jobs, ex.n_blob_jobs, st), "nb_walker_prep_move")
+
     def _launch_comp(self, ex, c, out, src):
         L, W = lib(), ex.W
         p = ex.preps[c["prep"]]
@@ -650,6 +672,8 @@ class LikelihoodPlan:
         free = [x for x in comps if x[0]["selfprep"]]
         branches = [[prep] + [lambda c=c, o=o: launch(c, o) for c, o in dependent[:1]]]
         branches += [[lambda c=c, o=o: launch(c, o)] for c, o in free]
+        if ex.n_blob_jobs:
+            branches.append([lambda: self._launch_blob_prep(ex, mv)])
         extra_dep = dependent[1:]
         joins = []
         if len(branches) > 1 or extra_dep:
@@ -679,7 +703,7 @@ class LikelihoodPlan:
                 joins.append(done)
         for done in joins:
             main.wait_event(done)
-        n += 1 + len(comps)
+        n += 1 + len(comps) + (1 if ex.n_blob_jobs else 0)
         L, st = lib(), eng.stream()
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
             if spec["kind"] != "pdist":
@@ -702,6 +726,8 @@ class LikelihoodPlan:
         """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
         stream (no forking): measurement aid for bench.py / tools/timeline.py."""
         out = [("walker_prep", lambda: self._launch_prep(ex, None))]
+        if ex.n_blob_jobs:
+            out.append(("blob_prep", lambda: self._launch_blob_prep(ex, None)))
         for i, (c, o) in enumerate(zip(self.comps, ex.outs)):
             name = ("syn%d" if c["kind"] == "syn" else "table%d") % i
             out.append((name, lambda c=c, o=o: self._launch_comp(ex, c, o, ex.src)))
