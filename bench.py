@@ -163,11 +163,15 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        """index None: no sampling (ranks > 0: one nvidia-smi loop per box is enough, and
+        eight of them polling the driver slow every rank's launches down)."""
         self.rows, self.proc = [], None
+        if index is None:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -269,7 +273,7 @@ def run_native(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if rank == 0 else None)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     torch.cuda.synchronize()
@@ -314,8 +318,10 @@ def run_native(args):
 
     sampler = nb.PlanSampler(W, 4, plan, seed=wl.SEED)  # sharded over the ranks when N > 1
     sampler._device().before_step = e2e_flush
-    h2d_step, d2h_step = sampler._device().io_bytes_per_step()
-    h2d_step, d2h_step = h2d_step * world, d2h_step * world  # every rank keeps the chain
+    h2d_step, d2h_step = sampler._device().io_bytes_per_step()  # rank 0 (reads the blobs too)
+    if world > 1:
+        d2h_step += (world - 1) * 8 * W * (4 + 1)  # the other ranks: chain + lnprob only
+        h2d_step *= world
     api = ("naima_b200.PlanSampler.sample (the sampler get_sampler()/run_sampler() build "
            "for a traced model; one State per step on the host)")
     state = sampler.run_mcmc(p0, args.warmup)

@@ -346,6 +346,7 @@ class DeviceEnsemble:
         self.step = eng.zeros(1, dtype=torch.int32)
         self.sync = eng.zeros(1, dtype=torch.int32)
         self.before_step = None
+        self.read_rows = True
         self.min_block = 0
         self.use_graph = use_graph
         self._graph = None
@@ -514,7 +515,7 @@ class DeviceEnsemble:
         self.run_loaded(n)
         pn["chain"][t0:t1].copy_(self.chain[t0:t1], non_blocking=True)
         pn["lp"][t0:t1].copy_(self.chain_lp[t0:t1], non_blocking=True)
-        if self.nb:
+        if self.nb and self.read_rows:
             pn["rows"][t0:t1].copy_(self.chain_blobs[t0:t1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -535,7 +536,7 @@ class DeviceEnsemble:
     def io_bytes_per_step(self):
         """(host->device, device->host) bytes moved per ensemble step by enqueue_steps."""
         h2d = 2 * self.Ns * (4 + 4 + 8 + 8)
-        d2h = 8 * self.W * (self.P + 1 + self.nb)
+        d2h = 8 * self.W * (self.P + 1 + (self.nb if self.read_rows else 0))
         return h2d, d2h
 
     def run(self, nsteps):
@@ -584,6 +585,13 @@ class PlanSampler(EnsembleSampler):
         if sharded and seed is None:
             raise ValueError("a sharded PlanSampler needs an explicit seed shared by all ranks")
         self.sharded = bool(sharded)
+        # sharded: only rank 0 reads the blob records back (every rank still keeps the
+        # chain and the log-probabilities); get_blobs() is None on the other ranks
+        self.read_rows = True
+        if self.sharded:
+            import torch.distributed as dist
+
+            self.read_rows = dist.get_rank(group) == 0
         super().__init__(nwalkers, ndim, self._log_prob, a=a, vectorize=True,
                          blobs_dtype=blobs_dtype, seed=seed, **kwargs)
 
@@ -607,6 +615,7 @@ class PlanSampler(EnsembleSampler):
                 self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
             self._de._random = self._random  # one stream, shared with the host-side API
             self._de.min_block = self.chunk
+            self._de.read_rows = self.read_rows
         return self._de
 
     def sample(self, initial_state, log_prob0=None, rstate0=None, blobs0=None, iterations=1,
@@ -645,8 +654,9 @@ class PlanSampler(EnsembleSampler):
         if store:
             self._grow(iterations)
             keep = getattr(self, "_rows", None)
-            self._rows = np.empty((self.iteration + iterations, self.nwalkers, max(de.nb, 1)))
-            if keep is not None and self.iteration:
+            self._rows = np.empty((self.iteration + iterations if self.read_rows else 0,
+                                   self.nwalkers, max(de.nb, 1)))
+            if keep is not None and self.iteration and self.read_rows:
                 self._rows[:self.iteration] = keep[:self.iteration]
         prev = state.coords
         done = 0
@@ -672,12 +682,12 @@ class PlanSampler(EnsembleSampler):
                     self._log_prob[it0:it0 + nblk] = hp["lp"][t0:t1]
                     chain, lps = self._chain[it0:it0 + nblk], self._log_prob[it0:it0 + nblk]
                     recs = None
-                    if de.nb:
+                    if de.nb and self.read_rows:
                         self._rows[it0:it0 + nblk] = hp["rows"][t0:t1]
                         recs = self._rows[it0:it0 + nblk]
                 else:
                     chain, lps = hp["chain"][t0:t1].copy(), hp["lp"][t0:t1].copy()
-                    recs = hp["rows"][t0:t1].copy() if de.nb else None
+                    recs = hp["rows"][t0:t1].copy() if (de.nb and self.read_rows) else None
                 if np.any(np.isnan(lps)):
                     raise ValueError("Probability function returned NaN")
                 for k in range(t1 - t0):
