@@ -362,6 +362,37 @@ int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
 int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int ld,
                              void* stream);
 
+/* --- walker sharding without a collective launch: peer stores over NVLink ------------
+ * The packed records live in buffers that every rank has mapped from every peer
+ * (symmetric memory).  nb_combine_lnprob_push is nb_combine_lnprob_ld writing this rank's
+ * records into its own buffer and then storing them into the same slots
+ * [i0, i0 + W) of every peer's buffer straight from the kernel; the last CTA to finish
+ * publishes flags[rank] = *gen + 1 on every peer (release, system scope).
+ * nb_stretch_update_packed_wait is nb_stretch_update_packed whose CTAs first wait until
+ * all `world` entries of this rank's flag array have reached *gen + 1 (acquire) and whose
+ * last CTA advances *gen.  Alternate two record buffers between the red and the blue half:
+ * a rank may then run at most one half-step ahead of a peer without overwriting records
+ * the peer still reads.  The exchange is part of the likelihood kernel's epilogue -- no
+ * NCCL call, nothing to launch between the combine and the accept step. */
+#define NB_MAX_PEERS 16
+typedef struct nb_peers {
+  int world, rank;
+  int i0;                               /* first slot of this rank's slice */
+  int ld;                               /* record pitch */
+  double* pack[NB_MAX_PEERS];           /* peer r's record buffer (own rank included) */
+  unsigned long long* flags[NB_MAX_PEERS]; /* peer r's flag array [world] */
+  unsigned long long* gen;              /* this rank's half-step generation counter */
+  int* ticket;                          /* int32 scratch, zero before the first launch */
+} nb_peers;
+/* nb: width of the blob record (lnprob is column nb of a packed record) */
+int nb_combine_lnprob_push(const nb_peers* peers_host, int nb, const nb_term* terms_host,
+                           int n_terms, int W, int N_E, const double* unit_fac,
+                           const double* data_flux,
+                           const double* err_lo, const double* err_hi, const int* ul,
+                           const double* cl, const double* prior, void* stream);
+int nb_stretch_update_packed_wait(const nb_stretch* mv_host, const nb_peers* peers_host,
+                                  void* stream);
+
 /* --- self-contained component kernels -------------------------------------------
  * nb_contract / nb_synchrotron with the walker's operands derived INSIDE the kernel from
  * the raw parameters (each warp / CTA repeats the few-hundred-instruction parameter map

@@ -50,6 +50,15 @@ class nb_stretch(ctypes.Structure):
                 ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp)]
 
 
+NB_MAX_PEERS = 16
+
+
+class nb_peers(ctypes.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("i0", c_int), ("ld", c_int),
+                ("pack", vp * NB_MAX_PEERS), ("flags", vp * NB_MAX_PEERS), ("gen", vp),
+                ("ticket", vp)]
+
+
 class nb_walker_src(ctypes.Structure):
     _fields_ = [("pars", vp), ("P", c_int), ("n_map", c_int),
                 ("map_host", ctypes.POINTER(nb_parmap)), ("mv_host", ctypes.POINTER(nb_stretch))]
@@ -97,6 +106,9 @@ PROTOTYPES = {
                           c_int, c_int, c_int, vp, vp, vp, vp, vp],
     "nb_synchrotron_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), c_int, vp,
                              c_int, vp, c_int, vp, c_int, vp, vp],
+    "nb_combine_lnprob_push": [ctypes.POINTER(nb_peers), c_int, ctypes.POINTER(nb_term), c_int,
+                               c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp],
+    "nb_stretch_update_packed_wait": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

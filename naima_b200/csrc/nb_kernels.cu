@@ -452,7 +452,18 @@ struct CombineKernelArgs {
   int has_mv;  // != 0: accept/reject the proposals and append the chain (nb_stretch)
   nb_stretch mv;
   const double* pars;  // [Ns][P] proposals
+  int has_peers;       // != 0: push the packed records to the peers' buffers (nb_peers)
+  nb_peers peers;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
     const __grid_constant__ CombineKernelArgs ka) {
@@ -570,6 +581,32 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
           }
           if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
         }
+      }
+    }
+  }
+  if (ka.has_peers) {
+    // epilogue: this warp's packed record goes to the same slot of every peer's buffer
+    // (plain stores over NVLink); then the last CTA to finish raises this rank's flag on
+    // every peer
+    const nb_peers& pr = ka.peers;
+    const unsigned long long epoch = *pr.gen + 1ull;
+    if (w < a.W) {
+      __syncwarp();
+      const double* rec = a.flux_model + (size_t)w * a.flux_ld;
+      for (int p = 0; p < pr.world; ++p) {
+        if (p == pr.rank) continue;
+        double* dst = pr.pack[p] + (size_t)(pr.i0 + w) * pr.ld;
+        for (int d = lane; d < pr.ld; d += 32) dst[d] = rec[d];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ticket = atomicAdd(pr.ticket, 1);
+      if (ticket == (int)gridDim.x - 1) {
+        *pr.ticket = 0;
+        __threadfence_system();
+        for (int p = 0; p < pr.world; ++p) st_release_sys(pr.flags[p] + pr.rank, epoch);
       }
     }
   }
@@ -1126,11 +1163,27 @@ __global__ void stretch_store_kernel(const double* __restrict__ coords,
 // accept step + chain append from all-gathered packed records (walker sharding): one
 // warp per proposal of the active half, identical on every rank
 // ---------------------------------------------------------------------------
+struct UpdateWait {
+  int world;                        // 0: no waiting (records came through a collective)
+  const unsigned long long* flags;  // this rank's flag array [world]
+  unsigned long long* gen;
+};
+
 __global__ void __launch_bounds__(128) stretch_update_packed_kernel(
-    const __grid_constant__ nb_stretch mv, const double* __restrict__ pack, int ld) {
+    const __grid_constant__ nb_stretch mv, const double* __restrict__ pack, int ld,
+    const __grid_constant__ UpdateWait uw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 4 + warp;
   const int t_step = *mv.step;
+  unsigned long long epoch = 0;
+  if (uw.world > 0) {
+    // every peer's slice of this half-step must have landed in our buffer
+    epoch = *uw.gen + 1ull;
+    if ((int)threadIdx.x < uw.world)
+      while (ld_acquire_sys(uw.flags + threadIdx.x) < epoch) {
+      }
+    __syncthreads();
+  }
   if (i < mv.Ns) {
     const size_t base = ((size_t)t_step * 2 + mv.split) * mv.Ns + i;
     const int sidx = mv.s_idx[base];
@@ -1159,14 +1212,15 @@ __global__ void __launch_bounds__(128) stretch_update_packed_kernel(
       if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
     }
   }
-  if (mv.split == 1) {
+  if (mv.split == 1 || uw.world > 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       int ticket = atomicAdd(mv.sync, 1);
       if (ticket == (int)gridDim.x - 1) {
         *mv.sync = 0;
-        *mv.step = t_step + 1;
+        if (mv.split == 1) *mv.step = t_step + 1;
+        if (uw.world > 0) *uw.gen = epoch;
       }
     }
   }
@@ -1585,7 +1639,8 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
   return 0;
 }
 
-static int launch_combine(const nb_stretch* mv, const double* pars, const nb_term* terms_host,
+static int launch_combine(const nb_peers* peers, const nb_stretch* mv, const double* pars,
+                          const nb_term* terms_host,
                           int n_terms, int W, int N_E, const double* unit_fac,
                           const double* data_flux, const double* err_lo, const double* err_hi,
                           const int* ul, const double* cl, const double* prior,
@@ -1607,6 +1662,16 @@ static int launch_combine(const nb_stretch* mv, const double* pars, const nb_ter
   a.lnp_ld = lnp_ld > 0 ? lnp_ld : 1;
   ka.has_mv = mv ? 1 : 0;
   ka.pars = pars;
+  ka.has_peers = peers ? 1 : 0;
+  if (peers) {
+    if (peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
+        peers->rank >= peers->world || peers->i0 < 0 || peers->ld != flux_ld || !peers->gen ||
+        !peers->ticket || !flux_model || !lnp)
+      return NB_EINVAL;
+    for (int p = 0; p < peers->world; ++p)
+      if (!peers->pack[p] || !peers->flags[p]) return NB_EINVAL;
+    ka.peers = *peers;
+  }
   if (mv) {
     if (!lnp || !pars || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
         !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->i0 != 0 || mv->P < 1 ||
@@ -1630,8 +1695,9 @@ int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
                       const double* unit_fac, const double* data_flux, const double* err_lo,
                       const double* err_hi, const int* ul, const double* cl, const double* prior,
                       double* flux_model, int flux_ld, double* lnp, void* stream) {
-  return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
-                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
+  return launch_combine(nullptr, nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac,
+                        data_flux, err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1,
+                        stream);
 }
 
 int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
@@ -1640,8 +1706,9 @@ int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
                          const double* prior, double* flux_model, int flux_ld, double* lnp,
                          int lnp_ld, void* stream) {
   if (lnp_ld < 1) return NB_EINVAL;
-  return launch_combine(nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac, data_flux,
-                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, lnp_ld, stream);
+  return launch_combine(nullptr, nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac,
+                        data_flux, err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp,
+                        lnp_ld, stream);
 }
 
 int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
@@ -1651,8 +1718,22 @@ int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
                              const double* cl, const double* prior, double* flux_model,
                              int flux_ld, double* lnp, void* stream) {
   if (!mv_host) return NB_EINVAL;
-  return launch_combine(mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux, err_lo,
-                        err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
+  return launch_combine(nullptr, mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux,
+                        err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
+}
+
+int nb_combine_lnprob_push(const nb_peers* peers, int nb, const nb_term* terms_host, int n_terms,
+                           int W, int N_E, const double* unit_fac, const double* data_flux,
+                           const double* err_lo, const double* err_hi, const int* ul,
+                           const double* cl, const double* prior, void* stream) {
+  if (!peers || peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
+      peers->rank >= peers->world || !peers->pack[peers->rank] || nb < N_E ||
+      peers->ld < nb + 1 || peers->i0 < 0)
+    return NB_EINVAL;
+  double* rec0 = peers->pack[peers->rank] + (size_t)peers->i0 * peers->ld;
+  return launch_combine(peers, nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac,
+                        data_flux, err_lo, err_hi, ul, cl, prior, rec0, peers->ld, rec0 + nb,
+                        peers->ld, stream);
 }
 
 int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
@@ -1876,7 +1957,31 @@ int nb_stretch_update_packed(const nb_stretch* mv, const double* pack, int ld, v
       ld < mv->nb + 1 + mv->P)
     return NB_EINVAL;
   if (mv->Ns == 0) return 0;
-  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(*mv, pack, ld);
+  UpdateWait uw;
+  uw.world = 0;
+  uw.flags = nullptr;
+  uw.gen = nullptr;
+  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(*mv, pack, ld,
+                                                                                uw);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_stretch_update_packed_wait(const nb_stretch* mv, const nb_peers* peers, void* stream) {
+  if (!mv || !peers || peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
+      peers->rank >= peers->world || !peers->pack[peers->rank] || !peers->flags[peers->rank] ||
+      !peers->gen || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
+      !mv->zz || !mv->lnu || !mv->n_accepted || mv->P < 1 || mv->Ns < 0 || mv->W < mv->Ns ||
+      mv->split < 0 || mv->split > 1 || mv->nb < 0 || (mv->nb > 0 && !mv->blobs) ||
+      peers->ld < mv->nb + 1 + mv->P)
+    return NB_EINVAL;
+  if (mv->Ns == 0) return 0;
+  UpdateWait uw;
+  uw.world = peers->world;
+  uw.flags = peers->flags[peers->rank];
+  uw.gen = peers->gen;
+  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(
+      *mv, peers->pack[peers->rank], peers->ld, uw);
   NB_CHECK_LAUNCH();
   return 0;
 }

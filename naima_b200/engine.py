@@ -378,11 +378,17 @@ def make_terms(terms):
 
 
 def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, lnp_out=None,
-            mv=None, pars_d=None, flux_ld=0, lnp_ld=1):
+            mv=None, pars_d=None, flux_ld=0, lnp_ld=1, peers=None, nb=0):
     """flux model (radiative.py:102-111) and, with `data`, lnprob (core.py:64-121); with
     `mv` (an nb_stretch) also the accept step and chain append of the half-step."""
     arr = make_terms(terms) if not isinstance(terms, ctypes.Array) else terms
     d = data
+    if peers is not None:  # records straight into this rank's slice, then pushed to the peers
+        check(lib().nb_combine_lnprob_push(
+            ctypes.byref(peers), nb, arr, len(arr), W, N_E, ptr(unit_fac_d), ptr(d.flux),
+            ptr(d.err_lo), ptr(d.err_hi), ptr(d.ul), ptr(d.cl), ptr(prior_d), stream()),
+            "nb_combine_lnprob_push")
+        return
     if mv is not None:
         check(lib().nb_combine_lnprob_update(
             ctypes.byref(mv), ptr(pars_d), arr, len(arr), W, N_E, ptr(unit_fac_d),

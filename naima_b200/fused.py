@@ -645,7 +645,7 @@ class LikelihoodPlan:
         else:
             eng.contract(c["table"], p, out=out)
 
-    def _enqueue(self, ex, mv=None, fuse_update=True):
+    def _enqueue(self, ex, mv=None, fuse_update=True, peers=None):
         """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
         (an nb_stretch describing a device-resident ensemble) the parameters are the
         stretch-move proposals of the active half, computed by the set-up kernel, and
@@ -717,7 +717,7 @@ class LikelihoodPlan:
         eng.combine(ex.terms, W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
                     prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
                     mv=mv if fuse_update else None, pars_d=ex.pars, flux_ld=ex.row_ld,
-                    lnp_ld=ex.lnp.stride(0))
+                    lnp_ld=ex.lnp.stride(0), peers=peers, nb=self.row_width)
         n += 1
         self.launches_per_eval = n
         return n

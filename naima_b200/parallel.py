@@ -108,7 +108,11 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
     The whole ensemble step (both halves, both collectives) is one CUDA-graph replay."""
 
     def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
-                 use_graph=True):
+                 use_graph=True, transport="auto"):
+        """transport: "p2p" -- the combine kernel stores the packed records into every
+        peer's buffer over NVLink itself and the accept kernel waits on per-rank flags
+        (symmetric memory; no collective launch); "nccl" -- one in-place all-gather per
+        half-step; "auto" -- p2p when symmetric memory can be set up, else nccl."""
         from . import engine as eng
 
         if seed is None:
@@ -121,12 +125,67 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             raise ValueError("the half-ensemble (%d) must divide evenly over %d ranks"
                              % (self.Ns, self.world))
         self.ld = plan.pack_width()
-        self.pack_full = eng.zeros(self.Ns, self.ld)
-        lo = self.rank * self.per
-        self.pack_local = self.pack_full[lo:lo + self.per]
-        self.ex = plan.executable(self.per, pack=self.pack_local)
         self.collectives = 0
+        self.transport = "nccl"
+        lo = self.rank * self.per
+        if self.world > 1 and transport in ("auto", "p2p"):
+            try:
+                self._setup_p2p()
+                self.transport = "p2p"
+            except Exception as e:  # no symmetric memory on this build / topology
+                if transport == "p2p":
+                    raise
+                import warnings
+
+                warnings.warn("naima_b200: peer-to-peer transport unavailable (%r); using the "
+                              "NCCL all-gather" % (e,))
+        if self.transport == "p2p":
+            # two record buffers, alternating between the red and the blue half-step
+            self.exs = [plan.executable(self.per, pack=self.packs[k][lo:lo + self.per])
+                        for k in range(2)]
+            self.ex = self.exs[0]
+        else:
+            self.pack_full = eng.zeros(self.Ns, self.ld)
+            self.pack_local = self.pack_full[lo:lo + self.per]
+            self.ex = plan.executable(self.per, pack=self.pack_local)
+            self.exs = [self.ex, self.ex]
         self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 1)
+
+    def _setup_p2p(self):
+        """Symmetric buffers: [2][Ns][ld] records and [world] flags, mapped on every rank."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import engine as eng
+        from ._lib import NB_MAX_PEERS, nb_peers
+
+        if self.world > NB_MAX_PEERS:
+            raise ValueError("more ranks than NB_MAX_PEERS")
+        group = self.group if self.group is not None else dist.group.WORLD
+        dev = eng.device()
+        n = self.Ns * self.ld
+        self._sym_pack = symm.empty(2 * n, dtype=torch.float64, device=dev)
+        self._sym_pack.zero_()
+        self._sym_flags = symm.empty(NB_MAX_PEERS, dtype=torch.int64, device=dev)
+        self._sym_flags.zero_()
+        h_pack = symm.rendezvous(self._sym_pack, group)
+        h_flags = symm.rendezvous(self._sym_flags, group)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self._handles = (h_pack, h_flags)
+        self.packs = [self._sym_pack[k * n:(k + 1) * n].view(self.Ns, self.ld) for k in range(2)]
+        self.gen = eng.zeros(1, dtype=torch.int64)
+        self.ticket = eng.zeros(1, dtype=torch.int32)
+        self.peers = []
+        for k in range(2):
+            pr = nb_peers()
+            pr.world, pr.rank, pr.i0, pr.ld = self.world, self.rank, self.rank * self.per, self.ld
+            for r in range(self.world):
+                pr.pack[r] = int(h_pack.buffer_ptrs[r]) + 8 * k * n
+                pr.flags[r] = int(h_flags.buffer_ptrs[r])
+            pr.gen, pr.ticket = self.gen.data_ptr(), self.ticket.data_ptr()
+            self.peers.append(pr)
 
     def set_state(self, coords, log_prob=None, rows=None):
         """Evaluate the initial ensemble sharded (unless given), then replicate."""
@@ -158,6 +217,13 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         for split in range(2):
             mv = self._stretch(split)
             mv.i0, mv.pars_ld = self.rank * self.per, self.ld
+            if self.transport == "p2p":
+                self.plan._enqueue(self.exs[split], mv=mv, fuse_update=False,
+                                   peers=self.peers[split])
+                check(L.nb_stretch_update_packed_wait(
+                    ctypes.byref(self._stretch(split)), ctypes.byref(self.peers[split]),
+                    eng.stream()), "nb_stretch_update_packed_wait")
+                continue
             self.plan._enqueue(self.ex, mv=mv, fuse_update=False)
             if self.world > 1:
                 _dist().all_gather_into_tensor(self.pack_full, self.pack_local, group=self.group)

@@ -29,15 +29,24 @@ p0 = wl.walkers(wl.C3_PTRUE, W)
 ref = nb.DeviceEnsemble(plan, W, seed=seed)  # single GPU, no communication
 ref.set_state(p0)
 rchain, rlp, rrows = ref.run(nsteps)
+racc = ref.acceptance_counts.copy()
 
-sh = parallel.ShardedDeviceEnsemble(plan, W, seed=seed)
-sh.set_state(p0)
-chain, lp, rows = sh.run(nsteps)
-assert sh.collectives >= 2, sh.collectives
-assert np.array_equal(chain, rchain), np.abs(chain - rchain).max()
-assert np.array_equal(lp, rlp)
-assert np.array_equal(rows, rrows)
-assert np.array_equal(sh.acceptance_counts, ref.acceptance_counts)
+for transport in ("nccl", "auto"):
+    sh = parallel.ShardedDeviceEnsemble(plan, W, seed=seed, transport=transport)
+    sh.set_state(p0)
+    chain, lp, rows = sh.run(nsteps)
+    assert sh.transport == "p2p" or sh.collectives >= 2, sh.collectives
+    assert np.array_equal(chain, rchain), np.abs(chain - rchain).max()
+    assert np.array_equal(lp, rlp)
+    assert np.array_equal(rows, rrows)
+    assert np.array_equal(sh.acceptance_counts, racc)
+    # a second block on the same ensemble (buffers, flags and generation counter carry on)
+    chain2, _, _ = sh.run(5)
+    if transport == "nccl":
+        want2, _, _ = ref.run(5)
+    assert np.array_equal(chain2, want2)
+    if rank == 0:
+        print("transport %s -> %s: chain bitwise equal" % (transport, sh.transport), flush=True)
 
 ps1 = nb.PlanSampler(W, 4, plan, seed=seed, sharded=False)
 ps1.run_mcmc(p0, nsteps)

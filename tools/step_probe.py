@@ -40,12 +40,10 @@ def run(ens, label):
         print("%-28s %8.1f us/step" % (label, t.item()), flush=True)
 
 
-run(parallel.ShardedDeviceEnsemble(plan, W, seed=1), "graph + all-gather")
-run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, use_graph=False), "eager + all-gather")
-orig = dist.all_gather_into_tensor
-dist.all_gather_into_tensor = lambda *a, **k: None
-run(parallel.ShardedDeviceEnsemble(plan, W, seed=1), "graph, no collective")
-dist.all_gather_into_tensor = orig
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p"), "graph + peer stores")
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="nccl"), "graph + all-gather")
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="nccl", use_graph=False),
+    "eager + all-gather")
 single = nb.DeviceEnsemble(plan, 256, seed=1)
 single.set_state(p0[:256])
 single.load_draws(nsteps + 10)
