@@ -383,6 +383,9 @@ typedef struct nb_peers {
   unsigned long long* flags[NB_MAX_PEERS]; /* peer r's flag array [world] */
   unsigned long long* gen;              /* this rank's half-step generation counter */
   int* ticket;                          /* int32 scratch, zero before the first launch */
+  double* mc_pack;                      /* NVSwitch multicast address of the record buffer
+                                           (one multimem.st reaches every peer), or NULL:
+                                           one store per peer */
 } nb_peers;
 /* nb: width of the blob record (lnprob is column nb of a packed record) */
 int nb_combine_lnprob_push(const nb_peers* peers_host, int nb, const nb_term* terms_host,

@@ -56,7 +56,7 @@ NB_MAX_PEERS = 16
 class nb_peers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("i0", c_int), ("ld", c_int),
                 ("pack", vp * NB_MAX_PEERS), ("flags", vp * NB_MAX_PEERS), ("gen", vp),
-                ("ticket", vp)]
+                ("ticket", vp), ("mc_pack", vp)]
 
 
 class nb_walker_src(ctypes.Structure):

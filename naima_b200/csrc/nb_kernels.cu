@@ -593,10 +593,17 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
     if (w < a.W) {
       __syncwarp();
       const double* rec = a.flux_model + (size_t)w * a.flux_ld;
-      for (int p = 0; p < pr.world; ++p) {
-        if (p == pr.rank) continue;
-        double* dst = pr.pack[p] + (size_t)(pr.i0 + w) * pr.ld;
-        for (int d = lane; d < pr.ld; d += 32) dst[d] = rec[d];
+      if (pr.mc_pack) {  // one multicast store per element: the switch replicates it
+        double* dst = pr.mc_pack + (size_t)(pr.i0 + w) * pr.ld;
+        for (int d = lane; d < pr.ld; d += 32)
+          asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(dst + d), "d"(rec[d])
+                       : "memory");
+      } else {
+        for (int p = 0; p < pr.world; ++p) {
+          if (p == pr.rank) continue;
+          double* dst = pr.pack[p] + (size_t)(pr.i0 + w) * pr.ld;
+          for (int d = lane; d < pr.ld; d += 32) dst[d] = rec[d];
+        }
       }
     }
     __threadfence_system();

@@ -31,8 +31,8 @@ ref.set_state(p0)
 rchain, rlp, rrows = ref.run(nsteps)
 racc = ref.acceptance_counts.copy()
 
-for transport in ("nccl", "auto"):
-    sh = parallel.ShardedDeviceEnsemble(plan, W, seed=seed, transport=transport)
+for transport, mc in (("nccl", False), ("p2p", False), ("p2p", True)):
+    sh = parallel.ShardedDeviceEnsemble(plan, W, seed=seed, transport=transport, multicast=mc)
     sh.set_state(p0)
     chain, lp, rows = sh.run(nsteps)
     assert sh.transport == "p2p" or sh.collectives >= 2, sh.collectives
@@ -46,7 +46,8 @@ for transport in ("nccl", "auto"):
         want2, _, _ = ref.run(5)
     assert np.array_equal(chain2, want2)
     if rank == 0:
-        print("transport %s -> %s: chain bitwise equal" % (transport, sh.transport), flush=True)
+        print("transport %s (multicast %s): chain bitwise equal"
+              % (sh.transport, getattr(sh, "uses_multicast", False)), flush=True)
 
 ps1 = nb.PlanSampler(W, 4, plan, seed=seed, sharded=False)
 ps1.run_mcmc(p0, nsteps)

@@ -40,7 +40,9 @@ def run(ens, label):
         print("%-28s %8.1f us/step" % (label, t.item()), flush=True)
 
 
-run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p"), "graph + peer stores")
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p"), "graph + multicast stores")
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p", multicast=False),
+    "graph + peer stores")
 run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="nccl"), "graph + all-gather")
 run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="nccl", use_graph=False),
     "eager + all-gather")
