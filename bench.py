@@ -305,16 +305,19 @@ def run_native(args):
     # blob records (model flux + We) come back device->host; the host consumes one State
     # per step.  L2 is flushed before every step here too (inside the wall-clock region,
     # so `value` below is conservative; `value_excl_flush` subtracts the flushes' device time).
-    flush_ev = []
-
     def e2e_flush():
-        if args.no_flush:
-            return
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        if not args.no_flush:
+            flush_buf.zero_()
+
+    # device time of one flush, measured apart (for value_excl_flush)
+    fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    flush_buf.zero_()
+    fe[0].record()
+    for _ in range(20):
         flush_buf.zero_()
-        b.record()
-        flush_ev.append((a, b))
+    fe[1].record()
+    torch.cuda.synchronize()
+    flush_one_s = 0.0 if args.no_flush else 1e-3 * fe[0].elapsed_time(fe[1]) / 20
 
     sampler = nb.PlanSampler(W, 4, plan, seed=wl.SEED)  # sharded over the ranks when N > 1
     sampler._device().before_step = e2e_flush
@@ -328,7 +331,6 @@ def run_native(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    del flush_ev[:]
     gen = sampler.sample(state, iterations=args.steps, store=True)
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -337,7 +339,7 @@ def run_native(args):
     e2e_t = time.perf_counter() - t0
     gen.close()
     torch.cuda.synchronize()
-    flush_s = 1e-3 * sum(a.elapsed_time(b) for a, b in flush_ev[:args.steps])
+    flush_s = flush_one_s * args.steps
     if world > 1:
         t = torch.tensor([e2e_t], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

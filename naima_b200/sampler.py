@@ -690,9 +690,10 @@ class PlanSampler(EnsembleSampler):
                     recs = hp["rows"][t0:t1].copy() if (de.nb and self.read_rows) else None
                 if np.any(np.isnan(lps)):
                     raise ValueError("Probability function returned NaN")
+                moved = np.any(np.concatenate([prev[None], chain[:-1]]) != chain, axis=2)
                 for k in range(t1 - t0):
                     coords = chain[k]
-                    self._accepted += np.any(coords != prev, axis=1)
+                    self._accepted += moved[k]
                     prev = coords
                     blobs = None
                     if recs is not None:
