@@ -9,6 +9,7 @@ device -- there is no CPU fallback.
 """
 from . import units  # noqa: F401
 from . import models  # noqa: F401
+from .analysis import find_ML, model_samples, read_run, save_run  # noqa: F401
 from .core import (get_sampler, lnprob, lnprobmodel, log_uniform_prior, normal_prior,  # noqa: F401
                    run_sampler, uniform_prior)
 from .fused import LikelihoodPlan, TraceError  # noqa: F401
