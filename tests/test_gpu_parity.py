@@ -6,6 +6,8 @@ The reference's own known-answer numbers are asserted at the reference tests'
 tolerance (assert_allclose default rtol 1e-7).  Most comparisons against the
 oracle are far tighter; the asserted bound is written next to each.
 """
+import os
+
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
@@ -693,6 +695,8 @@ def test_sampler_chain_parity(nb):
 
 def test_get_sampler_run_sampler(nb):
     """tests/test_functionfit.py shapes: API surface of get_sampler/run_sampler."""
+    from naima_b200 import units as u
+
     _, hess = rxj_tables()
     p0 = np.array((1e30, 3.0, np.log10(30)))
     labels = ["norm", "index", "log10(cutoff)"]
@@ -712,6 +716,27 @@ def test_get_sampler_run_sampler(nb):
         assert key in sampler.run_info
     assert sampler.labels == labels and sampler.modelfn is ElectronIC
     assert np.all((sampler.acceptance_fraction >= 0) & (sampler.acceptance_fraction <= 1))
+    # output-side callers: run archive round trip, ML point, posterior recompute
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "run.npz")
+        nb.save_run(fn, sampler)
+        res = nb.read_run(fn, modelfn=ElectronIC)
+    assert np.array_equal(res.get_chain(), sampler.get_chain())
+    assert np.array_equal(res.get_log_prob(), sampler.get_log_prob())
+    rb = res.get_blobs()[-1, 0]
+    assert_allclose(rb[0].value, b[0].value, rtol=0)
+    assert rb[0].unit.physical_type == b[0].unit.physical_type
+    assert_allclose(rb[1][1].value, b[1][1].value, rtol=0)
+    assert res.labels == labels and res.run_info["n_run"] == 3
+    ML, MLp, MLerr, (mx, my) = nb.find_ML(sampler, 0)
+    assert ML == sampler.get_log_prob().max() and my.shape == (28,)
+    E, m = nb.model_samples(res, [0.1, 100] * u.TeV, e_npoints=17, n_samples=12, seed=2)
+    assert m.shape == (12, 17) and m.unit.physical_type == "differential flux"
+    pars = res.get_chain(flat=True)[np.random.RandomState(2).randint(30, size=12)]
+    one = ElectronIC(pars[5], {"energy": E, "flux": hess["flux"][:1]})[0]
+    assert_allclose(m.value[5], one.to(m.unit).value, rtol=1e-10)
     # continue the run; non-traceable callbacks; per-walker mode; prefit
     sampler, pos = nb.run_sampler(nrun=2, sampler=sampler, pos=pos)
     assert sampler.get_chain().shape == (2, 10, 3)
