@@ -329,6 +329,12 @@ typedef struct nb_stretch {
   double* chain;       /* [n_steps][W][P] or NULL */
   double* chain_lp;    /* [n_steps][W] or NULL */
   double* chain_blobs; /* [n_steps][W][nb] or NULL */
+  /* replicated state updated by peers (nb_combine_lnprob_update_push): kernels that read
+   * `coords` first wait until wait_flags[0 .. wait_world) have all reached *wait_gen */
+  const unsigned long long* wait_flags; /* NULL: no waiting */
+  const unsigned long long* wait_gen;
+  int wait_world;
+  int pad2_;
 } nb_stretch;
 int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
                         const nb_parmap* map_host, int n_map, double* pm,
@@ -386,6 +392,15 @@ typedef struct nb_peers {
   double* mc_pack;                      /* NVSwitch multicast address of the record buffer
                                            (one multimem.st reaches every peer), or NULL:
                                            one store per peer */
+  /* replicated-state mode (nb_combine_lnprob_update_push): up to two symmetric arenas that
+   * hold the ensemble state and the chain on every rank; a local pointer inside arena k
+   * maps to arena_peer[k][r] + offset on rank r and to arena_mc[k] + offset for a
+   * multicast store (arena_mc[k] == NULL: one store per peer) */
+  char* arena_local[2];
+  char* arena_mc[2];
+  char* arena_peer[2][NB_MAX_PEERS];
+  unsigned long long arena_bytes[2];
+  unsigned long long* mc_flags;         /* multicast address of the flag arrays, or NULL */
 } nb_peers;
 /* nb: width of the blob record (lnprob is column nb of a packed record) */
 int nb_combine_lnprob_push(const nb_peers* peers_host, int nb, const nb_term* terms_host,
@@ -395,6 +410,20 @@ int nb_combine_lnprob_push(const nb_peers* peers_host, int nb, const nb_term* te
                            const double* cl, const double* prior, void* stream);
 int nb_stretch_update_packed_wait(const nb_stretch* mv_host, const nb_peers* peers_host,
                                   void* stream);
+/* Replicated-state sharding: nb_combine_lnprob_update for this rank's proposals
+ * [mv.i0, mv.i0 + W) whose accept step writes the walkers' new state (coords, lp, blob
+ * record, acceptance count) and their chain rows into EVERY rank's copy (multimem.st
+ * through the NVSwitch, or one store per peer), then raises flags[rank] = *gen + 1 on every
+ * rank and advances *gen.  The next half-step's kernels wait on the flags through
+ * nb_stretch.wait_*: no collective and no separate accept kernel -- the sharded step has
+ * exactly the launches of the single-GPU step. */
+int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* peers_host,
+                                  const double* pars, const nb_term* terms_host, int n_terms,
+                                  int W, int N_E, const double* unit_fac,
+                                  const double* data_flux, const double* err_lo,
+                                  const double* err_hi, const int* ul, const double* cl,
+                                  const double* prior, double* flux_model, int flux_ld,
+                                  double* lnp, void* stream);
 
 /* --- self-contained component kernels -------------------------------------------
  * nb_contract / nb_synchrotron with the walker's operands derived INSIDE the kernel from

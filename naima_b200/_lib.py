@@ -47,7 +47,8 @@ class nb_stretch(ctypes.Structure):
                 ("P", c_int), ("Ns", c_int), ("split", c_int), ("i0", c_int),
                 ("pars_ld", c_int), ("pad_", c_int), ("step", vp), ("sync", vp),
                 ("s_idx", vp), ("c_idx", vp), ("zz", vp), ("lnu", vp), ("n_accepted", vp),
-                ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp)]
+                ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp), ("wait_flags", vp),
+                ("wait_gen", vp), ("wait_world", c_int), ("pad2_", c_int)]
 
 
 NB_MAX_PEERS = 16
@@ -56,7 +57,9 @@ NB_MAX_PEERS = 16
 class nb_peers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("i0", c_int), ("ld", c_int),
                 ("pack", vp * NB_MAX_PEERS), ("flags", vp * NB_MAX_PEERS), ("gen", vp),
-                ("ticket", vp), ("mc_pack", vp)]
+                ("ticket", vp), ("mc_pack", vp), ("arena_local", vp * 2), ("arena_mc", vp * 2),
+                ("arena_peer", (vp * NB_MAX_PEERS) * 2), ("arena_bytes", ctypes.c_ulonglong * 2),
+                ("mc_flags", vp)]
 
 
 class nb_walker_src(ctypes.Structure):
@@ -109,6 +112,9 @@ PROTOTYPES = {
     "nb_combine_lnprob_push": [ctypes.POINTER(nb_peers), c_int, ctypes.POINTER(nb_term), c_int,
                                c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp],
     "nb_stretch_update_packed_wait": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp],
+    "nb_combine_lnprob_update_push": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp,
+                                      ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp,
+                                      vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

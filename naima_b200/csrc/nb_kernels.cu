@@ -34,6 +34,24 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Replicated ensemble state (walker sharding with peer pushes): spin until every rank's
+// flag has reached this rank's generation count, i.e. all pushes of the previous
+// half-step have landed in our copy.  Called by whole CTAs before they read coords.
+__device__ __forceinline__ void wait_for_peers(const nb_stretch& mv) {
+  if (mv.wait_flags == nullptr) return;
+  if ((int)threadIdx.x < mv.wait_world) {
+    const unsigned long long need = *mv.wait_gen;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
+                   : "=l"(v)
+                   : "l"(mv.wait_flags + threadIdx.x)
+                   : "memory");
+    } while (v < need);
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // particle distribution kernels
 // ---------------------------------------------------------------------------
@@ -453,6 +471,8 @@ struct CombineKernelArgs {
   nb_stretch mv;
   const double* pars;  // [Ns][P] proposals
   int has_peers;       // != 0: push the packed records to the peers' buffers (nb_peers)
+  int bcast;           // != 0 (with has_mv and has_peers): replicated state, the accept
+                       // step writes every rank's copy
   nb_peers peers;
 };
 
@@ -463,6 +483,34 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Replicated state: a store that lands in every rank's copy of the symmetric arena that
+// holds `local` (one multimem.st through the NVSwitch when a multicast mapping exists,
+// else one store per peer, own rank included).
+__device__ __forceinline__ int arena_of(const nb_peers& pr, const void* local) {
+  const char* p = reinterpret_cast<const char*>(local);
+  return (p >= pr.arena_local[1] && p < pr.arena_local[1] + pr.arena_bytes[1]) ? 1 : 0;
+}
+__device__ __forceinline__ void bcast_store(const nb_peers& pr, double* local, double v) {
+  const int k = arena_of(pr, local);
+  const size_t off = reinterpret_cast<char*>(local) - pr.arena_local[k];
+  if (pr.arena_mc[k]) {
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(pr.arena_mc[k] + off), "d"(v)
+                 : "memory");
+  } else {
+    for (int p = 0; p < pr.world; ++p) *reinterpret_cast<double*>(pr.arena_peer[k][p] + off) = v;
+  }
+}
+__device__ __forceinline__ void bcast_store(const nb_peers& pr, int* local, int v) {
+  const int k = arena_of(pr, local);
+  const size_t off = reinterpret_cast<char*>(local) - pr.arena_local[k];
+  if (pr.arena_mc[k]) {
+    asm volatile("multimem.st.weak.global.u32 [%0], %1;" ::"l"(pr.arena_mc[k] + off), "r"(v)
+                 : "memory");
+  } else {
+    for (int p = 0; p < pr.world; ++p) *reinterpret_cast<int*>(pr.arena_peer[k][p] + off) = v;
+  }
 }
 
 __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
@@ -478,7 +526,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   double mv_zz = 1.0, mv_lnu = 0.0, lp_old = 0.0;
   size_t mv_base = 0;
   if (ka.has_mv && w < a.W) {
-    mv_base = ((size_t)t_step * 2 + ka.mv.split) * ka.mv.Ns + w;
+    mv_base = ((size_t)t_step * 2 + ka.mv.split) * ka.mv.Ns + ka.mv.i0 + w;
     sidx = ka.mv.s_idx[mv_base];
     mv_zz = ka.mv.zz[mv_base];
     mv_lnu = ka.mv.lnu[mv_base];
@@ -561,36 +609,62 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         acc = __shfl_sync(0xffffffffu, acc, 0);
         __syncwarp();  // this warp's flux_model row is visible to all its lanes
         const size_t W_ = (size_t)mv.W;
+        const bool bc = ka.bcast != 0;
+        const nb_peers& pr = ka.peers;
         for (int d = lane; d < mv.P; d += 32) {
           double v = acc ? ka.pars[(size_t)w * mv.pars_ld + d] : mv.coords[(size_t)sidx * mv.P + d];
-          if (acc) mv.coords[(size_t)sidx * mv.P + d] = v;
-          if (mv.chain) mv.chain[((size_t)t_step * W_ + sidx) * mv.P + d] = v;
+          if (acc) {
+            if (bc) bcast_store(pr, &mv.coords[(size_t)sidx * mv.P + d], v);
+            else mv.coords[(size_t)sidx * mv.P + d] = v;
+          }
+          if (mv.chain) {
+            double* dst = &mv.chain[((size_t)t_step * W_ + sidx) * mv.P + d];
+            if (bc) bcast_store(pr, dst, v);
+            else *dst = v;
+          }
         }
         if (mv.nb > 0) {
           for (int d = lane; d < mv.nb; d += 32) {
             double v = acc ? a.flux_model[(size_t)w * a.flux_ld + d]
                            : mv.blobs[(size_t)sidx * mv.nb + d];
-            if (acc) mv.blobs[(size_t)sidx * mv.nb + d] = v;
-            if (mv.chain_blobs) mv.chain_blobs[((size_t)t_step * W_ + sidx) * mv.nb + d] = v;
+            if (acc) {
+              if (bc) bcast_store(pr, &mv.blobs[(size_t)sidx * mv.nb + d], v);
+              else mv.blobs[(size_t)sidx * mv.nb + d] = v;
+            }
+            if (mv.chain_blobs) {
+              double* dst = &mv.chain_blobs[((size_t)t_step * W_ + sidx) * mv.nb + d];
+              if (bc) bcast_store(pr, dst, v);
+              else *dst = v;
+            }
           }
         }
         if (lane == 0) {
           if (acc) {
-            mv.lp[sidx] = lv;
-            mv.n_accepted[sidx] += 1;
+            if (bc) {
+              bcast_store(pr, &mv.lp[sidx], lv);
+              bcast_store(pr, &mv.n_accepted[sidx], mv.n_accepted[sidx] + 1);
+            } else {
+              mv.lp[sidx] = lv;
+              mv.n_accepted[sidx] += 1;
+            }
           }
-          if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
+          if (mv.chain_lp) {
+            double* dst = &mv.chain_lp[(size_t)t_step * W_ + sidx];
+            if (bc) bcast_store(pr, dst, acc ? lv : lp_old);
+            else *dst = acc ? lv : lp_old;
+          }
         }
       }
     }
   }
   if (ka.has_peers) {
     // epilogue: this warp's packed record goes to the same slot of every peer's buffer
-    // (plain stores over NVLink); then the last CTA to finish raises this rank's flag on
+    // (plain stores over NVLink) -- or, replicated-state mode, the accept step above
+    // already wrote every copy; then the last CTA to finish raises this rank's flag on
     // every peer
     const nb_peers& pr = ka.peers;
     const unsigned long long epoch = *pr.gen + 1ull;
-    if (w < a.W) {
+    if (w < a.W && !ka.bcast) {
       __syncwarp();
       const double* rec = a.flux_model + (size_t)w * a.flux_ld;
       if (pr.mc_pack) {  // one multicast store per element: the switch replicates it
@@ -613,7 +687,14 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
       if (ticket == (int)gridDim.x - 1) {
         *pr.ticket = 0;
         __threadfence_system();
-        for (int p = 0; p < pr.world; ++p) st_release_sys(pr.flags[p] + pr.rank, epoch);
+        if (pr.mc_flags) {
+          asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(pr.mc_flags + pr.rank),
+                       "l"(epoch)
+                       : "memory");
+        } else {
+          for (int p = 0; p < pr.world; ++p) st_release_sys(pr.flags[p] + pr.rank, epoch);
+        }
+        if (ka.bcast) *pr.gen = epoch;  // packed mode: the accept kernel advances it
       }
     }
   }
@@ -738,6 +819,7 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   const double* p = a.pm.pars + (size_t)w * a.pm.P;
   __shared__ double s_q[NB_MAX_MOVE_PAR];
   if (a.has_mv) {
+    wait_for_peers(a.mv);
     // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
     if (tid < a.pm.P) {
       const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + a.mv.i0 + w;
@@ -916,6 +998,7 @@ __global__ void __launch_bounds__(256, 3) contract_fused_kernel(
     ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL,
                        a.lrs + (size_t)row0 * a.pitch, bytes, bar);
   }
+  if (fa.src.has_mv) wait_for_peers(fa.src.mv);
   for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
     sX[j] = a.xgrid[j];
     sLX[j] = fa.pd.lnx[j];
@@ -988,6 +1071,7 @@ __global__ void __launch_bounds__(256) synchrotron_fused_kernel(
   const int nint = a.N - 1;
   const int nsl = gridDim.y;
   const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
+  if (fa.src.has_mv) wait_for_peers(fa.src.mv);
   if (warp == 0) {
     double pp[PD_MAXPAR], Bv;
     warp_walker_params(fa.src, w, fa.pd.pd_off, fa.b_entry, pp, &Bv);
@@ -1670,18 +1754,32 @@ static int launch_combine(const nb_peers* peers, const nb_stretch* mv, const dou
   ka.has_mv = mv ? 1 : 0;
   ka.pars = pars;
   ka.has_peers = peers ? 1 : 0;
+  ka.bcast = (peers && mv) ? 1 : 0;
   if (peers) {
     if (peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
-        peers->rank >= peers->world || peers->i0 < 0 || peers->ld != flux_ld || !peers->gen ||
-        !peers->ticket || !flux_model || !lnp)
+        peers->rank >= peers->world || !peers->gen || !peers->ticket || !flux_model || !lnp)
       return NB_EINVAL;
-    for (int p = 0; p < peers->world; ++p)
-      if (!peers->pack[p] || !peers->flags[p]) return NB_EINVAL;
+    if (!ka.bcast) {
+      if (peers->i0 < 0 || peers->ld != flux_ld) return NB_EINVAL;
+      for (int p = 0; p < peers->world; ++p)
+        if (!peers->pack[p] || !peers->flags[p]) return NB_EINVAL;
+    } else {
+      if (!peers->arena_local[0] || peers->arena_bytes[0] == 0) return NB_EINVAL;
+      for (int k = 0; k < 2; ++k)
+        if (peers->arena_local[k] && !peers->arena_mc[k])
+          for (int p = 0; p < peers->world; ++p)
+            if (!peers->arena_peer[k][p]) return NB_EINVAL;
+      if (!peers->mc_flags)
+        for (int p = 0; p < peers->world; ++p)
+          if (!peers->flags[p]) return NB_EINVAL;
+    }
     ka.peers = *peers;
   }
   if (mv) {
+    const bool sharded = peers != nullptr;  // replicated state: this rank's slice only
     if (!lnp || !pars || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
-        !mv->zz || !mv->lnu || !mv->n_accepted || mv->Ns != W || mv->i0 != 0 || mv->P < 1 ||
+        !mv->zz || !mv->lnu || !mv->n_accepted || (!sharded && (mv->Ns != W || mv->i0 != 0)) ||
+        (sharded && (mv->i0 < 0 || mv->i0 + W > mv->Ns)) || mv->P < 1 ||
         mv->W < W || (mv->pars_ld != 0 && mv->pars_ld < mv->P) ||
         mv->split < 0 || mv->split > 1 || mv->nb < 0 ||
         (mv->nb > 0 && (!mv->blobs || !flux_model || mv->nb < N_E || mv->nb > flux_ld)))
@@ -1727,6 +1825,19 @@ int nb_combine_lnprob_update(const nb_stretch* mv_host, const double* pars,
   if (!mv_host) return NB_EINVAL;
   return launch_combine(nullptr, mv_host, pars, terms_host, n_terms, W, N_E, unit_fac, data_flux,
                         err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1, stream);
+}
+
+int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* peers_host,
+                                  const double* pars, const nb_term* terms_host, int n_terms,
+                                  int W, int N_E, const double* unit_fac,
+                                  const double* data_flux, const double* err_lo,
+                                  const double* err_hi, const int* ul, const double* cl,
+                                  const double* prior, double* flux_model, int flux_ld,
+                                  double* lnp, void* stream) {
+  if (!mv_host || !peers_host) return NB_EINVAL;
+  return launch_combine(peers_host, mv_host, pars, terms_host, n_terms, W, N_E, unit_fac,
+                        data_flux, err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1,
+                        stream);
 }
 
 int nb_combine_lnprob_push(const nb_peers* peers, int nb, const nb_term* terms_host, int n_terms,

@@ -55,6 +55,8 @@ def stream():
 
 def to_dev(a, dtype=torch.float64):
     a = np.ascontiguousarray(a)
+    if not a.flags.writeable:  # torch.from_numpy warns on read-only views (np.broadcast_to ...)
+        a = a.copy()
     return torch.from_numpy(a).to(device=device(), dtype=dtype)
 
 
@@ -383,6 +385,13 @@ def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, l
     `mv` (an nb_stretch) also the accept step and chain append of the half-step."""
     arr = make_terms(terms) if not isinstance(terms, ctypes.Array) else terms
     d = data
+    if peers is not None and mv is not None:  # replicated state: accept step writes every copy
+        check(lib().nb_combine_lnprob_update_push(
+            ctypes.byref(mv), ctypes.byref(peers), ptr(pars_d), arr, len(arr), W, N_E,
+            ptr(unit_fac_d), ptr(d.flux), ptr(d.err_lo), ptr(d.err_hi), ptr(d.ul), ptr(d.cl),
+            ptr(prior_d), ptr(flux_out), flux_ld, ptr(lnp_out), stream()),
+            "nb_combine_lnprob_update_push")
+        return
     if peers is not None:  # records straight into this rank's slice, then pushed to the peers
         check(lib().nb_combine_lnprob_push(
             ctypes.byref(peers), nb, arr, len(arr), W, N_E, ptr(unit_fac_d), ptr(d.flux),

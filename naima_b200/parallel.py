@@ -131,6 +131,13 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         self.collectives = 0
         self.transport = "nccl"
         lo = self.rank * self.per
+        if self.world > 1 and transport == "fused":
+            self._setup_fused()
+            self.transport = "fused"
+            self.ex = plan.executable(self.per)
+            self.exs = [self.ex, self.ex]
+            self.kernel_launches_per_step = 2 * plan.launches_per_eval
+            return
         if self.world > 1 and transport in ("auto", "p2p"):
             try:
                 self._setup_p2p()
@@ -153,6 +160,100 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             self.ex = plan.executable(self.per, pack=self.pack_local)
             self.exs = [self.ex, self.ex]
         self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 1)
+
+    def _setup_fused(self):
+        """Replicated state in symmetric memory: every rank holds coords / lp / blob records /
+        acceptance counts (arena 0) and the chain (arena 1, per block of steps); the combine
+        kernel's accept step writes all copies."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import engine as eng
+        from ._lib import NB_MAX_PEERS, nb_peers
+
+        if self.world > NB_MAX_PEERS:
+            raise ValueError("more ranks than NB_MAX_PEERS")
+        self._group = self.group if self.group is not None else dist.group.WORLD
+        dev = eng.device()
+        W, P, nb = self.W, self.P, max(self.nb, 1)
+        n_acc_d = (W + 1) // 2
+        total = W * P + W + W * nb + n_acc_d
+        arena = symm.empty(total, dtype=torch.float64, device=dev)
+        arena.zero_()
+        flags = symm.empty(NB_MAX_PEERS, dtype=torch.int64, device=dev)
+        flags.zero_()
+        h_arena = symm.rendezvous(arena, self._group)
+        h_flags = symm.rendezvous(flags, self._group)
+        self._sym = [arena, flags, h_arena, h_flags]
+        o = 0
+        self.coords = arena[o:o + W * P].view(W, P); o += W * P
+        self.lp = arena[o:o + W]; o += W
+        self.blobs = arena[o:o + W * nb].view(W, nb); o += W * nb
+        self.n_acc = arena[o:o + n_acc_d].view(torch.int32)[:W]
+        self.gen = eng.zeros(1, dtype=torch.int64)
+        self.ticket = eng.zeros(1, dtype=torch.int32)
+        pr = nb_peers()
+        pr.world, pr.rank, pr.i0, pr.ld = self.world, self.rank, self.rank * self.per, 0
+        pr.arena_local[0] = arena.data_ptr()
+        pr.arena_bytes[0] = 8 * total
+        mc = int(getattr(h_arena, "multicast_ptr", 0) or 0) if self.multicast else 0
+        pr.arena_mc[0] = mc or None
+        mcf = int(getattr(h_flags, "multicast_ptr", 0) or 0) if self.multicast else 0
+        pr.mc_flags = mcf or None
+        for r in range(self.world):
+            pr.arena_peer[0][r] = int(h_arena.buffer_ptrs[r])
+            pr.flags[r] = int(h_flags.buffer_ptrs[r])
+        pr.gen, pr.ticket = self.gen.data_ptr(), self.ticket.data_ptr()
+        self.peers_fused = pr
+        self._flags_local = flags
+        self.uses_multicast = bool(mc)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def _alloc_chain(self, n):
+        if getattr(self, "transport", "") != "fused" and not hasattr(self, "peers_fused"):
+            return super()._alloc_chain(n)
+        import torch
+        import torch.distributed._symmetric_memory as symm
+
+        from . import engine as eng
+
+        W, P, nb = self.W, self.P, self.nb
+        total = n * W * (P + 1 + nb)
+        arena = symm.empty(total, dtype=torch.float64, device=eng.device())
+        arena.zero_()
+        h = symm.rendezvous(arena, self._group)
+        self._sym_chain = (arena, h)
+        pr = self.peers_fused
+        pr.arena_local[1] = arena.data_ptr()
+        pr.arena_bytes[1] = 8 * total
+        mc = int(getattr(h, "multicast_ptr", 0) or 0) if self.multicast else 0
+        pr.arena_mc[1] = mc or None
+        for r in range(self.world):
+            pr.arena_peer[1][r] = int(h.buffer_ptrs[r])
+        o = n * W * P
+        chain = arena[:o].view(n, W, P)
+        chain_lp = arena[o:o + n * W].view(n, W)
+        chain_blobs = arena[o + n * W:].view(n, W, nb) if nb else None
+        self._sync_ranks()
+        return chain, chain_lp, chain_blobs
+
+    def _sync_ranks(self):
+        import torch
+
+        if self.world > 1:
+            torch.cuda.synchronize()
+            _dist().barrier(group=self.group)
+
+    def _stretch(self, split):
+        mv = super()._stretch(split)
+        if getattr(self, "transport", "") == "fused":
+            mv.i0 = self.rank * self.per
+            mv.wait_flags = self._flags_local.data_ptr()
+            mv.wait_gen = self.gen.data_ptr()
+            mv.wait_world = self.world
+        return mv
 
     def _setup_p2p(self):
         """Symmetric buffers: [2][Ns][ld] records and [world] flags, mapped on every rank."""
@@ -213,7 +314,9 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
                 dist.all_gather_into_tensor(full, local, group=self.group)
                 pack = full.cpu().numpy()
             log_prob, rows = pack[:, 0].copy(), np.ascontiguousarray(pack[:, 1:])
+        self._sync_ranks()  # no rank is still stepping (and pushing into our copy)
         super().set_state(coords, log_prob, rows)
+        self._sync_ranks()  # every copy is in place before anybody steps
 
     def _enqueue_step(self):
         from . import engine as eng
@@ -221,6 +324,12 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
 
         L = lib()
         for split in range(2):
+            if self.transport == "fused":
+                # same launches as the single-GPU step: the accept step inside the combine
+                # kernel writes every rank's copy of the state and raises the flags
+                self.plan._enqueue(self.ex, mv=self._stretch(split), fuse_update=True,
+                                   peers=self.peers_fused)
+                continue
             mv = self._stretch(split)
             mv.i0, mv.pars_ld = self.rank * self.per, self.ld
             if self.transport == "p2p":

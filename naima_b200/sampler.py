@@ -408,10 +408,18 @@ class DeviceEnsemble:
         self.c_idx = eng.zeros(n, 2, Ns, dtype=torch.int32)
         self.zz = eng.zeros(n, 2, Ns)
         self.lnu = eng.zeros(n, 2, Ns)
-        self.chain = eng.zeros(n, W, self.P)
-        self.chain_lp = eng.zeros(n, W)
-        self.chain_blobs = eng.zeros(n, W, self.nb) if self.nb else None
+        self.chain, self.chain_lp, self.chain_blobs = self._alloc_chain(n)
         self._graph = None
+
+    def _alloc_chain(self, n):
+        """Chain buffers for n steps (overridden where they live in symmetric memory)."""
+        from . import engine as eng
+
+        return (eng.zeros(n, self.W, self.P), eng.zeros(n, self.W),
+                eng.zeros(n, self.W, self.nb) if self.nb else None)
+
+    def _sync_ranks(self):
+        """Rendezvous of all ranks that share this ensemble's state (single GPU: no-op)."""
 
     def _stretch(self, split):
         """nb_stretch descriptor of the active half `split` over the current buffers."""
@@ -458,6 +466,7 @@ class DeviceEnsemble:
                                   self.n_acc.clone(), self.step.clone())
             self._enqueue_step()
             torch.cuda.synchronize()
+            self._sync_ranks()  # nobody is still pushing into the state restored below
             g = torch.cuda.CUDAGraph()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
@@ -471,6 +480,8 @@ class DeviceEnsemble:
             self.blobs.copy_(b0)
             self.n_acc.copy_(a0)
             self.step.copy_(s0)
+            torch.cuda.synchronize()
+            self._sync_ranks()  # every copy is restored before anybody steps again
         for _ in range(nsteps):
             if self.before_step is not None:
                 self.before_step()  # measurement hook (bench.py flushes L2 here)
@@ -572,11 +583,12 @@ class PlanSampler(EnsembleSampler):
     the chain is identical to the host-driven sampler's for the same seed."""
 
     def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=16, chunk=256,
-                 blobs_dtype=None, group=None, sharded=None, **kwargs):
+                 blobs_dtype=None, group=None, sharded=None, transport="nccl", **kwargs):
         self.plan = plan
         self.block, self.chunk = int(block), int(chunk)
         self._de = None
         self.group = group
+        self.transport = transport
         if sharded is None:
             import torch.distributed as dist
 
@@ -610,7 +622,7 @@ class PlanSampler(EnsembleSampler):
                 from .parallel import ShardedDeviceEnsemble
 
                 self._de = ShardedDeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0,
-                                                 group=self.group)
+                                                 group=self.group, transport=self.transport)
             else:
                 self._de = DeviceEnsemble(self.plan, self.nwalkers, a=self.a, seed=0)
             self._de._random = self._random  # one stream, shared with the host-side API

@@ -31,11 +31,13 @@ ref.set_state(p0)
 rchain, rlp, rrows = ref.run(nsteps)
 racc = ref.acceptance_counts.copy()
 
-for transport, mc in (("nccl", False), ("p2p", False), ("p2p", True)):
+for transport, mc in (("nccl", False), ("p2p", False), ("p2p", True), ("fused", False),
+                      ("fused", True)):
     sh = parallel.ShardedDeviceEnsemble(plan, W, seed=seed, transport=transport, multicast=mc)
     sh.set_state(p0)
     chain, lp, rows = sh.run(nsteps)
-    assert sh.transport == "p2p" or sh.collectives >= 2, sh.collectives
+    assert sh.transport == transport
+    assert sh.transport != "nccl" or sh.collectives >= 2, sh.collectives
     assert np.array_equal(chain, rchain), np.abs(chain - rchain).max()
     assert np.array_equal(lp, rlp)
     assert np.array_equal(rows, rrows)

@@ -40,6 +40,10 @@ def run(ens, label):
         print("%-28s %8.1f us/step" % (label, t.item()), flush=True)
 
 
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="fused"),
+    "graph, replicated state (mc)")
+run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="fused", multicast=False),
+    "graph, replicated state (p2p)")
 run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p"), "graph + multicast stores")
 run(parallel.ShardedDeviceEnsemble(plan, W, seed=1, transport="p2p", multicast=False),
     "graph + peer stores")
