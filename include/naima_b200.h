@@ -417,6 +417,10 @@ int nb_stretch_update_packed_wait(const nb_stretch* mv_host, const nb_peers* pee
  * rank and advances *gen.  The next half-step's kernels wait on the flags through
  * nb_stretch.wait_*: no collective and no separate accept kernel -- the sharded step has
  * exactly the launches of the single-GPU step. */
+/* One-CTA kernel that returns once every rank's pushes of all completed half-steps have
+ * landed in this rank's copy (mv.wait_*): enqueue it before reading the replicated state
+ * or the chain from the host or with a copy. */
+int nb_peer_wait(const nb_stretch* mv_host, void* stream);
 int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* peers_host,
                                   const double* pars, const nb_term* terms_host, int n_terms,
                                   int W, int N_E, const double* unit_fac,

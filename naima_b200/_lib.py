@@ -115,6 +115,7 @@ PROTOTYPES = {
     "nb_combine_lnprob_update_push": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp,
                                       ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp,
                                       vp, vp, vp, vp, vp, c_int, vp, vp],
+    "nb_peer_wait": [ctypes.POINTER(nb_stretch), vp],
     "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],

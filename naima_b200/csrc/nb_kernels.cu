@@ -1317,6 +1317,8 @@ __global__ void __launch_bounds__(128) stretch_update_packed_kernel(
   }
 }
 
+__global__ void peer_wait_kernel(const __grid_constant__ nb_stretch mv) { wait_for_peers(mv); }
+
 // ---------------------------------------------------------------------------
 // fp64 FMA throughput probe (roofline denominator, measured by the caller)
 // ---------------------------------------------------------------------------
@@ -2100,6 +2102,15 @@ int nb_stretch_update_packed_wait(const nb_stretch* mv, const nb_peers* peers, v
   uw.gen = peers->gen;
   stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(
       *mv, peers->pack[peers->rank], peers->ld, uw);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_peer_wait(const nb_stretch* mv, void* stream) {
+  if (!mv || !mv->wait_flags || !mv->wait_gen || mv->wait_world < 1 ||
+      mv->wait_world > NB_MAX_PEERS)
+    return NB_EINVAL;
+  peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(*mv);
   NB_CHECK_LAUNCH();
   return 0;
 }

@@ -108,8 +108,15 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
     The whole ensemble step (both halves, both collectives) is one CUDA-graph replay."""
 
     def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
-                 use_graph=True, transport="nccl", multicast=True):
-        """transport: "p2p" -- the combine kernel stores the packed records into every
+                 use_graph=True, transport="auto", multicast=True):
+        """transport: "fused" -- replicated state in symmetric memory: the combine kernel's
+        accept step writes every rank's copy of the walkers' state and chain rows (one
+        multimem.st per element through the NVSwitch when `multicast`, else one store per
+        peer) and raises per-rank flags that the next half-step's kernels wait on; the
+        sharded step has exactly the launches of the single-GPU step (measured 140 us/step on
+        8 B200s against 165 for "nccl" and 115 on one GPU); "auto" (default) -- "fused" when
+        symmetric memory can be set up, else "nccl";
+        "p2p" -- the combine kernel stores the packed records into every
         peer's buffer over NVLink itself and the accept kernel waits on per-rank flags
         (symmetric memory; no collective launch; with `multicast` one multimem.st per
         element through the NVSwitch instead of one store per peer); "nccl" -- one in-place
@@ -131,14 +138,27 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         self.collectives = 0
         self.transport = "nccl"
         lo = self.rank * self.per
-        if self.world > 1 and transport == "fused":
-            self._setup_fused()
-            self.transport = "fused"
+        if self.world > 1 and transport in ("auto", "fused"):
+            try:
+                self._setup_fused()
+                self.transport = "fused"
+            except Exception as e:  # no symmetric memory on this build / topology
+                if transport == "fused":
+                    raise
+                import warnings
+
+                warnings.warn("naima_b200: replicated-state transport unavailable (%r); using "
+                              "the NCCL all-gather" % (e,))
+                for name in ("peers_fused", "_flags_local"):
+                    self.__dict__.pop(name, None)
+                super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=True,
+                                 use_graph=use_graph)
+        if self.transport == "fused":
             self.ex = plan.executable(self.per)
             self.exs = [self.ex, self.ex]
             self.kernel_launches_per_step = 2 * plan.launches_per_eval
             return
-        if self.world > 1 and transport in ("auto", "p2p"):
+        if self.world > 1 and transport == "p2p":
             try:
                 self._setup_p2p()
                 self.transport = "p2p"
@@ -245,6 +265,19 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         if self.world > 1:
             torch.cuda.synchronize()
             _dist().barrier(group=self.group)
+
+    def _wait_pushes(self):
+        if getattr(self, "transport", "") == "fused" and hasattr(self, "s_idx"):
+            from . import engine as eng
+            from ._lib import check, lib
+
+            check(lib().nb_peer_wait(ctypes.byref(self._stretch(0)), eng.stream()),
+                  "nb_peer_wait")
+
+    @property
+    def acceptance_counts(self):
+        self._wait_pushes()
+        return self.n_acc.cpu().numpy()
 
     def _stretch(self, split):
         mv = super()._stretch(split)

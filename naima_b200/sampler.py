@@ -421,6 +421,10 @@ class DeviceEnsemble:
     def _sync_ranks(self):
         """Rendezvous of all ranks that share this ensemble's state (single GPU: no-op)."""
 
+    def _wait_pushes(self):
+        """Enqueue a wait for the peers' writes into this rank's copy of the state and the
+        chain (replicated-state sharding only; single GPU: no-op)."""
+
     def _stretch(self, split):
         """nb_stretch descriptor of the active half `split` over the current buffers."""
         from ._lib import nb_stretch
@@ -558,6 +562,7 @@ class DeviceEnsemble:
 
         self.load_draws(nsteps)
         self.run_loaded(nsteps)
+        self._wait_pushes()
         torch.cuda.synchronize()
         chain = self.chain[:nsteps].cpu().numpy()
         lp = self.chain_lp[:nsteps].cpu().numpy()
@@ -583,7 +588,7 @@ class PlanSampler(EnsembleSampler):
     the chain is identical to the host-driven sampler's for the same seed."""
 
     def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=16, chunk=256,
-                 blobs_dtype=None, group=None, sharded=None, transport="nccl", **kwargs):
+                 blobs_dtype=None, group=None, sharded=None, transport="auto", **kwargs):
         self.plan = plan
         self.block, self.chunk = int(block), int(chunk)
         self._de = None
