@@ -412,7 +412,8 @@ int nb_stretch_update_packed_wait(const nb_stretch* mv_host, const nb_peers* pee
                                   void* stream);
 /* Replicated-state sharding: nb_combine_lnprob_update for this rank's proposals
  * [mv.i0, mv.i0 + W) whose accept step writes the walkers' new state (coords, lp, blob
- * record, acceptance count) and their chain rows into EVERY rank's copy (multimem.st
+ * record) and their chain rows into EVERY rank's copy (n_accepted stays local to the
+ * deciding rank: sum it over ranks on the host) (multimem.st
  * through the NVSwitch, or one store per peer), then raises flags[rank] = *gen + 1 on every
  * rank and advances *gen.  The next half-step's kernels wait on the flags through
  * nb_stretch.wait_*: no collective and no separate accept kernel -- the sharded step has

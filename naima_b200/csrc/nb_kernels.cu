@@ -640,13 +640,12 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         }
         if (lane == 0) {
           if (acc) {
-            if (bc) {
-              bcast_store(pr, &mv.lp[sidx], lv);
-              bcast_store(pr, &mv.n_accepted[sidx], mv.n_accepted[sidx] + 1);
-            } else {
-              mv.lp[sidx] = lv;
-              mv.n_accepted[sidx] += 1;
-            }
+            if (bc) bcast_store(pr, &mv.lp[sidx], lv);
+            else mv.lp[sidx] = lv;
+            // acceptance counts stay local to the deciding rank (replicated mode: the
+            // host sums them over ranks; a read-modify-write of replicated data would
+            // depend on the arrival order of different ranks' stores)
+            mv.n_accepted[sidx] += 1;
           }
           if (mv.chain_lp) {
             double* dst = &mv.chain_lp[(size_t)t_step * W_ + sidx];

@@ -197,8 +197,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         self._group = self.group if self.group is not None else dist.group.WORLD
         dev = eng.device()
         W, P, nb = self.W, self.P, max(self.nb, 1)
-        n_acc_d = (W + 1) // 2
-        total = W * P + W + W * nb + n_acc_d
+        total = W * P + W + W * nb
         arena = symm.empty(total, dtype=torch.float64, device=dev)
         arena.zero_()
         flags = symm.empty(NB_MAX_PEERS, dtype=torch.int64, device=dev)
@@ -210,7 +209,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         self.coords = arena[o:o + W * P].view(W, P); o += W * P
         self.lp = arena[o:o + W]; o += W
         self.blobs = arena[o:o + W * nb].view(W, nb); o += W * nb
-        self.n_acc = arena[o:o + n_acc_d].view(torch.int32)[:W]
+        # self.n_acc stays a local tensor: each rank counts the acceptances it decided
         self.gen = eng.zeros(1, dtype=torch.int64)
         self.ticket = eng.zeros(1, dtype=torch.int32)
         pr = nb_peers()
@@ -276,8 +275,11 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
 
     @property
     def acceptance_counts(self):
-        self._wait_pushes()
-        return self.n_acc.cpu().numpy()
+        if getattr(self, "transport", "") != "fused":
+            return self.n_acc.cpu().numpy()
+        tot = self.n_acc.clone()  # per-rank counts of the proposals this rank decided
+        _dist().all_reduce(tot, group=self.group)
+        return tot.cpu().numpy()
 
     def _stretch(self, split):
         mv = super()._stretch(split)
