@@ -296,6 +296,12 @@ def run_native(args):
     value = W * args.steps / (total_ms * 1e-3)
     gpu_launches = ens.kernel_launches_per_step * args.steps
     lp_final = ens.lp.cpu().numpy()
+    # acceptance fraction from the chain this rank holds (no collective: the sharded
+    # ensemble's acceptance_counts sums per-rank counters with an all-reduce)
+    ens._wait_pushes()
+    torch.cuda.synchronize()
+    ch = ens.chain[:args.warmup + args.steps].cpu().numpy()
+    acc_frac = float(np.mean(np.any(ch[1:] != ch[:-1], axis=2))) if len(ch) > 1 else None
     assert np.all(np.isfinite(lp_final[np.isfinite(lp_final)])) and not np.any(np.isnan(lp_final))
 
     # ---- end-to-end loop through the public API -----------------------------------
@@ -359,9 +365,10 @@ def run_native(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, W), "clocks": clk, "e2e": e2e,
             "gpu_launches": int(gpu_launches),
-            "collectives_per_step": 2, "roofline": None, "cpu_baseline": None,
-            "acceptance_fraction": float(np.mean(ens.acceptance_counts)
-                                         / (args.steps + args.warmup)),
+            "transport": getattr(ens, "transport", None),
+            "collectives_per_step": 2 if getattr(ens, "transport", "") == "nccl" else 0,
+            "roofline": None, "cpu_baseline": None,
+            "acceptance_fraction": acc_frac,
         }
         print(json.dumps(line))
         return
@@ -457,8 +464,7 @@ def run_native(args):
         "config": workload_config(world, W), "clocks": clk, "e2e": e2e,
         "gpu_launches": int(gpu_launches), "roofline": roofline, "roofline_fp64": roofline_fp64,
         "cpu_baseline": cpu, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
-        "acceptance_fraction": float(np.mean(ens.acceptance_counts)
-                                     / (args.steps + args.warmup)),
+        "acceptance_fraction": acc_frac,
     }
     print(json.dumps(line))
 
