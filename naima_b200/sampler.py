@@ -528,6 +528,7 @@ class DeviceEnsemble:
                           ("lnu", self.lnu)):
             dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
         self.run_loaded(n)
+        self._wait_pushes()  # replicated-state sharding: the peers' rows of these steps
         pn["chain"][t0:t1].copy_(self.chain[t0:t1], non_blocking=True)
         pn["lp"][t0:t1].copy_(self.chain_lp[t0:t1], non_blocking=True)
         if self.nb and self.read_rows:
