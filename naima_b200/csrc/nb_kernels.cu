@@ -3,11 +3,18 @@
 // Design: every radiative process is  spec[w,e] = sum_c coef *
 // trapz_loglog(n[w,:] * K_c[e,:], x).  The emissivity tables K are walker
 // independent, so they are built once per (grid, photon energies, seeds) by the
-// *_table kernels in the reference's operation order; per ensemble half-step
-// only nb_pd_prep (particle distribution on the grid) and nb_contract (the
-// log-log trapezoid contraction, table tile staged into shared memory by TMA
-// bulk copies, warp-shuffle reduction along the integration axis) run.
-// Synchrotron depends on the walker through B and is one fused kernel.
+// *_table kernels in the reference's operation order.  One likelihood evaluation of W
+// walkers is then
+//   walker_prep_kernel        parameter map + priors (+ stretch-move proposals), the
+//                             particle distribution on the grids in log space
+//   contract_kernel           log-log trapezoid contraction; table tile staged in shared
+//                             memory by TMA bulk copies, warp-shuffle reduction along
+//                             the integration axis                (|| on a forked branch:)
+//   synchrotron_fused_kernel  self-contained: parameters -> operands -> AKP10 integral
+//   combine_lnprob_kernel     component sums, units, Gaussian/upper-limit likelihood
+//                             (+ emcee accept step, chain append, and -- walker sharding
+//                             -- the replicated state written to every rank over NVLink)
+// captured with the device-resident ensemble state in one CUDA graph per ensemble step.
 // All arithmetic is IEEE fp64; no tensor cores (there is no dense contraction).
 #include <cuda_runtime.h>
 #include <stdint.h>
