@@ -84,3 +84,44 @@ def test_product_has_no_cpu_path():
         ic.flux([1, 10] * u.TeV)
     with pytest.raises(RuntimeError, match="CUDA"):
         nb.trapz_loglog([1.0, 2.0], [1.0, 2.0])
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct of include/naima_b200.h, as gcc lays them out,
+    against the ctypes mirrors in naima_b200/_lib.py."""
+    import ctypes
+    import subprocess
+
+    from naima_b200 import _lib
+
+    structs = {
+        "nb_term": ["src", "wscale", "ld", "off", "group_end", "div"],
+        "nb_parmap": ["src", "fn", "scale", "dst_off", "dst_stride"],
+        "nb_prior": ["par", "kind", "a", "b"],
+        "nb_prep_job": ["kind", "N", "pd_off", "x", "invdlx", "e_mul1", "xn", "wpitch",
+                        "x_to_energy", "energy_out", "energy_stride"],
+        "nb_stretch": ["coords", "nb", "split", "i0", "pars_ld", "step", "sync", "s_idx",
+                       "n_accepted", "chain_blobs", "wait_flags", "wait_gen", "wait_world"],
+        "nb_peers": ["world", "rank", "i0", "ld", "pack", "flags", "gen", "ticket", "mc_pack",
+                     "arena_local", "arena_mc", "arena_peer", "arena_bytes", "mc_flags"],
+        "nb_walker_src": ["pars", "P", "n_map", "map_host", "mv_host"],
+        "nb_pd_desc": ["kind", "pd_off", "e_mul1", "n_scale", "lnx", "invdlx"],
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>',
+             '#include "%s"' % os.path.join(ROOT, "include", "naima_b200.h"), "int main(void) {"]
+    for name, fields in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fields:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines.append("  return 0;\n}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    got = dict(zip(out[::2], map(int, out[1::2])))
+    for name, fields in structs.items():
+        cls = getattr(_lib, name)
+        assert ctypes.sizeof(cls) == got[name], name
+        for f in fields:
+            assert getattr(cls, f).offset == got["%s.%s" % (name, f)], (name, f)

@@ -189,3 +189,39 @@ def test_priors_scalar_conventions():
     assert nb.normal_prior(1.0, 1.0, 2.0) == -0.5 * (2 * np.pi * 2.0)
     assert nb.log_uniform_prior(4.0, 1, None) == 0.25
     assert nb.log_uniform_prior(0.5, 1, 3) == -np.inf
+
+
+def test_device_ensemble_draws_follow_the_host_sampler_stream():
+    """DeviceEnsemble pre-draws the random numbers of a block of steps; they must be the
+    numbers the host-driven EnsembleSampler (emcee's draw order) consumes, so that both
+    produce the same chain from the same seed."""
+    from naima_b200.sampler import DeviceEnsemble
+
+    class Draws(DeviceEnsemble):  # no device: only the host-side drawing logic
+        def __init__(self, W, seed, a=2.0):
+            self.W, self.Ns, self.a = W, W // 2, a
+            self._random = np.random.mtrand.RandomState(seed)
+            self._all_inds = np.arange(W)
+
+    W, n, a = 14, 5, 2.0
+    s_idx, c_idx, zz, lnu = Draws(W, 9)._draw_block(n)
+    rs = np.random.mtrand.RandomState(9)
+    for t in range(n):
+        rs.choice(1, p=[1.0])  # emcee: self._random.choice(self._moves, p=self._weights)
+        inds = np.arange(W) % 2
+        rs.shuffle(inds)
+        for split in range(2):
+            S1 = inds == split
+            comp = np.flatnonzero(~S1)
+            assert np.array_equal(s_idx[t, split], np.flatnonzero(S1))
+            assert np.array_equal(zz[t, split], ((a - 1.0) * rs.rand(W // 2) + 1) ** 2.0 / a)
+            assert np.array_equal(c_idx[t, split], comp[rs.randint(W // 2, size=(W // 2,))])
+            assert np.array_equal(lnu[t, split], np.log(rs.rand(W // 2)))
+    # replaying k steps from a saved generator state lands on the same state
+    d = Draws(W, 9)
+    rng0 = d._random.get_state()
+    d._draw_block(3)
+    after3 = d._random.get_state()
+    d._draw_block(4)
+    got = d.rng_state_after(rng0, 3)
+    assert got[0] == after3[0] and np.array_equal(got[1], after3[1]) and got[2:] == after3[2:]
