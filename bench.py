@@ -435,7 +435,22 @@ def run_native(args):
                 "note": "the path is fp64-pipe / latency bound by construction (arithmetic "
                         "intensity > 1e3 flop/B, everything L2 resident): the HBM fraction is "
                         "small on purpose; see roofline_fp64 and DESIGN.md section 4"}
-    roofline_fp64 = {"peak_tflops_measured_dfma": fp64_peak, "kernels": per_kernel,
+    # what ncu measured for the binding resource (committed captures, same shapes)
+    ncu = {}
+    for key, fn in (("contract", "ncu_contract.json"), ("synchrotron", "ncu_synchrotron.json")):
+        pth = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(pth):
+            with open(pth) as f:
+                rec = json.load(f)["launches"][-1]
+            ncu[key] = {
+                "source": "profiles/" + fn,
+                "fp64_pipe_pct_of_peak": float(
+                    rec["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0]),
+                "issue_active_pct": float(
+                    rec["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                "duration_us": float(rec["gpu__time_duration.sum"][0]),
+                "dram_bytes_per_launch": rec["dram_bytes_per_launch"]}
+    roofline_fp64 = {"peak_tflops_measured_dfma": fp64_peak, "kernels": per_kernel, "ncu": ncu,
                      "stage_us": {k: 1e3 * v for k, v in kt.items()},
                      "plan_eval_us": 1e3 * t_eval, "walkers_per_launch": Wh}
 
