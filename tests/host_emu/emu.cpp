@@ -183,6 +183,50 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
   free(cb);
 }
 
+// contract_fused_kernel<RT=1>, one walker: operands derived on the fly from the grid's
+// ln x table (contract_lane_selfprep), lane decomposition + shuffle tree
+void emu_contract_selfprep(int kind, const double* p, double m1, double m2, double ns,
+                           const double* K, const double* lrs, int R, int N, int pitch,
+                           const double* x, const double* lnx, const double* dlx,
+                           const double* invdlx, double* out) {
+  PdLog S = pd_log_setup(kind, p, ns);
+  pd_log_setup_grid(S, m1, m2);
+  int nint = N - 1, m = odd_chunk(nint);
+  for (int r = 0; r < R; ++r) {
+    double part[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
+      double acc = 0.0;
+      if (i0 < nint)
+        contract_lane_selfprep<1>(S, x, lnx, dlx, invdlx, K + (size_t)r * pitch,
+                                  lrs + (size_t)r * pitch, pitch, i0, i1, &acc);
+      part[lane] = acc;
+    }
+    out[r] = tree32(part);
+  }
+}
+
+// synchrotron_fused_kernel for one walker: node set-up from the ln x table, then the
+// same pair-of-warps integration as emu_synchrotron
+void emu_synchrotron_fused(int kind, const double* p, double m1, double m2, double ns,
+                           const double* gam, const double* lnx, int N, const double* invdlx,
+                           const double* dlx, double B, const double* E_erg, int N_E,
+                           double* out) {
+  PdLog S = pd_log_setup(kind, p, ns);
+  pd_log_setup_grid(S, m1, m2);
+  double* xn = (double*)malloc(sizeof(double) * N);
+  double* ds1 = (double*)malloc(sizeof(double) * N);
+  for (int j = 0; j < N; ++j) {
+    PdNode nd = pd_log_node_tab(S, gam[j], lnx[j]);
+    xn[j] = gam[j] * pd_log_value_fast(S, nd);
+    ds1[j] = 0.0;
+    if (j < N - 1) ds1[j] = pd_log_ds1(S, nd, pd_log_node_tab(S, gam[j + 1], lnx[j + 1]), invdlx[j]);
+  }
+  emu_synchrotron(gam, N, xn, ds1, invdlx, dlx, B, E_erg, N_E, out);
+  free(xn);
+  free(ds1);
+}
+
 // combine_lnprob_kernel
 void emu_combine_lnprob(const nb_term* terms, int n_terms, int W, int N_E,
                         const double* unit_fac, const double* data_flux, const double* err_lo,

@@ -331,3 +331,57 @@ def test_combine_lnprob(emu, rxj_data):
         assert_allclose(fm[w], model, rtol=1e-15)
         ref = o.lnprobmodel(model, data) + prior[w] if np.isfinite(prior[w]) else prior[w]
         assert_allclose(lnp[w], ref, rtol=1e-14)
+
+
+@pytest.mark.parametrize("pd", PDS, ids=lambda p: p.kind)
+def test_selfprep_kernels(emu, pd):
+    """The self-contained kernels' math (operands from the grid's ln x table, no set-up
+    arrays): nb_contract_fused against the oracle's IC integral, nb_synchrotron_fused against
+    the oracle's synchrotron spectrum, for every particle distribution."""
+    gam = o.electron_grid(100e9, 1e15, 100)
+    N = gam.size
+    pitch = (N + 1) & ~1
+    lnx = np.log(gam)
+    dlx = np.zeros(N)
+    dlx[:-1] = np.log(gam[1:] / gam[:-1])
+    invdlx = np.zeros(N)
+    invdlx[:-1] = 1.0 / dlx[:-1]
+    Eph = np.logspace(8, 14.5, 9) / o.mec2_eV
+    with np.errstate(all="ignore"):
+        Kref = np.concatenate([o.iso_ic_on_planck(gam, T, Eph) for T in (2.72548, 3000.0)], axis=0)
+    R = Kref.shape[0]
+    K = np.zeros((R, pitch))
+    K[:, :N] = Kref
+    lrs = np.zeros((R, pitch))
+    out = np.empty(R)
+    with np.errstate(all="ignore"):
+        emu.emu_finalize(P(K), R, N, pitch, P(invdlx), P(lrs))
+        emu.emu_contract_selfprep(KINDS[pd.kind], P(pdpar(pd)), ctypes.c_double(o.mec2_erg),
+                                  ctypes.c_double(o.erg_eV), ctypes.c_double(o.mec2_eV), P(K),
+                                  P(lrs), R, N, pitch, P(gam), P(lnx), P(dlx), P(invdlx), P(out))
+        ref = o.trapz_loglog(o.nelec(pd, gam) * Kref, gam)
+    nz = ref != 0
+    assert nz.sum() > R // 2
+    big = ref > ref.max() * 1e-200  # below: the reference itself runs through subnormals
+    assert_allclose(out[big], ref[big], rtol=2e-10)
+    assert np.all(out[~nz] == 0)
+    # synchrotron on the default grid
+    gam = o.electron_grid(1e9, 1e9 * o.mec2_eV, 100)
+    N = gam.size
+    lnx = np.log(gam)
+    dlx = np.zeros(N)
+    dlx[:-1] = np.log(gam[1:] / gam[:-1])
+    invdlx = np.zeros(N)
+    invdlx[:-1] = 1.0 / dlx[:-1]
+    E_eV = np.logspace(-5, 6.3, 17)
+    E_erg = E_eV * o.eV_erg
+    for B in (3.24e-6, 2e-5):
+        out = np.empty(E_eV.size)
+        with np.errstate(all="ignore"):
+            emu.emu_synchrotron_fused(KINDS[pd.kind], P(pdpar(pd)), ctypes.c_double(o.mec2_erg),
+                                      ctypes.c_double(o.erg_eV), ctypes.c_double(o.mec2_eV),
+                                      P(gam), P(lnx), N, P(invdlx), P(dlx), ctypes.c_double(B),
+                                      P(E_erg), E_eV.size, P(out))
+        ref = o.synchrotron_spectrum(pd, E_eV, B)
+        big = ref > ref.max() * 1e-200
+        assert_allclose(out[big], ref[big], rtol=5e-10)
