@@ -639,8 +639,9 @@ class PlanSampler(EnsembleSampler):
     def sample(self, initial_state, log_prob0=None, rstate0=None, blobs0=None, iterations=1,
                tune=False, skip_initial_state_check=False, thin_by=1, thin=None, store=True,
                progress=False):
-        if self.nwalkers % 2 or self.nwalkers < 2 * self.ndim:
-            # odd ensembles / live_dangerously: the host-driven loop handles them
+        if self.nwalkers % 2 or self.nwalkers < 2 * self.ndim or self.ndim > 32:
+            # odd ensembles / live_dangerously / more parameters than the fused proposal
+            # kernel maps (NB_MAX_MOVE_PAR): the host-driven loop handles them
             yield from super().sample(initial_state, log_prob0=log_prob0, rstate0=rstate0,
                                       blobs0=blobs0, iterations=iterations,
                                       skip_initial_state_check=skip_initial_state_check,
