@@ -147,6 +147,28 @@ def lib():
     return _lib
 
 
+HOST_LIB_PATH = os.path.join(HERE, "libnaima_b200_host.so")
+_host = False
+
+
+def host_lib():
+    """The host-side helper library (random draws of the device-resident sampler), or None
+    when it has not been built -- callers then use the equivalent NumPy code."""
+    global _host
+    if _host is False:
+        _host = None
+        if os.path.exists(HOST_LIB_PATH):
+            try:
+                H = ctypes.CDLL(HOST_LIB_PATH)
+                H.nb_host_draw_steps.restype = c_int
+                H.nb_host_draw_steps.argtypes = [vp, ctypes.POINTER(c_int), c_int, c_int, c_dbl,
+                                                 vp, vp, vp, vp]
+                _host = H
+            except (OSError, AttributeError):
+                _host = None
+    return _host
+
+
 class NaimaB200Error(RuntimeError):
     pass
 

@@ -29,6 +29,23 @@ def _nvcc():
     return "nvcc"
 
 
+HOST_LIB = os.path.join(HERE, "libnaima_b200_host.so")
+HOST_SRC = os.path.join(CSRC, "nb_host.c")
+
+
+def build_host_library(force=False):
+    """The host-side helper (random draws of the device-resident sampler), plain C.
+    -ffp-contract=off: its arithmetic must round like NumPy's."""
+    if (not force and os.path.exists(HOST_LIB)
+            and os.path.getmtime(HOST_LIB) >= os.path.getmtime(HOST_SRC)):
+        return HOST_LIB
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", HOST_LIB, HOST_SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    return HOST_LIB
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -38,6 +55,7 @@ def needs_build():
 
 
 def build_library(force=False, verbose=False):
+    build_host_library(force=force)
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])

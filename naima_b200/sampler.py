@@ -323,6 +323,8 @@ class DeviceEnsemble:
     once at the end of the block.
     """
 
+    use_host_lib = True  # C helper for the random draws (NumPy calls when it is absent)
+
     def __init__(self, plan, nwalkers, a=2.0, seed=None, store_blobs=True, use_graph=True):
         import torch
 
@@ -385,14 +387,42 @@ class DeviceEnsemble:
             c_idx[split] = half[1 - split][rs.randint(Ns, size=(Ns,))]
             lnu[split] = np.log(rs.rand(Ns))
 
+    def _draw_into(self, s_idx, c_idx, zz, lnu):
+        """Draws of len(zz) consecutive ensemble steps into [n][2][Ns] arrays (C-contiguous;
+        lnu receives log(accept uniform)).  Uses the C helper (nb_host_draw_steps: the same
+        MT19937 stream and algorithms as numpy.random.RandomState, bit for bit) when it is
+        built, else the NumPy calls of _draw_step."""
+        import ctypes
+
+        from ._lib import host_lib
+
+        n = len(zz)
+        H = host_lib() if self.use_host_lib else None
+        ok = (H is not None and n > 0 and self.W % 2 == 0
+              and all(x.flags.c_contiguous for x in (s_idx, c_idx, zz, lnu))
+              and s_idx.dtype == np.int32 and c_idx.dtype == np.int32)
+        if ok:
+            st = self._random.get_state()
+            if st[0] == "MT19937":
+                key = np.array(st[1], dtype=np.uint32)  # private copy, advanced in place
+                pos = ctypes.c_int(int(st[2]))
+                rc = H.nb_host_draw_steps(key.ctypes.data, ctypes.byref(pos), self.W, n,
+                                          float(self.a), s_idx.ctypes.data, c_idx.ctypes.data,
+                                          zz.ctypes.data, lnu.ctypes.data)
+                if rc == 0:
+                    self._random.set_state((st[0], key, pos.value, st[3], st[4]))
+                    np.log(lnu, out=lnu)
+                    return
+        for t in range(n):
+            self._draw_step(s_idx[t], c_idx[t], zz[t], lnu[t])
+
     def _draw_block(self, n):
         Ns = self.Ns
         s_idx = np.empty((n, 2, Ns), dtype=np.int32)
         c_idx = np.empty((n, 2, Ns), dtype=np.int32)
         zz = np.empty((n, 2, Ns))
         lnu = np.empty((n, 2, Ns))
-        for t in range(n):
-            self._draw_step(s_idx[t], c_idx[t], zz[t], lnu[t])
+        self._draw_into(s_idx, c_idx, zz, lnu)
         return s_idx, c_idx, zz, lnu
 
     def _alloc_block(self, n):
@@ -522,8 +552,7 @@ class DeviceEnsemble:
         n = t1 - t0
         pn, hp = self._pin, self._pin_np
         rng0 = self._random.get_state()  # generator state before the block
-        for t in range(t0, t1):
-            self._draw_step(hp["s_idx"][t], hp["c_idx"][t], hp["zz"][t], hp["lnu"][t])
+        self._draw_into(hp["s_idx"][t0:t1], hp["c_idx"][t0:t1], hp["zz"][t0:t1], hp["lnu"][t0:t1])
         for name, dev in (("s_idx", self.s_idx), ("c_idx", self.c_idx), ("zz", self.zz),
                           ("lnu", self.lnu)):
             dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
@@ -541,10 +570,7 @@ class DeviceEnsemble:
         """Generator state after k steps drawn from state rng0 (replays the draws)."""
         keep = self._random.get_state()
         self._random.set_state(rng0)
-        scratch = (np.empty((2, self.Ns), dtype=np.int32), np.empty((2, self.Ns), dtype=np.int32),
-                   np.empty((2, self.Ns)), np.empty((2, self.Ns)))
-        for _ in range(k):
-            self._draw_step(*scratch)
+        self._draw_block(k)
         out = self._random.get_state()
         self._random.set_state(keep)
         return out

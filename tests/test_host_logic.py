@@ -225,3 +225,43 @@ def test_device_ensemble_draws_follow_the_host_sampler_stream():
     d._draw_block(4)
     got = d.rng_state_after(rng0, 3)
     assert got[0] == after3[0] and np.array_equal(got[1], after3[1]) and got[2:] == after3[2:]
+
+
+@pytest.mark.parametrize("W", [2, 6, 14, 256, 1030])
+def test_host_draw_helper_is_bit_identical_to_numpy(W):
+    """nb_host_draw_steps (C, MT19937 + numpy's legacy algorithms restated) against the NumPy
+    calls it replaces: same numbers, same generator state afterwards, for slices of a larger
+    buffer (the sampler writes straight into its pinned staging arrays)."""
+    from naima_b200._lib import host_lib
+    from naima_b200.sampler import DeviceEnsemble
+
+    if host_lib() is None:
+        pytest.skip("host helper library not built")
+
+    class Draws(DeviceEnsemble):
+        def __init__(self, W, seed, a, use_c):
+            self.W, self.Ns, self.a = W, W // 2, a
+            self._random = np.random.mtrand.RandomState(seed)
+            self._all_inds = np.arange(W)
+            self.use_host_lib = use_c
+
+    for seed, a in ((0, 2.0), (5, 2.0), (11, 1.6)):
+        c, py = Draws(W, seed, a, True), Draws(W, seed, a, False)
+        c._random.rand(seed + 1), py._random.rand(seed + 1)  # not at a fresh state
+        big = [np.zeros((9, 2, W // 2), dtype=np.int32), np.zeros((9, 2, W // 2), dtype=np.int32),
+               np.zeros((9, 2, W // 2)), np.zeros((9, 2, W // 2))]
+        for t0, t1 in ((0, 1), (1, 4), (4, 9)):
+            c._draw_into(*[x[t0:t1] for x in big])
+        want = py._draw_block(9)
+        for got, ref in zip(big, want):
+            assert np.array_equal(got, ref)
+        assert c._random.rand() == py._random.rand()
+        # the replay used for rewinding after an early generator exit
+        rng0 = c._random.get_state()
+        c._draw_block(5)
+        s3 = py._random.get_state()  # same state as c had at rng0
+        py._draw_block(3)
+        after3 = py._random.get_state()
+        got = c.rng_state_after(rng0, 3)
+        assert got[0] == after3[0] and np.array_equal(got[1], after3[1]) and got[2] == after3[2]
+        del s3
