@@ -387,11 +387,12 @@ class DeviceEnsemble:
             c_idx[split] = half[1 - split][rs.randint(Ns, size=(Ns,))]
             lnu[split] = np.log(rs.rand(Ns))
 
-    def _draw_into(self, s_idx, c_idx, zz, lnu):
+    def _draw_into(self, s_idx, c_idx, zz, lnu, state=None):
         """Draws of len(zz) consecutive ensemble steps into [n][2][Ns] arrays (C-contiguous;
         lnu receives log(accept uniform)).  Uses the C helper (nb_host_draw_steps: the same
         MT19937 stream and algorithms as numpy.random.RandomState, bit for bit) when it is
-        built, else the NumPy calls of _draw_step."""
+        built, else the NumPy calls of _draw_step.  `state`: the generator's current
+        get_state() if the caller already has it (saves one 85 us call)."""
         import ctypes
 
         from ._lib import host_lib
@@ -402,7 +403,7 @@ class DeviceEnsemble:
               and all(x.flags.c_contiguous for x in (s_idx, c_idx, zz, lnu))
               and s_idx.dtype == np.int32 and c_idx.dtype == np.int32)
         if ok:
-            st = self._random.get_state()
+            st = state if state is not None else self._random.get_state()
             if st[0] == "MT19937":
                 key = np.array(st[1], dtype=np.uint32)  # private copy, advanced in place
                 pos = ctypes.c_int(int(st[2]))
@@ -552,7 +553,8 @@ class DeviceEnsemble:
         n = t1 - t0
         pn, hp = self._pin, self._pin_np
         rng0 = self._random.get_state()  # generator state before the block
-        self._draw_into(hp["s_idx"][t0:t1], hp["c_idx"][t0:t1], hp["zz"][t0:t1], hp["lnu"][t0:t1])
+        self._draw_into(hp["s_idx"][t0:t1], hp["c_idx"][t0:t1], hp["zz"][t0:t1],
+                        hp["lnu"][t0:t1], state=rng0)
         for name, dev in (("s_idx", self.s_idx), ("c_idx", self.c_idx), ("zz", self.zz),
                           ("lnu", self.lnu)):
             dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
@@ -614,7 +616,7 @@ class PlanSampler(EnsembleSampler):
     enqueued `block` at a time so that the host's drawing overlaps the device's stepping;
     the chain is identical to the host-driven sampler's for the same seed."""
 
-    def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=16, chunk=256,
+    def __init__(self, nwalkers, ndim, plan, a=2.0, seed=None, block=32, chunk=256,
                  blobs_dtype=None, group=None, sharded=None, transport="auto", **kwargs):
         self.plan = plan
         self.block, self.chunk = int(block), int(chunk)
