@@ -33,7 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "walker-steps/sec (ensemble lnprob evals/s)"
+METRIC = "walker-steps/sec (ensemble lnprob evals/s) at 1/2/4/8 B200 vs CPU ref"  # BASELINE.json
 UNIT = "walker-steps/s"
 W_PER_GPU = 256
 FLUSH_MIB = 160  # > the 126 MB L2 of a B200
