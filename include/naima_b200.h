@@ -119,12 +119,6 @@ int nb_ic_seed_table(const double* gam, int N, const double* Eph, int N_E,
                      const double* eps0, const double* phn, int Ns, double* K, int pitch,
                      int row0, void* stream);
 
-/* Same with a per-walker seed density phn[W][Ns] (synchrotron self-Compton):
- * K is [W][N_E][pitch]. */
-int nb_ic_seed_table_batched(const double* gam, int N, const double* Eph, int N_E,
-                             const double* eps0, const double* phn, int Ns, int W,
-                             double* K, int pitch, void* stream);
-
 /* Bremsstrahlung, Baring+99 (radiative.py:838-938): rows [row0 + e] get
  * sigma_ee / mec2_eV (cm2/eV), rows [row0 + N_E + e] get sigma_1 (cm2/mec2). */
 int nb_brems_table(const double* gam, int N, const double* eps, int N_E, double* K,
@@ -143,7 +137,9 @@ int nb_pp_lut_table(const double* tx, int nx, const double* ty, int ny, const do
                     int pitch, int row0, void* stream);
 
 /* lrs[r][j] = ln(K[r][j+1]/K[r][j]) * invdlx[j]   (j < N-1; NaN for sign changes,
- * which selects trapz_loglog's log branch, utils.py:341-345). */
+ * which selects trapz_loglog's log branch, utils.py:341-345; 2^600 when either end
+ * point is zero: such an interval is zero whatever the slope, utils.py:347, and the
+ * finite sentinel lets the lean cell of nb_contract_ex do without a zero test). */
 int nb_table_finalize(const double* K, int R, int N, int pitch, const double* invdlx,
                       double* lrs, void* stream);
 
@@ -161,12 +157,33 @@ int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
                 const double* dlx, const double* xgrid, const double* coef, double* out,
                 int exact, void* stream);
 
+/* First non-zero node of every row (row_j0[R], int32; N for an all-zero row) and
+ * *flags |= 1 (int32, zero it first) when the table holds a negative or non-finite entry. */
+int nb_table_scan(const double* K, int R, int N, int pitch, int* row_j0, int* flags,
+                  void* stream);
+
+/* nb_contract with the table's row_j0 (may be NULL): a row tile starts integrating at its
+ * first live column (leading zeros -- kinematic limits, thresholds -- are skipped exactly),
+ * and mode 0: careful cell (every trapz_loglog edge case per interval), 1: reference
+ * operation order (= nb_contract exact), 2: lean cell -- 8 fp64 instructions per interval,
+ * irregular slopes (|b+1| <= 1e-10, NaN, inf) detected per (walker, row tile) and
+ * re-integrated with the careful cell; requires lrs from nb_table_finalize (zero end
+ * points carry its finite sentinel slope) and a table without negative entries. */
+int nb_contract_ex(const double* K, const double* lrs, int R, int N, int pitch,
+                   const int* row_j0, const double* xn, const double* ds1, int wpitch, int W,
+                   const double* dlx, const double* xgrid, const double* coef, double* out,
+                   int mode, void* stream);
+
 /* --- synchrotron, fused (Synchrotron._spectrum radiative.py:282-342) -------
  * out[w][e] = spectrum in 1/(s eV) for B[w] (Gauss) on grid gam[N] with
- * operands xn/ds1 from nb_pd_prep; E_erg[N_E] photon energies in erg. */
-int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1, int wpitch,
-                   const double* invdlx, const double* dlx, const double* B, int W,
-                   const double* E_erg, int N_E, double* out, void* stream);
+ * operands xn/ds1 from nb_pd_prep; E_erg[N_E] photon energies in erg.
+ * gm2[j] = gam[j]^-2 and g23[j] = cbrt(gam[j]^-2) are the grid's walker-independent
+ * node tables (both NULL: computed per node in the kernel); out_ld >= N_E is the row
+ * pitch of out (0 = N_E). */
+int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g23,
+                   const double* xn, const double* ds1, int wpitch, const double* invdlx,
+                   const double* dlx, const double* B, int W, const double* E_erg, int N_E,
+                   double* out, int out_ld, void* stream);
 
 /* --- combine + likelihood (BaseRadiative.flux radiative.py:102-111,
  * lnprobmodel/lnprob core.py:64-121) ------------------------------------------
@@ -207,7 +224,7 @@ int nb_combine_lnprob(const nb_term* terms_host, int n_terms, int W, int N_E,
  *     NB_PRIOR_NORMAL       -0.5*(2 pi b) - (v-a)^2/(2 b)  (literal) core.py:42-44
  *     NB_PRIOR_LOGUNIFORM   v > 0 && v >= a && v <= b ? 1/v : -inf   core.py:47-58
  * map_host / priors_host are HOST arrays (copied into the launch).  prior_out may
- * be NULL. */
+ * be NULL.  Evaluated by nb_walker_prep[_move] and the self-contained kernels. */
 #define NB_FN_ID 0
 #define NB_FN_POW10 1
 #define NB_FN_EXP 2
@@ -228,9 +245,6 @@ typedef struct nb_prior {
   int kind;
   double a, b;
 } nb_prior;
-int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, int n_map,
-                 double* out, const nb_prior* priors_host, int n_priors, double* prior_out,
-                 void* stream);
 
 /* --- per-walker set-up, fused ----------------------------------------------------
  * nb_param_map, then for every job the nb_pd_prep operands of one particle
@@ -271,42 +285,52 @@ int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch
                         int Ns, int phn_wstride, int W, double* out, int out_ld, int out_off,
                         void* stream);
 
+/* --- synchrotron self-Compton: IC on a per-walker tabulated seed, hoisted ----------
+ * The same integral as nb_ic_seed_spectrum (radiative.py:609-655 + 684) for seed
+ * densities that differ per walker (examples/CrabNebula_SynSSC.py:24-28), with the
+ * walker-independent factor f_AA81(gam_g, eps0_s, Eph_e) tabulated once:
+ *   nb_ssc_table   Ft[s][r], Lt[s][r] (log-slope along s, sentinel for zero end points),
+ *                  r = e*N + g, row pitch Rp (multiple of 128, >= N_E*N); coef[r] =
+ *                  3/4 sigma_T c / gam_g^2.  invdlx_s[s] = 1/ln(eps0[s+1]/eps0[s]).
+ *   nb_ssc_seed    sxn[w][s] = sum_k fac_k * src_k[w][off_k + s]  (dn/dE in 1/(mec2 cm3)
+ *                  from luminosities in 1/(s eV): Lsy / (4 pi R^2 c) * 2.24 * mec2[eV]),
+ *                  sds[w][s] = its slope term ln(sxn[s+1]/sxn[s]) * invdlx_s[s].
+ *   nb_ssc_inner   inner[w][r] = coef[r] * trapz_loglog_s(Ft[:, r] * sxn[w, :] / eps0, eps0)
+ *                  -- lean cell, rows with an irregular slope redone with the careful cell.
+ *   nb_ssc_outer   out[w][out_off + e] = coef_e[e] * trapz_loglog_g(n_e[w, :] * inner[w, e, :],
+ *                  gam) with the electron operands xn / ds1 of nb_pd_prep; coef_e = Eph/E_eV. */
+#define NB_SSC_MAX_SRC 4
+typedef struct nb_ssc_src {
+  const double* src; /* [W][ld] */
+  int ld, off;
+  double fac;
+} nb_ssc_src;
+int nb_ssc_table(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
+                 const double* invdlx_s, int Ns, double* Ft, double* Lt, double* coef,
+                 long long Rp, void* stream);
+int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const double* invdlx_s,
+                double* sxn, double* sds, int spitch, void* stream);
+int nb_ssc_inner(const double* Ft, const double* Lt, const double* coef, long long Rp, int Ns,
+                 const double* sxn, const double* sds, int spitch, int W, const double* dlx_s,
+                 double* inner, void* stream);
+int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const double* xn,
+                 const double* ds1, int wpitch, const double* dlx, const double* invdlx,
+                 const double* coef_e, double* out, int out_ld, int out_off, void* stream);
+
 /* --- ensemble stretch move (emcee StretchMove, driven from core.py:127-160) --
- * q[i][:] = c[i][:] - (c[i][:] - s[i][:]) * zz[i]  for Ns walkers of the active
- * half; s/c are gathered rows (device), zz[Ns]. */
-int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
-                       const double* zz, int Ns, double* q, void* stream);
-
-/* accept/reject: for i < Ns with lnpdiff = (P-1) ln zz + new_lp - lp[s_idx] > ln u:
- * coords/lp rows s_idx[i] are overwritten by q/new_lp; accepted[i] = 1. */
-int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const double* q,
-                      const double* new_lp, const double* zz, const double* lnu, int Ns,
-                      int* accepted, void* stream);
-
-/* Device-resident variant for CUDA-graph replay: the draws of n_steps ensemble
- * steps are resident as s_idx/c_idx [n_steps][2][Ns] (int32), zz/lnu
- * [n_steps][2][Ns]; the current step t is read from *step (device int32).
- * nb_stretch_move proposes the active half `split` of step t; nb_stretch_update
- * accepts/rejects it (also the per-walker blob rows blobs[W][nb] when nb > 0),
- * counts acceptances in n_accepted[W], and for split == 1 appends the ensemble
- * to chain[t][W][P] / chain_lp[t][W] / chain_blobs[t][W][nb] (each may be NULL)
- * and increments *step. */
-int nb_stretch_move(const double* coords, int P, int Ns, int split, const int* step,
-                    const int* s_idx, const int* c_idx, const double* zz, double* q,
-                    void* stream);
-int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, int P, int Ns,
-                      int split, int* step, const int* s_idx, const double* zz,
-                      const double* lnu, const double* q, const double* new_lp,
-                      const double* new_blobs, int* n_accepted, double* chain,
-                      double* chain_lp, double* chain_blobs, void* stream);
-
-/* Fused form: the whole red-blue half-step in three launches --
- *   nb_walker_prep_move  (nb_stretch_move + nb_walker_prep: proposals are computed by
- *                         the set-up CTAs themselves and published to `pars`)
- *   nb_contract / nb_synchrotron ... (independent, may run concurrently)
- *   nb_combine_lnprob_update (nb_combine_lnprob + nb_stretch_update incl. the chain
- *                         append: every walker's row of step t is written by the warp
- *                         that decides its proposal)
+ * Device-resident: the draws of n_steps ensemble steps are resident as s_idx/c_idx
+ * [n_steps][2][Ns] (int32), zz/lnu [n_steps][2][Ns]; the current step t is read from
+ * *step (device int32).  The whole red-blue half-step is three launches --
+ *   nb_walker_prep_move  (proposal q[i][:] = c[i][:] - (c[i][:] - s[i][:]) * zz[i] of
+ *                         the active half + nb_walker_prep: the set-up CTAs compute the
+ *                         proposals themselves and publish them to `pars`)
+ *   nb_contract / nb_synchrotron_fused ... (independent, may run concurrently)
+ *   nb_combine_lnprob_update (nb_combine_lnprob + accept step: proposal i is accepted when
+ *                         (P-1) ln zz + new_lp - lp[s_idx] > ln u, overwriting the
+ *                         walker's coords / lp / blob record and counting in n_accepted;
+ *                         the walker's row of step t is appended to chain / chain_lp /
+ *                         chain_blobs by the warp that decides its proposal; a NaN new_lp
+ *                         is never accepted but IS written to chain_lp)
  * `step` is read at kernel start by all kernels of a step and incremented by the last
  * CTA of the split == 1 combine kernel to finish (ticket in `sync`, an int32 scratch
  * word that must be zero before the first launch). */
@@ -368,30 +392,19 @@ int nb_combine_lnprob_ld(const nb_term* terms_host, int n_terms, int W, int N_E,
 int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int ld,
                              void* stream);
 
-/* --- walker sharding without a collective launch: peer stores over NVLink ------------
- * The packed records live in buffers that every rank has mapped from every peer
- * (symmetric memory).  nb_combine_lnprob_push is nb_combine_lnprob_ld writing this rank's
- * records into its own buffer and then storing them into the same slots
- * [i0, i0 + W) of every peer's buffer straight from the kernel; the last CTA to finish
- * publishes flags[rank] = *gen + 1 on every peer (release, system scope).
- * nb_stretch_update_packed_wait is nb_stretch_update_packed whose CTAs first wait until
- * all `world` entries of this rank's flag array have reached *gen + 1 (acquire) and whose
- * last CTA advances *gen.  Alternate two record buffers between the red and the blue half:
- * a rank may then run at most one half-step ahead of a peer without overwriting records
- * the peer still reads.  The exchange is part of the likelihood kernel's epilogue -- no
- * NCCL call, nothing to launch between the combine and the accept step. */
+/* --- walker sharding without a collective launch: replicated state over NVLink --------
+ * The ensemble state and the chain live in buffers that every rank has mapped from every
+ * peer (symmetric memory).  See nb_combine_lnprob_update_push below. */
 #define NB_MAX_PEERS 16
 typedef struct nb_peers {
   int world, rank;
-  int i0;                               /* first slot of this rank's slice */
-  int ld;                               /* record pitch */
-  double* pack[NB_MAX_PEERS];           /* peer r's record buffer (own rank included) */
+  int i0;                               /* unused (reserved) */
+  int ld;                               /* unused (reserved) */
+  double* pack[NB_MAX_PEERS];           /* unused (reserved) */
   unsigned long long* flags[NB_MAX_PEERS]; /* peer r's flag array [world] */
   unsigned long long* gen;              /* this rank's half-step generation counter */
   int* ticket;                          /* int32 scratch, zero before the first launch */
-  double* mc_pack;                      /* NVSwitch multicast address of the record buffer
-                                           (one multimem.st reaches every peer), or NULL:
-                                           one store per peer */
+  double* mc_pack;                      /* unused (reserved) */
   /* replicated-state mode (nb_combine_lnprob_update_push): up to two symmetric arenas that
    * hold the ensemble state and the chain on every rank; a local pointer inside arena k
    * maps to arena_peer[k][r] + offset on rank r and to arena_mc[k] + offset for a
@@ -402,14 +415,6 @@ typedef struct nb_peers {
   unsigned long long arena_bytes[2];
   unsigned long long* mc_flags;         /* multicast address of the flag arrays, or NULL */
 } nb_peers;
-/* nb: width of the blob record (lnprob is column nb of a packed record) */
-int nb_combine_lnprob_push(const nb_peers* peers_host, int nb, const nb_term* terms_host,
-                           int n_terms, int W, int N_E, const double* unit_fac,
-                           const double* data_flux,
-                           const double* err_lo, const double* err_hi, const int* ul,
-                           const double* cl, const double* prior, void* stream);
-int nb_stretch_update_packed_wait(const nb_stretch* mv_host, const nb_peers* peers_host,
-                                  void* stream);
 /* Replicated-state sharding: nb_combine_lnprob_update for this rank's proposals
  * [mv.i0, mv.i0 + W) whose accept step writes the walkers' new state (coords, lp, blob
  * record) and their chain rows into EVERY rank's copy (n_accepted stays local to the
@@ -431,7 +436,7 @@ int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* pee
                                   double* lnp, void* stream);
 
 /* --- self-contained component kernels -------------------------------------------
- * nb_contract / nb_synchrotron with the walker's operands derived INSIDE the kernel from
+ * nb_synchrotron with the walker's operands derived INSIDE the kernel from
  * the raw parameters (each warp / CTA repeats the few-hundred-instruction parameter map
  * and evaluates the particle distribution at the nodes it integrates), so that a
  * likelihood evaluation needs no set-up launch in front of its components.
@@ -457,13 +462,11 @@ typedef struct nb_pd_desc {
   const double* lnx;    /* [N] */
   const double* invdlx; /* [N-1] */
 } nb_pd_desc;
-int nb_contract_fused(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
-                      const double* lrs, int R, int N, int pitch, int W, const double* dlx,
-                      const double* xgrid, const double* coef, double* out, void* stream);
-/* b_entry: index of the map entry holding B [G] */
+/* b_entry: index of the map entry holding B [G]; gm2 / g23 / out_ld as nb_synchrotron */
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
-                         const double* gam, int N, const double* dlx, int W,
-                         const double* E_erg, int N_E, double* out, void* stream);
+                         const double* gam, int N, const double* gm2, const double* g23,
+                         const double* dlx, int W, const double* E_erg, int N_E, double* out,
+                         int out_ld, void* stream);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

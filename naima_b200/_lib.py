@@ -72,6 +72,10 @@ class nb_pd_desc(ctypes.Structure):
                 ("e_mul2", c_dbl), ("n_scale", c_dbl), ("lnx", vp), ("invdlx", vp)]
 
 
+class nb_ssc_src(ctypes.Structure):
+    _fields_ = [("src", vp), ("ld", c_int), ("off", c_int), ("fac", c_dbl)]
+
+
 # name -> (argtypes); every function returns int
 PROTOTYPES = {
     "nb_trapz_loglog": [vp, c_int, c_int, c_int, vp, c_int, vp, vp, vp],
@@ -90,11 +94,18 @@ PROTOTYPES = {
     "nb_table_finalize": [vp, c_int, c_int, c_int, vp, vp, vp],
     "nb_contract": [vp, vp, c_int, c_int, c_int, c_ll, vp, vp, c_int, c_int, vp, vp, vp, vp,
                     c_int, vp],
-    "nb_synchrotron": [vp, c_int, vp, vp, c_int, vp, vp, vp, c_int, vp, c_int, vp, vp],
+    "nb_synchrotron": [vp, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp, c_int, vp,
+                       c_int, vp],
+    "nb_table_scan": [vp, c_int, c_int, c_int, vp, vp, vp],
+    "nb_contract_ex": [vp, vp, c_int, c_int, c_int, vp, vp, vp, c_int, c_int, vp, vp, vp, vp,
+                       c_int, vp],
+    "nb_ssc_table": [vp, c_int, vp, c_int, vp, vp, c_int, vp, vp, vp, c_ll, vp],
+    "nb_ssc_seed": [ctypes.POINTER(nb_ssc_src), c_int, c_int, c_int, vp, vp, vp, c_int, vp],
+    "nb_ssc_inner": [vp, vp, vp, c_ll, c_int, vp, vp, c_int, c_int, vp, vp, vp],
+    "nb_ssc_outer": [vp, c_ll, c_int, c_int, c_int, vp, vp, c_int, vp, vp, vp, vp, c_int, c_int,
+                     vp],
     "nb_combine_lnprob": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp, vp,
                           vp, vp, c_int, vp, vp],
-    "nb_param_map": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
-                     ctypes.POINTER(nb_prior), c_int, vp, vp],
     "nb_walker_prep": [vp, c_int, c_int, ctypes.POINTER(nb_parmap), c_int, vp,
                        ctypes.POINTER(nb_prior), c_int, vp, ctypes.POINTER(nb_prep_job), c_int, vp],
     "nb_walker_prep_move": [ctypes.POINTER(nb_stretch), vp, c_int, c_int,
@@ -105,22 +116,12 @@ PROTOTYPES = {
     "nb_combine_lnprob_ld": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp,
                              vp, vp, vp, c_int, vp, c_int, vp],
     "nb_stretch_update_packed": [ctypes.POINTER(nb_stretch), vp, c_int, vp],
-    "nb_contract_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), vp, vp, c_int,
-                          c_int, c_int, c_int, vp, vp, vp, vp, vp],
     "nb_synchrotron_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), c_int, vp,
-                             c_int, vp, c_int, vp, c_int, vp, vp],
-    "nb_combine_lnprob_push": [ctypes.POINTER(nb_peers), c_int, ctypes.POINTER(nb_term), c_int,
-                               c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp],
-    "nb_stretch_update_packed_wait": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp],
+                             c_int, vp, vp, vp, c_int, vp, c_int, vp, c_int, vp],
     "nb_combine_lnprob_update_push": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp,
                                       ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp,
                                       vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_peer_wait": [ctypes.POINTER(nb_stretch), vp],
-    "nb_stretch_propose": [vp, c_int, vp, vp, vp, c_int, vp, vp],
-    "nb_stretch_accept": [vp, vp, c_int, vp, vp, vp, vp, vp, c_int, vp, vp],
-    "nb_stretch_move": [vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp],
-    "nb_stretch_update": [vp, vp, vp, c_int, c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp,
-                          vp, vp, vp, vp, vp, vp, vp],
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
 }
 

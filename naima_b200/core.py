@@ -253,6 +253,29 @@ def _prefit(p0, data, model, prior):
     return p0, P0_IS_ML
 
 
+def _batch_safe(p0, data, model, prior, n=3):
+    """True if the callbacks give, for a [n, P] batch of parameter vectors (seen by them as
+    ``pars[P, n]``), the same log-probabilities as n separate reference-style calls.  Valid
+    reference callbacks that branch on ``pars``, interpolate with scalar parameters or
+    broadcast ``pars[k]`` against ``data['energy']`` fail or mis-broadcast when batched; they
+    keep the reference's one-call-per-walker semantics instead."""
+    p0 = np.asarray(p0, dtype=float)
+    P = p0 * (1.0 + 1e-3 * np.arange(1, n + 1)[:, None])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            single = np.array([float(lnprob(p, data, model, prior)[0]) for p in P])
+        except Exception:
+            return True  # broken either way: let the sampler surface the error as before
+        try:
+            batched = np.asarray(lnprob(P, data, model, prior)[0], dtype=float)
+        except Exception:
+            return False
+    if batched.shape != (n,):
+        return False
+    return bool(np.allclose(batched, single, rtol=1e-8, atol=0.0, equal_nan=True))
+
+
 def get_sampler(data_table=None, p0=None, model=None, prior=None, nwalkers=500, nburn=100,
                 guess=True, interactive=False, prefit=False, labels=None, threads=None,
                 data_sed=None, vectorize=True, fused=True, seed=None):
@@ -327,6 +350,9 @@ def get_sampler(data_table=None, p0=None, model=None, prior=None, nwalkers=500, 
             plan = LikelihoodPlan(model, prior, data, len(p0))
         except TraceError as e:
             log.info("model/prior callbacks are not traceable (%s); using batched callbacks", e)
+    if plan is None and vectorize and not _batch_safe(p0, data, model, prior):
+        log.info("model/prior callbacks are not batch-aware; calling them once per walker")
+        vectorize = False
     if plan is not None:
         # device-resident stepping behind the EnsembleSampler API
         sampler = PlanSampler(nwalkers, len(p0), plan, blobs_dtype=np.dtype(object), seed=seed)

@@ -288,19 +288,50 @@ __global__ void table_finalize_kernel(const double* __restrict__ K, int N, int p
   size_t r = blockIdx.y;
   if (j >= pitch) return;
   double v = 0.0;
-  if (j < N - 1) v = log(K[r * pitch + j + 1] / K[r * pitch + j]) * invdlx[j];
+  if (j < N - 1) {
+    const double k1 = K[r * pitch + j], k2 = K[r * pitch + j + 1];
+    // zero end point: the interval is zero whatever the slope (utils.py:347); store the
+    // finite sentinel instead of ln(0) so that the lean cell needs no zero test
+    v = (k1 == 0.0 || k2 == 0.0) ? NB_BIG_SLOPE : log(k2 / k1) * invdlx[j];
+  }
   lrs[r * pitch + j] = v;
+}
+
+// per row: index of the first non-zero node (N when the row is all zero) -- the contraction
+// skips the leading zeros of a row tile (the kinematic limit of IC / bremsstrahlung, the
+// pion-production threshold); flags |= 1 when any entry is negative or not finite (such
+// tables keep the careful cell: their NaN slopes select trapz_loglog's log branch)
+__global__ void table_scan_kernel(const double* __restrict__ K, int R, int N, int pitch,
+                                  int* __restrict__ row_j0, int* __restrict__ flags) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  int first = N;
+  bool bad = false;
+  for (int j = lane; j < N; j += 32) {
+    const double k = K[(size_t)r * pitch + j];
+    if (k != 0.0 && j < first) first = j;
+    bad = bad || !(k >= 0.0) || !(k < INFINITY);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  const bool anybad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    row_j0[r] = first;
+    if (anybad) atomicOr(flags, 1);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // the hot contraction
 // ---------------------------------------------------------------------------
 // CTA = 8 warps.  blockIdx.x selects a tile of RT table rows, staged in shared
-// memory with two TMA bulk copies (K and lrs); blockIdx.y selects a group of
-// walkers, one walker per warp at a time.  Lane l integrates the contiguous
-// interval range [l*m, (l+1)*m) (m odd => conflict-free 64-bit smem reads),
-// carrying x*y of the previous node in a register; the 32 partial sums are
-// combined with a shuffle tree.
+// memory with TMA bulk copies (K and lrs, one copy per row from the tile's first live
+// column on); blockIdx.y selects a group of walkers, one walker per warp at a time.  Lane l
+// integrates the contiguous interval range [jt + l*m, jt + (l+1)*m) (m odd => conflict-free
+// 64-bit smem reads), carrying x*y of the previous node in a register; the 32 partial sums
+// are combined with a shuffle tree.
+// MODE 0: careful cell (interval_fast), 1: reference operation order (interval_exact),
+// 2: lean cell (cell_lean) with a per-(walker, tile) fall-back to the careful cell.
 struct ContractArgs {
   const double* K;
   const double* lrs;
@@ -312,13 +343,16 @@ struct ContractArgs {
   const double* xgrid;
   const double* coef;
   double* out;
-  int m;
+  const int* row_j0;  // first non-zero node per row, or NULL
   int w_per_cta;
 };
 
-template <int RT, bool EXACT>
+constexpr unsigned NB_SPIN_LIMIT = 1u << 28;  // ~ a second of polling: trap instead of hanging
+
+template <int RT, int MODE>
 __global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool EXACT = MODE == 1;
   double* sK = reinterpret_cast<double*>(smem_raw);
   double* sL = sK + (size_t)RT * a.pitch;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sL + (EXACT ? 0 : (size_t)RT * a.pitch));
@@ -326,6 +360,22 @@ __global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
   const int row0 = blockIdx.x * RT;
   const int nrows = min(RT, a.R - row0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nint = a.N - 1;
+
+  // first live column of the tile (even: 16-byte aligned bulk copies)
+  int jt = 0;
+  if (a.row_j0) {
+    jt = a.N;
+    for (int r = 0; r < nrows; ++r) jt = min(jt, a.row_j0[row0 + r]);
+    jt = max(jt - 1, 0) & ~1;  // the interval left of the first non-zero node is zero anyway
+  }
+  const int wbeg = blockIdx.y * a.w_per_cta;
+  const int wend = min(wbeg + a.w_per_cta, a.W);
+  if (jt >= nint) {  // all-zero tile
+    for (int k = threadIdx.x; k < (wend - wbeg) * nrows; k += blockDim.x)
+      a.out[(size_t)(wbeg + k / nrows) * a.R + row0 + k % nrows] = 0.0;
+    return;
+  }
 
   if (threadIdx.x == 0) {
     ptx::mbarrier_init(bar, 1);
@@ -333,30 +383,47 @@ __global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t bytes = (uint32_t)nrows * (uint32_t)a.pitch * 8u;
+    const uint32_t bytes = (uint32_t)(a.pitch - jt) * 8u;
     ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar,
-                                   EXACT ? bytes : 2u * bytes);
-    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK,
-                       a.K + (size_t)row0 * a.pitch, bytes, bar);
-    if (!EXACT)
-      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL,
-                         a.lrs + (size_t)row0 * a.pitch, bytes, bar);
+                                   (EXACT ? 1u : 2u) * bytes * (uint32_t)nrows);
+    for (int r = 0; r < nrows; ++r) {
+      const size_t off = (size_t)r * a.pitch + jt;
+      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK + off,
+                         a.K + (size_t)row0 * a.pitch + off, bytes, bar);
+      if (!EXACT)
+        ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL + off,
+                           a.lrs + (size_t)row0 * a.pitch + off, bytes, bar);
+    }
   }
-  while (!ptx::mbarrier_try_wait_parity(bar, 0)) {
+  if (nrows < RT) {  // rows beyond the table: zeros (their results are not stored)
+    for (int k = threadIdx.x; k < (RT - nrows) * a.pitch; k += blockDim.x) {
+      sK[(size_t)nrows * a.pitch + k] = 0.0;
+      if (!EXACT) sL[(size_t)nrows * a.pitch + k] = NB_BIG_SLOPE;
+    }
+    __syncthreads();
   }
+  for (unsigned spin = 0; !ptx::mbarrier_try_wait_parity(bar, 0);)
+    if (++spin > NB_SPIN_LIMIT) __trap();  // a bulk copy that never completes: fail loudly
 
-  const int nint = a.N - 1;
-  const int i0 = lane * a.m;
-  const int i1 = min(i0 + a.m, nint);
-  const int wbeg = blockIdx.y * a.w_per_cta;
-  const int wend = min(wbeg + a.w_per_cta, a.W);
+  const int m = odd_chunk(nint - jt);
+  const int i0 = jt + lane * m;
+  const int i1 = min(i0 + m, nint);
 
   for (int w = wbeg + warp; w < wend; w += 8) {
     double acc[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-    if (i0 < nint) {
-      const double* xnw = a.xn + (size_t)w * a.wpitch;
+    const double* xnw = a.xn + (size_t)w * a.wpitch;
+    if (MODE == 2) {
+      const double* dsw = a.ds1 + (size_t)w * a.wpitch;
+      unsigned worst = 0u;
+      if (i0 < nint) worst = contract_lane_lean<RT>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc);
+      if (__any_sync(0xffffffffu, worst >= NB_REG_RANGE)) {  // irregular slope somewhere: redo
+#pragma unroll
+        for (int r = 0; r < RT; ++r) acc[r] = 0.0;
+        if (i0 < nint) contract_lane_fast<RT>(xnw, dsw, a.dlx, sK, sL, a.pitch, i0, i1, acc);
+      }
+    } else if (i0 < nint) {
       if (EXACT)
         contract_lane_exact<RT>(xnw, a.xgrid, sK, a.pitch, i0, i1, acc);
       else
@@ -376,96 +443,6 @@ __global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// synchrotron (fused): CTA = (walker, photon-energy slice)
-// ---------------------------------------------------------------------------
-struct SynArgs {
-  const double* gam;
-  int N;
-  const double* xn;
-  const double* ds1;
-  int wpitch;
-  const double* invdlx;
-  const double* dlx;
-  const double* B;
-  int W;
-  const double* E_erg;
-  int N_E;
-  double* out;
-  int e_per_cta;
-};
-
-__global__ void __launch_bounds__(256) synchrotron_kernel(SynArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx; per photon energy: first live node
-  double* s_iec = reinterpret_cast<double*>(smem_raw);
-  double* s_cb = s_iec + a.N;
-  double* s_xn = s_cb + a.N;
-  double* s_ds = s_xn + a.N;
-  double* s_idl = s_ds + a.N;
-  double* s_dl = s_idl + a.N;
-  int* s_js = reinterpret_cast<int*>(s_dl + a.N);  // [e_per_cta]
-  __shared__ int s_jmin;
-
-  const int w = blockIdx.x;
-  const double Bw = a.B[w];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nint = a.N - 1;
-  // this CTA's photon energies: e = blockIdx.y + k * gridDim.y, k < ne (strided, so that
-  // every slice gets the same mix of cheap and expensive energies)
-  const int nsl = gridDim.y;
-  const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
-
-  // nodes whose exp(-E/Ec) underflows to zero contribute nothing: find, per photon
-  // energy, the first node that can be non-zero, and only set up nodes from the
-  // smallest of them on
-  if (threadIdx.x == 0) s_jmin = a.N;
-  __syncthreads();
-  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[blockIdx.y + k * nsl]);
-    s_js[k] = js;
-    atomicMin(&s_jmin, js);
-  }
-  __syncthreads();
-  const int jmin = s_jmin;
-  for (int j = jmin + threadIdx.x; j < a.N; j += blockDim.x) {
-    syn_node(a.gam[j], Bw, &s_iec[j], &s_cb[j]);
-    s_xn[j] = a.xn[(size_t)w * a.wpitch + j];
-    s_ds[j] = a.ds1[(size_t)w * a.wpitch + j];
-    if (j < nint) {
-      s_idl[j] = a.invdlx[j];
-      s_dl[j] = a.dlx[j];
-    }
-  }
-  __syncthreads();
-
-  // each photon energy is integrated by a pair of warps (64 lanes, ~5 intervals per lane
-  // on the default grids): the per-lane chains are serial, so short chains and many warps
-  // are what keeps the fp64 pipe busy.  The two partial sums meet in shared memory.
-  double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
-  const int pair = warp >> 1, half = warp & 1;
-  for (int k = pair; k < ne; k += 4) {
-    const double E = a.E_erg[blockIdx.y + k * nsl];
-    const int js = s_js[k];
-    const int len = nint - js;
-    double acc = 0.0;
-    if (len > 0) {
-      const int m = odd_chunk2(len);
-      const int i0 = js + (half * 32 + lane) * m;
-      const int i1 = min(i0 + m, nint);
-      if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
-      acc = warp_sum(acc);
-    }
-    if (lane == 0) s_part[2 * k + half] = acc;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-    const int e = blockIdx.y + k * nsl;
-    const double acc = s_part[2 * k] + s_part[2 * k + 1];
-    a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, a.E_erg[e], acc);
-  }
-}
-
-// ---------------------------------------------------------------------------
 // combine + likelihood: one warp per walker.  Lanes evaluate the model flux and the
 // Gaussian terms of the photon energies e = lane, lane + 32, ... into shared memory;
 // lane 0 then adds the terms in numpy's summation order (a few hundred cycles).
@@ -477,9 +454,8 @@ struct CombineKernelArgs {
   int has_mv;  // != 0: accept/reject the proposals and append the chain (nb_stretch)
   nb_stretch mv;
   const double* pars;  // [Ns][P] proposals
-  int has_peers;       // != 0: push the packed records to the peers' buffers (nb_peers)
-  int bcast;           // != 0 (with has_mv and has_peers): replicated state, the accept
-                       // step writes every rank's copy
+  int has_peers;       // != 0 (with has_mv): replicated state, the accept step writes every
+                       // rank's copy (nb_peers)
   nb_peers peers;
 };
 
@@ -522,7 +498,7 @@ __device__ __forceinline__ void bcast_store(const nb_peers& pr, int* local, int 
 
 __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
     const __grid_constant__ CombineKernelArgs ka) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const CombineArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
@@ -616,7 +592,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         acc = __shfl_sync(0xffffffffu, acc, 0);
         __syncwarp();  // this warp's flux_model row is visible to all its lanes
         const size_t W_ = (size_t)mv.W;
-        const bool bc = ka.bcast != 0;
+        const bool bc = ka.has_peers != 0;
         const nb_peers& pr = ka.peers;
         for (int d = lane; d < mv.P; d += 32) {
           double v = acc ? ka.pars[(size_t)w * mv.pars_ld + d] : mv.coords[(size_t)sidx * mv.P + d];
@@ -655,37 +631,23 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
             mv.n_accepted[sidx] += 1;
           }
           if (mv.chain_lp) {
+            // a NaN log-probability is never accepted (the comparison above is false) but
+            // must not stay hidden: it goes into the chain row, where the host finds it and
+            // raises emcee's "Probability function returned NaN"
+            const double rec = (acc || lv != lv) ? lv : lp_old;
             double* dst = &mv.chain_lp[(size_t)t_step * W_ + sidx];
-            if (bc) bcast_store(pr, dst, acc ? lv : lp_old);
-            else *dst = acc ? lv : lp_old;
+            if (bc) bcast_store(pr, dst, rec);
+            else *dst = rec;
           }
         }
       }
     }
   }
   if (ka.has_peers) {
-    // epilogue: this warp's packed record goes to the same slot of every peer's buffer
-    // (plain stores over NVLink) -- or, replicated-state mode, the accept step above
-    // already wrote every copy; then the last CTA to finish raises this rank's flag on
-    // every peer
+    // replicated state: the accept step above already wrote every rank's copy; the last CTA
+    // to finish raises this rank's flag on every peer
     const nb_peers& pr = ka.peers;
     const unsigned long long epoch = *pr.gen + 1ull;
-    if (w < a.W && !ka.bcast) {
-      __syncwarp();
-      const double* rec = a.flux_model + (size_t)w * a.flux_ld;
-      if (pr.mc_pack) {  // one multicast store per element: the switch replicates it
-        double* dst = pr.mc_pack + (size_t)(pr.i0 + w) * pr.ld;
-        for (int d = lane; d < pr.ld; d += 32)
-          asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(dst + d), "d"(rec[d])
-                       : "memory");
-      } else {
-        for (int p = 0; p < pr.world; ++p) {
-          if (p == pr.rank) continue;
-          double* dst = pr.pack[p] + (size_t)(pr.i0 + w) * pr.ld;
-          for (int d = lane; d < pr.ld; d += 32) dst[d] = rec[d];
-        }
-      }
-    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -700,7 +662,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
         } else {
           for (int p = 0; p < pr.world; ++p) st_release_sys(pr.flags[p] + pr.rank, epoch);
         }
-        if (ka.bcast) *pr.gen = epoch;  // packed mode: the accept kernel advances it
+        *pr.gen = epoch;
       }
     }
   }
@@ -719,41 +681,6 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
 }
 
 // ---------------------------------------------------------------------------
-// stretch move helpers
-// ---------------------------------------------------------------------------
-__global__ void stretch_propose_kernel(const double* __restrict__ coords, int P,
-                                       const int* __restrict__ s_idx,
-                                       const int* __restrict__ c_idx,
-                                       const double* __restrict__ zz, int Ns,
-                                       double* __restrict__ q) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Ns * P) return;
-  int i = t / P, d = t - i * P;
-  double c = coords[(size_t)c_idx[i] * P + d];
-  double s = coords[(size_t)s_idx[i] * P + d];
-  q[t] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz[i]));  // numpy's rounding, no FMA
-}
-
-__global__ void stretch_accept_kernel(double* __restrict__ coords, double* __restrict__ lp, int P,
-                                      const int* __restrict__ s_idx, const double* __restrict__ q,
-                                      const double* __restrict__ new_lp,
-                                      const double* __restrict__ zz,
-                                      const double* __restrict__ lnu, int Ns,
-                                      int* __restrict__ accepted) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Ns) return;
-  int s = s_idx[i];
-  double lnpdiff = (P - 1) * log(zz[i]) + new_lp[i] - lp[s];
-  int acc = lnpdiff > lnu[i];
-  if (acc) {
-    for (int d = 0; d < P; ++d) coords[(size_t)s * P + d] = q[(size_t)i * P + d];
-    lp[s] = new_lp[i];
-  }
-  accepted[i] = acc;
-}
-
-
-// ---------------------------------------------------------------------------
 // parameter map + priors: one thread per walker
 // ---------------------------------------------------------------------------
 struct ParamMapArgs {
@@ -764,28 +691,6 @@ struct ParamMapArgs {
   double* out;
   double* prior_out;
 };
-
-__global__ void param_map_kernel(ParamMapArgs a) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= a.W) return;
-  const double* p = a.pars + (size_t)w * a.P;
-  for (int k = 0; k < a.n_out; ++k) {
-    const nb_parmap m = a.map[k];
-    double v = m.scale;
-    if (m.src >= 0) {
-      double x = p[m.src];
-      if (m.fn == NB_FN_POW10) x = pow(10.0, x);
-      else if (m.fn == NB_FN_EXP) x = exp(x);
-      v = x * m.scale;
-    }
-    a.out[m.dst_off + (long long)w * m.dst_stride] = v;
-  }
-  if (a.prior_out) {
-    double lp = 0.0;
-    for (int k = 0; k < a.n_pri; ++k) lp += prior_eval(a.pri[k].kind, p[a.pri[k].par], a.pri[k].a, a.pri[k].b);
-    a.prior_out[w] = lp;
-  }
-}
 
 // ---------------------------------------------------------------------------
 // fused per-walker set-up: parameter map + priors, then every particle-distribution
@@ -813,7 +718,7 @@ struct WalkerPrepArgs {
 };
 
 __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant__ WalkerPrepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_node = reinterpret_cast<double*>(smem_raw);  // energy items: n at every node
   __shared__ double s_pm[NB_MAX_MAP];
   __shared__ double s_n[PREP_CHUNK + 1];
@@ -967,100 +872,42 @@ __device__ __forceinline__ void warp_walker_params(const WalkerSrc& s, int w, lo
   *scalar = scalar_entry >= 0 ? sc : 0.0;
 }
 
-struct ContractFusedArgs {
-  ContractArgs a;  // xn / ds1 / wpitch unused
-  WalkerSrc src;
-  PdDesc pd;
+// ---------------------------------------------------------------------------
+// synchrotron: CTA = (walker, strided slice of photon energies)
+// ---------------------------------------------------------------------------
+struct SynArgs {
+  const double* gam;
+  int N;
+  const double* gm2;  // g^-2 per node, or NULL (computed here)
+  const double* g23;  // cbrt(g^-2) per node, or NULL
+  const double* xn;   // operand arrays [W][wpitch] (plain kernel; NULL in the fused kernel)
+  const double* ds1;
+  int wpitch;
+  const double* invdlx;
+  const double* dlx;
+  const double* B;    // [W] (plain kernel)
+  int W;
+  const double* E_erg;
+  int N_E;
+  double* out;
+  int out_ld;         // row pitch of out (>= N_E)
+  int e_per_cta;
 };
 
-template <int RT>
-__global__ void __launch_bounds__(256, 3) contract_fused_kernel(
-    const __grid_constant__ ContractFusedArgs fa) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ PdLog s_S[8];  // per warp: keeps the distribution constants out of registers
-  const ContractArgs& a = fa.a;
-  double* sK = reinterpret_cast<double*>(smem_raw);
-  double* sL = sK + (size_t)RT * a.pitch;
-  double* sX = sL + (size_t)RT * a.pitch;  // grid tables: x, ln x, dlx, invdlx
-  double* sLX = sX + a.pitch;
-  double* sDL = sLX + a.pitch;
-  double* sIDL = sDL + a.pitch;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sIDL + a.pitch);
-
-  const int row0 = blockIdx.x * RT;
-  const int nrows = min(RT, a.R - row0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    ptx::mbarrier_init(bar, 1);
-    ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t bytes = (uint32_t)nrows * (uint32_t)a.pitch * 8u;
-    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar,
-                                   2u * bytes);
-    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK,
-                       a.K + (size_t)row0 * a.pitch, bytes, bar);
-    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL,
-                       a.lrs + (size_t)row0 * a.pitch, bytes, bar);
-  }
-  if (fa.src.has_mv) wait_for_peers(fa.src.mv);
-  for (int j = threadIdx.x; j < a.N; j += blockDim.x) {
-    sX[j] = a.xgrid[j];
-    sLX[j] = fa.pd.lnx[j];
-    if (j < a.N - 1) {
-      sDL[j] = a.dlx[j];
-      sIDL[j] = fa.pd.invdlx[j];
-    }
-  }
-  __syncthreads();
-  while (!ptx::mbarrier_try_wait_parity(bar, 0)) {
-  }
-
-  const int nint = a.N - 1;
-  const int i0 = lane * a.m;
-  const int i1 = min(i0 + a.m, nint);
-  const int wbeg = blockIdx.y * a.w_per_cta;
-  const int wend = min(wbeg + a.w_per_cta, a.W);
-  const int nwarps = blockDim.x >> 5;
-  for (int w = wbeg + warp; w < wend; w += nwarps) {
-    double pp[PD_MAXPAR], unused;
-    warp_walker_params(fa.src, w, fa.pd.pd_off, -1, pp, &unused);
-    if (lane == 0) {
-      PdLog S = pd_log_setup(fa.pd.kind, pp, fa.pd.n_scale);
-      pd_log_setup_grid(S, fa.pd.e_mul1, fa.pd.e_mul2);
-      s_S[warp] = S;
-    }
-    __syncwarp();
-    double acc[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-    if (i0 < nint)
-      contract_lane_selfprep<RT>(s_S[warp], sX, sLX, sDL, sIDL, sK, sL, a.pitch, i0, i1, acc);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      double v = warp_sum(acc[r]);
-      if (lane == 0 && r < nrows) {
-        int row = row0 + r;
-        if (a.coef) v *= a.coef[row];
-        a.out[(size_t)w * a.R + row] = v;
-      }
-    }
-  }
-}
-
 struct SynFusedArgs {
-  SynArgs a;  // xn / ds1 / wpitch / B / invdlx unused
+  SynArgs a;
   WalkerSrc src;
   PdDesc pd;
   int b_entry;
 };
 
-__global__ void __launch_bounds__(256) synchrotron_fused_kernel(
-    const __grid_constant__ SynFusedArgs fa) {
+// FUSED: warp 0 derives the walker's parameters (proposal -> parameter map -> log-space
+// constants) and the CTA evaluates the particle distribution at the nodes itself; else the
+// operands come from nb_pd_prep's arrays.
+template <bool FUSED>
+__device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFusedArgs* fa) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SynArgs& a = fa.a;
+  // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx; per photon energy: first live node
   double* s_iec = reinterpret_cast<double*>(smem_raw);
   double* s_cb = s_iec + a.N;
   double* s_xn = s_cb + a.N;
@@ -1075,22 +922,32 @@ __global__ void __launch_bounds__(256) synchrotron_fused_kernel(
   const int w = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nint = a.N - 1;
+  // this CTA's photon energies: e = blockIdx.y + k * gridDim.y, k < ne (strided, so that
+  // every slice gets the same mix of cheap and expensive energies)
   const int nsl = gridDim.y;
   const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
-  if (fa.src.has_mv) wait_for_peers(fa.src.mv);
-  if (warp == 0) {
-    double pp[PD_MAXPAR], Bv;
-    warp_walker_params(fa.src, w, fa.pd.pd_off, fa.b_entry, pp, &Bv);
-    if (lane == 0) {
-      PdLog S = pd_log_setup(fa.pd.kind, pp, fa.pd.n_scale);
-      pd_log_setup_grid(S, fa.pd.e_mul1, fa.pd.e_mul2);
-      s_S = S;
-      s_B = Bv;
-      s_jmin = a.N;
+  if (FUSED) {
+    if (fa->src.has_mv) wait_for_peers(fa->src.mv);
+    if (warp == 0) {
+      double pp[PD_MAXPAR], Bv;
+      warp_walker_params(fa->src, w, fa->pd.pd_off, fa->b_entry, pp, &Bv);
+      if (lane == 0) {
+        PdLog S = pd_log_setup(fa->pd.kind, pp, fa->pd.n_scale);
+        pd_log_setup_grid(S, fa->pd.e_mul1, fa->pd.e_mul2);
+        s_S = S;
+        s_B = Bv;
+        s_jmin = a.N;
+      }
     }
+  } else if (threadIdx.x == 0) {
+    s_B = a.B[w];
+    s_jmin = a.N;
   }
   __syncthreads();
   const double Bw = s_B;
+  // nodes whose exp(-E/Ec) underflows to zero contribute nothing: find, per photon
+  // energy, the first node that can be non-zero, and only set up nodes from the
+  // smallest of them on
   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
     int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[blockIdx.y + k * nsl]);
     s_js[k] = js;
@@ -1098,21 +955,40 @@ __global__ void __launch_bounds__(256) synchrotron_fused_kernel(
   }
   __syncthreads();
   const int jmin = s_jmin;
+  double ikB, cbk;
+  syn_walker(Bw, &ikB, &cbk);
   for (int j = jmin + threadIdx.x; j < a.N; j += blockDim.x) {
     const double g = a.gam[j];
-    syn_node(g, Bw, &s_iec[j], &s_cb[j]);
-    const PdNode nd = pd_log_node_tab(s_S, g, fa.pd.lnx[j]);
-    s_xn[j] = g * pd_log_value_fast(s_S, nd);
-    if (j < nint) {
-      const double idl = fa.pd.invdlx[j];
-      const PdNode nd2 = pd_log_node_tab(s_S, a.gam[j + 1], fa.pd.lnx[j + 1]);
-      s_ds[j] = pd_log_ds1(s_S, nd, nd2, idl);
-      s_idl[j] = idl;
-      s_dl[j] = a.dlx[j];
+    if (a.gm2) {
+      s_iec[j] = ikB * a.gm2[j];
+      s_cb[j] = cbk * a.g23[j];
+    } else {
+      syn_node(g, Bw, &s_iec[j], &s_cb[j]);
+    }
+    if (FUSED) {
+      const PdNode nd = pd_log_node_tab(s_S, g, fa->pd.lnx[j]);
+      s_xn[j] = g * pd_log_value_fast(s_S, nd);
+      if (j < nint) {
+        const double idl = a.invdlx[j];
+        const PdNode nd2 = pd_log_node_tab(s_S, a.gam[j + 1], fa->pd.lnx[j + 1]);
+        s_ds[j] = pd_log_ds1(s_S, nd, nd2, idl);
+        s_idl[j] = idl;
+        s_dl[j] = a.dlx[j];
+      }
+    } else {
+      s_xn[j] = a.xn[(size_t)w * a.wpitch + j];
+      s_ds[j] = a.ds1[(size_t)w * a.wpitch + j];
+      if (j < nint) {
+        s_idl[j] = a.invdlx[j];
+        s_dl[j] = a.dlx[j];
+      }
     }
   }
   __syncthreads();
 
+  // each photon energy is integrated by a pair of warps (64 lanes, ~5 intervals per lane
+  // on the default grids): the per-lane chains are serial, so short chains and many warps
+  // are what keeps the fp64 pipe busy.  The two partial sums meet in shared memory.
   double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
   const int pair = warp >> 1, half = warp & 1;
   for (int k = pair; k < ne; k += 4) {
@@ -1133,8 +1009,17 @@ __global__ void __launch_bounds__(256) synchrotron_fused_kernel(
   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
     const int e = blockIdx.y + k * nsl;
     const double acc = s_part[2 * k] + s_part[2 * k + 1];
-    a.out[(size_t)w * a.N_E + e] = syn_finish(Bw, a.E_erg[e], acc);
+    a.out[(size_t)w * a.out_ld + e] = syn_finish(Bw, a.E_erg[e], acc);
   }
+}
+
+__global__ void __launch_bounds__(256) synchrotron_kernel(const __grid_constant__ SynArgs a) {
+  synchrotron_cta<false>(a, nullptr);
+}
+
+__global__ void __launch_bounds__(256) synchrotron_fused_kernel(
+    const __grid_constant__ SynFusedArgs fa) {
+  synchrotron_cta<true>(fa.a, &fa);
 }
 
 // ---------------------------------------------------------------------------
@@ -1195,92 +1080,200 @@ __global__ void __launch_bounds__(256) ic_seed_spectrum_kernel(
 }
 
 // ---------------------------------------------------------------------------
-// device-resident stretch move (draws resident for n_steps, step index on device)
+// synchrotron self-Compton: IC on a seed photon field that differs per walker
+// (radiative.py:609-655 with the seed density of examples/CrabNebula_SynSSC.py:24-28)
+//
+//   spec[w][e] = Eph_e/E_e * trapz_g( n_e[w][g] * 3/4 sigma_T c / g^2 *
+//                       trapz_s( F[e][g][s] * phn[w][s] / eps0_s , eps0 ), gam )
+//
+// F = f_AA81(gam_g, eps0_s, Eph_e) (incl. its two step functions) does not depend on the
+// walker: it is tabulated once, s-major (Ft[s][r], r = e*N + g, so that consecutive threads
+// = consecutive rows read consecutive addresses), together with its log-slopes along s.
+// Per half-step:  ssc_seed_kernel (seed density and its slopes from the synchrotron
+// luminosities) -> ssc_inner_kernel (the N_s-long inner trapezoid of every (e, g) row for
+// all walkers: 8.7 M rows x intervals per walker at C4, the heavy part) -> ssc_outer_kernel
+// (the outer trapezoid over gam).
 // ---------------------------------------------------------------------------
-__global__ void stretch_move_kernel(const double* __restrict__ coords, int P, int Ns, int split,
-                                    const int* __restrict__ step, const int* __restrict__ s_idx,
-                                    const int* __restrict__ c_idx, const double* __restrict__ zz,
-                                    double* __restrict__ q) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Ns * P) return;
-  size_t base = ((size_t)(*step) * 2 + split) * Ns;
-  int i = t / P, d = t - i * P;
-  double c = coords[(size_t)c_idx[base + i] * P + d];
-  double s = coords[(size_t)s_idx[base + i] * P + d];
-  q[t] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz[base + i]));  // numpy's rounding, no FMA
-}
-
-__global__ void stretch_update_kernel(double* __restrict__ coords, double* __restrict__ lp,
-                                      double* __restrict__ blobs, int nb, int P, int Ns, int split,
-                                      const int* __restrict__ step, const int* __restrict__ s_idx,
-                                      const double* __restrict__ zz, const double* __restrict__ lnu,
-                                      const double* __restrict__ q,
-                                      const double* __restrict__ new_lp,
-                                      const double* __restrict__ new_blobs,
-                                      int* __restrict__ n_accepted) {
-  // one warp per proposal: lanes copy the blob row
-  int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (i >= Ns) return;
-  size_t base = ((size_t)(*step) * 2 + split) * Ns;
-  int s = s_idx[base + i];
-  double nl = new_lp[i];
-  double lnpdiff = (P - 1) * log(zz[base + i]) + nl - lp[s];
-  bool acc = lnpdiff > lnu[base + i];
-  if (acc) {
-    for (int d = lane; d < P; d += 32) coords[(size_t)s * P + d] = q[(size_t)i * P + d];
-    for (int d = lane; d < nb; d += 32) blobs[(size_t)s * nb + d] = new_blobs[(size_t)i * nb + d];
-    if (lane == 0) {
-      lp[s] = nl;
-      n_accepted[s] += 1;
+__global__ void ssc_table_kernel(const double* __restrict__ gam, int N,
+                                 const double* __restrict__ Eph, int N_E,
+                                 const double* __restrict__ eps0,
+                                 const double* __restrict__ invdlx_s, int Ns,
+                                 double* __restrict__ Ft, double* __restrict__ Lt,
+                                 double* __restrict__ coef, long long Rp) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rp) return;
+  const long long R = (long long)N_E * N;
+  if (r >= R) {  // padding rows: zero integrand, sentinel slope
+    for (int s = 0; s < Ns; ++s) {
+      Ft[s * Rp + r] = 0.0;
+      Lt[s * Rp + r] = NB_BIG_SLOPE;
     }
+    coef[r] = 0.0;
+    return;
   }
+  const int e = (int)(r / N), j = (int)(r - (long long)e * N);
+  const double g = gam[j], ep = Eph[e];
+  double f1 = ic_mono_f(g, eps0[0], ep);
+  Ft[r] = f1;
+  for (int s = 1; s < Ns; ++s) {
+    const double f2 = ic_mono_f(g, eps0[s], ep);
+    Ft[s * Rp + r] = f2;
+    Lt[(s - 1) * Rp + r] = slope_or_sentinel(f1, f2, invdlx_s[s - 1]);
+    f1 = f2;
+  }
+  Lt[(long long)(Ns - 1) * Rp + r] = 0.0;
+  coef[r] = (3.0 / 4.0) * SIGT * 29979245800.0 / (g * g);
 }
 
-__global__ void stretch_store_kernel(const double* __restrict__ coords,
-                                     const double* __restrict__ lp,
-                                     const double* __restrict__ blobs, int nb, int W, int P,
-                                     int* __restrict__ step, double* __restrict__ chain,
-                                     double* __restrict__ chain_lp,
-                                     double* __restrict__ chain_blobs) {
-  // single CTA so the step increment is ordered after every read of *step
-  const size_t t = (size_t)(*step);
-  if (chain)
-    for (int k = threadIdx.x; k < W * P; k += blockDim.x) chain[t * W * P + k] = coords[k];
-  if (chain_lp)
-    for (int k = threadIdx.x; k < W; k += blockDim.x) chain_lp[t * W + k] = lp[k];
-  if (chain_blobs)
-    for (int k = threadIdx.x; k < W * nb; k += blockDim.x)
-      chain_blobs[t * W * nb + k] = blobs[k];
+
+struct SscSeedArgs {
+  const double* src[NB_SSC_MAX_SRC];  // luminosities [W][ld] in 1/(s eV)
+  int ld[NB_SSC_MAX_SRC], off[NB_SSC_MAX_SRC];
+  double fac[NB_SSC_MAX_SRC];         // -> dn/dE in 1/(mec2 cm3)
+  int n_src, W, Ns, spitch;
+  const double* invdlx_s;
+  double* sxn;  // [W][spitch] seed density (the contraction's x*y operand: eps0 * phn/eps0)
+  double* sds;  // [W][spitch] its slope term d ln(phn/eps0)/d ln eps0 + 1
+};
+
+__global__ void ssc_seed_kernel(const __grid_constant__ SscSeedArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+  if (s >= a.spitch) return;
+  double p1 = 0.0, p2 = 0.0;
+  if (s < a.Ns)
+    for (int k = 0; k < a.n_src; ++k) {
+      const double* row = a.src[k] + (size_t)w * a.ld[k] + a.off[k];
+      p1 += a.fac[k] * row[s];
+      if (s + 1 < a.Ns) p2 += a.fac[k] * row[s + 1];
+    }
+  a.sxn[(size_t)w * a.spitch + s] = p1;
+  a.sds[(size_t)w * a.spitch + s] = (s + 1 < a.Ns) ? slope_or_sentinel(p1, p2, a.invdlx_s[s]) : 0.0;
+}
+
+struct SscInnerArgs {
+  const double* Ft;
+  const double* Lt;
+  const double* coef;  // [Rp]
+  long long Rp;        // row pitch of the s-major tables (multiple of 128)
+  int Ns;
+  const double* sxn;
+  const double* sds;
+  int spitch, W;
+  const double* dlx_s;  // [Ns-1] ln(eps0[s+1]/eps0[s]) (careful cell only)
+  double* inner;        // [W][Rp]
+};
+
+// thread = one (e, g) row, WT walkers in registers; the walkers' seed operands sit in shared
+// memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell
+template <int WT>
+__global__ void __launch_bounds__(128) ssc_inner_kernel(const __grid_constant__ SscInnerArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* s_op = reinterpret_cast<double2*>(smem_raw);           // [Ns][WT]
+  double* s_x0 = reinterpret_cast<double*>(s_op + (size_t)WT * a.Ns);  // [WT]
+  const int w0 = blockIdx.x * WT;
+  const int Ns = a.Ns;
+  for (int k = threadIdx.x; k < WT * Ns; k += blockDim.x) {
+    const int s = k / WT, wl = k - s * WT, w = w0 + wl;
+    double2 v = make_double2(0.0, NB_BIG_SLOPE);
+    if (w < a.W && s + 1 < Ns)
+      v = make_double2(a.sxn[(size_t)w * a.spitch + s + 1], a.sds[(size_t)w * a.spitch + s]);
+    s_op[k] = v;
+  }
+  if (threadIdx.x < WT)
+    s_x0[threadIdx.x] = (w0 + (int)threadIdx.x < a.W) ? a.sxn[(size_t)(w0 + threadIdx.x) * a.spitch]
+                                                      : 0.0;
   __syncthreads();
-  if (threadIdx.x == 0) *step = (int)t + 1;
+  const long long r = (long long)blockIdx.y * blockDim.x + threadIdx.x;  // < Rp by construction
+  const double* Kc = a.Ft + r;
+  const double* Lc = a.Lt + r;
+  double acc[WT], prev[WT];
+  unsigned worst = 0u;
+  const double k1 = Kc[0];
+#pragma unroll
+  for (int w = 0; w < WT; ++w) {
+    acc[w] = 0.0;
+    prev[w] = s_x0[w] * k1;
+  }
+  double k2 = Kc[a.Rp], l = Lc[0];
+  const double2* op_s = s_op;
+#pragma unroll 2
+  for (int s = 0; s < Ns - 1; ++s, op_s += WT) {
+    const int sn = (s + 1 < Ns - 1) ? s + 1 : s;  // the last prefetch repeats (unused)
+    const double k2n = Kc[(long long)(sn + 1) * a.Rp], ln = Lc[(long long)sn * a.Rp];
+#pragma unroll
+    for (int w = 0; w < WT; ++w) {
+      const double2 op = op_s[w];
+      const double xy2 = op.x * k2;
+      cell_lean(prev[w], xy2, op.y + l, acc[w], worst);
+      prev[w] = xy2;
+    }
+    k2 = k2n;
+    l = ln;
+  }
+  const double cf = a.coef[r];
+  if (worst >= NB_REG_RANGE) {
+    // an irregular slope somewhere on this row (sign change in the table, |b+1| <= 1e-10,
+    // NaN operands): redo the row with the careful cell
+#pragma unroll 1
+    for (int w = 0; w < WT; ++w) {
+      double xy1 = s_x0[w] * Kc[0], t = 0.0;
+      for (int s = 0; s < Ns - 1; ++s) {
+        const double2 op = s_op[s * WT + w];
+        const double xy2 = op.x * Kc[(long long)(s + 1) * a.Rp];
+        t += interval_fast(xy1, xy2, op.y + Lc[(long long)s * a.Rp], a.dlx_s[s]);
+        xy1 = xy2;
+      }
+      if (w0 + w < a.W) a.inner[(size_t)(w0 + w) * a.Rp + r] = t * cf;
+    }
+    return;
+  }
+#pragma unroll
+  for (int w = 0; w < WT; ++w)
+    if (w0 + w < a.W) a.inner[(size_t)(w0 + w) * a.Rp + r] = acc[w] * cf;
+}
+
+struct SscOuterArgs {
+  const double* inner;  // [W][Rp], row e*N + g
+  long long Rp;
+  int N, N_E, W;
+  const double* xn;     // electron operands on the gam grid [W][wpitch]
+  const double* ds1;
+  int wpitch;
+  const double* dlx;
+  const double* invdlx;
+  const double* coef_e;  // [N_E] Eph/E_eV
+  double* out;
+  int out_ld, out_off;
+};
+
+// one warp per (walker, photon energy): outer trapezoid over gam, careful cell (the inner
+// integral's own slope needs one log per node)
+__global__ void __launch_bounds__(256) ssc_outer_kernel(const __grid_constant__ SscOuterArgs a) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= a.W * a.N_E) return;
+  const int w = gw / a.N_E, e = gw - w * a.N_E;
+  const double* in = a.inner + (size_t)w * a.Rp + (size_t)e * a.N;
+  const double* xn = a.xn + (size_t)w * a.wpitch;
+  const double* ds = a.ds1 + (size_t)w * a.wpitch;
+  double acc = 0.0;
+  for (int j = lane; j < a.N - 1; j += 32) {
+    const double y1 = in[j], y2 = in[j + 1];
+    const double bp1 = ds[j] + log(y2 / y1) * a.invdlx[j];
+    acc += interval_fast(xn[j] * y1, xn[j + 1] * y2, bp1, a.dlx[j]);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) a.out[(size_t)w * a.out_ld + a.out_off + e] = a.coef_e[e] * acc;
 }
 
 // ---------------------------------------------------------------------------
 // accept step + chain append from all-gathered packed records (walker sharding): one
 // warp per proposal of the active half, identical on every rank
 // ---------------------------------------------------------------------------
-struct UpdateWait {
-  int world;                        // 0: no waiting (records came through a collective)
-  const unsigned long long* flags;  // this rank's flag array [world]
-  unsigned long long* gen;
-};
-
 __global__ void __launch_bounds__(128) stretch_update_packed_kernel(
-    const __grid_constant__ nb_stretch mv, const double* __restrict__ pack, int ld,
-    const __grid_constant__ UpdateWait uw) {
+    const __grid_constant__ nb_stretch mv, const double* __restrict__ pack, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 4 + warp;
   const int t_step = *mv.step;
-  unsigned long long epoch = 0;
-  if (uw.world > 0) {
-    // every peer's slice of this half-step must have landed in our buffer
-    epoch = *uw.gen + 1ull;
-    if ((int)threadIdx.x < uw.world)
-      while (ld_acquire_sys(uw.flags + threadIdx.x) < epoch) {
-      }
-    __syncthreads();
-  }
   if (i < mv.Ns) {
     const size_t base = ((size_t)t_step * 2 + mv.split) * mv.Ns + i;
     const int sidx = mv.s_idx[base];
@@ -1306,18 +1299,18 @@ __global__ void __launch_bounds__(128) stretch_update_packed_kernel(
         mv.lp[sidx] = lv;
         mv.n_accepted[sidx] += 1;
       }
-      if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = acc ? lv : lp_old;
+      // a NaN log-probability is recorded in the chain (the host raises on it)
+      if (mv.chain_lp) mv.chain_lp[(size_t)t_step * W_ + sidx] = (acc || lv != lv) ? lv : lp_old;
     }
   }
-  if (mv.split == 1 || uw.world > 0) {
+  if (mv.split == 1) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       int ticket = atomicAdd(mv.sync, 1);
       if (ticket == (int)gridDim.x - 1) {
         *mv.sync = 0;
-        if (mv.split == 1) *mv.step = t_step + 1;
-        if (uw.world > 0) *uw.gen = epoch;
+        *mv.step = t_step + 1;
       }
     }
   }
@@ -1465,20 +1458,6 @@ int nb_ic_seed_table(const double* gam, int N, const double* Eph, int N_E, const
   return 0;
 }
 
-int nb_ic_seed_table_batched(const double* gam, int N, const double* Eph, int N_E,
-                             const double* eps0, const double* phn, int Ns, int W, double* K,
-                             int pitch, void* stream) {
-  if (!gam || !Eph || !eps0 || !phn || !K || N < 2 || N_E < 1 || Ns < 1 || pitch < N || W < 0)
-    return NB_EINVAL;
-  if (W == 0) return 0;
-  if (W > 65535) return NB_ETOOLARGE;
-  dim3 grid((pitch + 127) / 128, N_E, W);
-  ic_seed_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(
-      gam, N, Eph, N_E, eps0, phn, Ns, Ns, K, pitch, 0, (long long)N_E * pitch);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
 int nb_brems_table(const double* gam, int N, const double* eps, int N_E, double* K, int pitch,
                    int row0, void* stream) {
   if (!gam || !eps || !K || N < 2 || N_E < 1 || pitch < N || row0 < 0) return NB_EINVAL;
@@ -1525,39 +1504,55 @@ int nb_table_finalize(const double* K, int R, int N, int pitch, const double* in
 
 }  // extern "C"
 
-template <int RT, bool EXACT>
+template <int RT, int MODE>
 static int launch_contract(const ContractArgs& a, int smem, cudaStream_t st) {
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(contract_kernel<RT, EXACT>,
+    cudaError_t e = cudaFuncSetAttribute(contract_kernel<RT, MODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
-  contract_kernel<RT, EXACT><<<grid, 256, smem, st>>>(a);
+  contract_kernel<RT, MODE><<<grid, 256, smem, st>>>(a);
   NB_CHECK_LAUNCH();
   return 0;
 }
 
+template <int MODE>
+static int dispatch_contract(int RT, const ContractArgs& a, int smem, cudaStream_t st) {
+  if (RT == 8) return launch_contract<8, MODE>(a, smem, st);
+  if (RT == 4) return launch_contract<4, MODE>(a, smem, st);
+  return launch_contract<2, MODE>(a, smem, st);
+}
+
 extern "C" {
 
-int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
-                long long K_wstride, const double* xn, const double* ds1, int wpitch, int W,
-                const double* dlx, const double* xgrid, const double* coef, double* out,
-                int exact, void* stream) {
-  if (!K || !xn || !out || R < 1 || N < 2 || pitch < N || wpitch < N || W < 0)
+int nb_table_scan(const double* K, int R, int N, int pitch, int* row_j0, int* flags,
+                  void* stream) {
+  if (!K || !row_j0 || !flags || R < 1 || N < 2 || pitch < N) return NB_EINVAL;
+  table_scan_kernel<<<(R * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(K, R, N, pitch, row_j0,
+                                                                         flags);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_contract_ex(const double* K, const double* lrs, int R, int N, int pitch,
+                   const int* row_j0, const double* xn, const double* ds1, int wpitch, int W,
+                   const double* dlx, const double* xgrid, const double* coef, double* out,
+                   int mode, void* stream) {
+  if (!K || !xn || !out || R < 1 || N < 2 || pitch < N || wpitch < N || W < 0 || mode < 0 ||
+      mode > 2)
     return NB_EINVAL;
+  const bool exact = mode == 1;
   if (!exact && (!lrs || !ds1 || !dlx)) return NB_EINVAL;
   if (exact && !xgrid) return NB_EINVAL;
-  if (K_wstride != 0) return NB_EINVAL;  // per-walker tables go through nb_contract_batched
   if ((pitch & 1) || ((uintptr_t)K & 15) || (lrs && ((uintptr_t)lrs & 15))) return NB_EALIGN;
   if (W == 0) return 0;
   ContractArgs a;
   a.K = K; a.lrs = lrs; a.R = R; a.N = N; a.pitch = pitch;
   a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch; a.W = W;
-  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out;
-  a.m = odd_chunk(N - 1);
+  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out; a.row_j0 = row_j0;
   // rows per tile: largest of 8/4/2 whose K+lrs tile stays <= ~96 KB (2 CTAs/SM)
   int narr = exact ? 1 : 2;
   long long row_bytes = (long long)narr * pitch * 8;
@@ -1565,47 +1560,66 @@ int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
   while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
   if (RT * row_bytes + 16 > 227 * 1024) return NB_ETOOLARGE;
   int smem = (int)(RT * row_bytes + 16);
-  // walkers per CTA: enough CTAs to fill 148 SMs twice when W allows it
+  // walkers per CTA (multiple of the 8 warps): as few as keeps the whole grid resident in
+  // one wave (148 SMs x CTAs that fit by shared memory, at most 3 by registers) -- a second
+  // partial wave costs more than longer CTAs
+  int resident = (int)((227LL * 1024) / (smem + 1024));
+  if (resident > 3) resident = 3;
+  if (resident < 1) resident = 1;
   int row_tiles = (R + RT - 1) / RT;
   int wpc = 8;
-  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 4 * 148) wpc <<= 1;
+  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 148LL * resident) wpc <<= 1;
   a.w_per_cta = wpc;
   cudaStream_t st = as_stream(stream);
-  if (exact) {
-    if (RT == 8) return launch_contract<8, true>(a, smem, st);
-    if (RT == 4) return launch_contract<4, true>(a, smem, st);
-    return launch_contract<2, true>(a, smem, st);
-  }
-  if (RT == 8) return launch_contract<8, false>(a, smem, st);
-  if (RT == 4) return launch_contract<4, false>(a, smem, st);
-  return launch_contract<2, false>(a, smem, st);
+  if (mode == 1) return dispatch_contract<1>(RT, a, smem, st);
+  if (mode == 2) return dispatch_contract<2>(RT, a, smem, st);
+  return dispatch_contract<0>(RT, a, smem, st);
 }
 
-int nb_synchrotron(const double* gam, int N, const double* xn, const double* ds1, int wpitch,
-                   const double* invdlx, const double* dlx, const double* B, int W,
-                   const double* E_erg, int N_E, double* out, void* stream) {
-  if (!gam || !xn || !ds1 || !invdlx || !dlx || !B || !E_erg || !out || N < 2 || wpitch < N ||
-      W < 0 || N_E < 1)
-    return NB_EINVAL;
-  if (W == 0) return 0;
-  SynArgs a;
-  a.gam = gam; a.N = N; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
-  a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
+int nb_contract(const double* K, const double* lrs, int R, int N, int pitch,
+                long long K_wstride, const double* xn, const double* ds1, int wpitch, int W,
+                const double* dlx, const double* xgrid, const double* coef, double* out,
+                int exact, void* stream) {
+  if (K_wstride != 0) return NB_EINVAL;  // per-walker seed fields: nb_ssc_*
+  return nb_contract_ex(K, lrs, R, N, pitch, nullptr, xn, ds1, wpitch, W, dlx, xgrid, coef, out,
+                        exact ? 1 : 0, stream);
+}
+
+static int syn_geometry(SynArgs& a, int N, int W, int N_E, long long* smem) {
   // photon energies per CTA: every CTA repeats the per-walker node set-up, so take as
   // many as still leaves >= 2 CTAs per SM (148 SMs), but at least one per warp
   int epc = (N_E + 7) & ~7;
   while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
   a.e_per_cta = epc;
-  long long smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
-  if (smem > 226 * 1024) return NB_ETOOLARGE;
+  *smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
+  return (*smem > 224 * 1024) ? NB_ETOOLARGE : 0;
+}
+
+int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g23,
+                   const double* xn, const double* ds1, int wpitch, const double* invdlx,
+                   const double* dlx, const double* B, int W, const double* E_erg, int N_E,
+                   double* out, int out_ld, void* stream) {
+  if (!gam || !xn || !ds1 || !invdlx || !dlx || !B || !E_erg || !out || N < 2 || wpitch < N ||
+      W < 0 || N_E < 1 || (gm2 == nullptr) != (g23 == nullptr))
+    return NB_EINVAL;
+  if (out_ld == 0) out_ld = N_E;
+  if (out_ld < N_E) return NB_EINVAL;
+  if (W == 0) return 0;
+  SynArgs a;
+  a.gam = gam; a.N = N; a.gm2 = gm2; a.g23 = g23; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
+  a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
+  a.out_ld = out_ld;
+  long long smem;
+  int rc = syn_geometry(a, N, W, N_E, &smem);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synchrotron_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(W, (N_E + epc - 1) / epc);
+  dim3 grid(W, (N_E + a.e_per_cta - 1) / a.e_per_cta);
   synchrotron_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(a);
   NB_CHECK_LAUNCH();
   return 0;
@@ -1651,63 +1665,15 @@ static int fill_pd_desc(PdDesc& d, const nb_pd_desc* pd) {
   return 0;
 }
 
-}  // extern "C"
-
-template <int RT>
-static int launch_contract_fused(const ContractFusedArgs& fa, int smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(contract_fused_kernel<RT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const ContractArgs& a = fa.a;
-  dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
-  contract_fused_kernel<RT><<<grid, 256, smem, st>>>(fa);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" {
-
-int nb_contract_fused(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
-                      const double* lrs, int R, int N, int pitch, int W, const double* dlx,
-                      const double* xgrid, const double* coef, double* out, void* stream) {
-  if (!K || !lrs || !dlx || !xgrid || !out || R < 1 || N < 2 || pitch < N || W < 0)
-    return NB_EINVAL;
-  if ((pitch & 1) || ((uintptr_t)K & 15) || ((uintptr_t)lrs & 15)) return NB_EALIGN;
-  ContractFusedArgs fa;
-  int rc = fill_walker_src(fa.src, src, W);
-  if (rc) return rc;
-  rc = fill_pd_desc(fa.pd, pd);
-  if (rc) return rc;
-  if (W == 0) return 0;
-  ContractArgs& a = fa.a;
-  a.K = K; a.lrs = lrs; a.R = R; a.N = N; a.pitch = pitch;
-  a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0; a.W = W;
-  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out;
-  a.m = odd_chunk(N - 1);
-  long long row_bytes = 2LL * pitch * 8, grid_bytes = 4LL * pitch * 8;
-  int RT = 8;
-  while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
-  if (RT * row_bytes + grid_bytes + 16 > 224 * 1024) return NB_ETOOLARGE;
-  int smem = (int)(RT * row_bytes + grid_bytes + 16);
-  int row_tiles = (R + RT - 1) / RT;
-  int wpc = 8;
-  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 4 * 148) wpc <<= 1;
-  a.w_per_cta = wpc;
-  cudaStream_t st = as_stream(stream);
-  if (RT == 8) return launch_contract_fused<8>(fa, smem, st);
-  if (RT == 4) return launch_contract_fused<4>(fa, smem, st);
-  return launch_contract_fused<2>(fa, smem, st);
-}
-
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
-                         const double* gam, int N, const double* dlx, int W,
-                         const double* E_erg, int N_E, double* out, void* stream) {
-  if (!gam || !dlx || !E_erg || !out || N < 2 || W < 0 || N_E < 1 || b_entry < 0)
+                         const double* gam, int N, const double* gm2, const double* g23,
+                         const double* dlx, int W, const double* E_erg, int N_E, double* out,
+                         int out_ld, void* stream) {
+  if (!gam || !dlx || !E_erg || !out || N < 2 || W < 0 || N_E < 1 || b_entry < 0 ||
+      (gm2 == nullptr) != (g23 == nullptr))
     return NB_EINVAL;
+  if (out_ld == 0) out_ld = N_E;
+  if (out_ld < N_E) return NB_EINVAL;
   SynFusedArgs fa;
   int rc = fill_walker_src(fa.src, src, W);
   if (rc) return rc;
@@ -1717,14 +1683,12 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
   if (W == 0) return 0;
   fa.b_entry = b_entry;
   SynArgs& a = fa.a;
-  a.gam = gam; a.N = N; a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0;
+  a.gam = gam; a.N = N; a.gm2 = gm2; a.g23 = g23; a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0;
   a.invdlx = pd->invdlx; a.dlx = dlx; a.B = nullptr; a.W = W; a.E_erg = E_erg; a.N_E = N_E;
-  a.out = out;
-  int epc = (N_E + 7) & ~7;
-  while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
-  a.e_per_cta = epc;
-  long long smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
-  if (smem > 224 * 1024) return NB_ETOOLARGE;
+  a.out = out; a.out_ld = out_ld;
+  long long smem;
+  rc = syn_geometry(a, N, W, N_E, &smem);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synchrotron_fused_kernel,
@@ -1732,7 +1696,7 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(W, (N_E + epc - 1) / epc);
+  dim3 grid(W, (N_E + a.e_per_cta - 1) / a.e_per_cta);
   synchrotron_fused_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(fa);
   NB_CHECK_LAUNCH();
   return 0;
@@ -1762,25 +1726,18 @@ static int launch_combine(const nb_peers* peers, const nb_stretch* mv, const dou
   ka.has_mv = mv ? 1 : 0;
   ka.pars = pars;
   ka.has_peers = peers ? 1 : 0;
-  ka.bcast = (peers && mv) ? 1 : 0;
   if (peers) {
-    if (peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
+    if (!mv || peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
         peers->rank >= peers->world || !peers->gen || !peers->ticket || !flux_model || !lnp)
       return NB_EINVAL;
-    if (!ka.bcast) {
-      if (peers->i0 < 0 || peers->ld != flux_ld) return NB_EINVAL;
-      for (int p = 0; p < peers->world; ++p)
-        if (!peers->pack[p] || !peers->flags[p]) return NB_EINVAL;
-    } else {
-      if (!peers->arena_local[0] || peers->arena_bytes[0] == 0) return NB_EINVAL;
-      for (int k = 0; k < 2; ++k)
-        if (peers->arena_local[k] && !peers->arena_mc[k])
-          for (int p = 0; p < peers->world; ++p)
-            if (!peers->arena_peer[k][p]) return NB_EINVAL;
-      if (!peers->mc_flags)
+    if (!peers->arena_local[0] || peers->arena_bytes[0] == 0) return NB_EINVAL;
+    for (int k = 0; k < 2; ++k)
+      if (peers->arena_local[k] && !peers->arena_mc[k])
         for (int p = 0; p < peers->world; ++p)
-          if (!peers->flags[p]) return NB_EINVAL;
-    }
+          if (!peers->arena_peer[k][p]) return NB_EINVAL;
+    if (!peers->mc_flags)
+      for (int p = 0; p < peers->world; ++p)
+        if (!peers->flags[p]) return NB_EINVAL;
     ka.peers = *peers;
   }
   if (mv) {
@@ -1846,72 +1803,6 @@ int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* pee
   return launch_combine(peers_host, mv_host, pars, terms_host, n_terms, W, N_E, unit_fac,
                         data_flux, err_lo, err_hi, ul, cl, prior, flux_model, flux_ld, lnp, 1,
                         stream);
-}
-
-int nb_combine_lnprob_push(const nb_peers* peers, int nb, const nb_term* terms_host, int n_terms,
-                           int W, int N_E, const double* unit_fac, const double* data_flux,
-                           const double* err_lo, const double* err_hi, const int* ul,
-                           const double* cl, const double* prior, void* stream) {
-  if (!peers || peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
-      peers->rank >= peers->world || !peers->pack[peers->rank] || nb < N_E ||
-      peers->ld < nb + 1 || peers->i0 < 0)
-    return NB_EINVAL;
-  double* rec0 = peers->pack[peers->rank] + (size_t)peers->i0 * peers->ld;
-  return launch_combine(peers, nullptr, nullptr, terms_host, n_terms, W, N_E, unit_fac,
-                        data_flux, err_lo, err_hi, ul, cl, prior, rec0, peers->ld, rec0 + nb,
-                        peers->ld, stream);
-}
-
-int nb_stretch_propose(const double* coords, int P, const int* s_idx, const int* c_idx,
-                       const double* zz, int Ns, double* q, void* stream) {
-  if (!coords || !s_idx || !c_idx || !zz || !q || P < 1 || Ns < 0) return NB_EINVAL;
-  if (Ns == 0) return 0;
-  int n = Ns * P;
-  stretch_propose_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords, P, s_idx, c_idx,
-                                                                         zz, Ns, q);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
-int nb_stretch_accept(double* coords, double* lp, int P, const int* s_idx, const double* q,
-                      const double* new_lp, const double* zz, const double* lnu, int Ns,
-                      int* accepted, void* stream) {
-  if (!coords || !lp || !s_idx || !q || !new_lp || !zz || !lnu || !accepted || P < 1 || Ns < 0)
-    return NB_EINVAL;
-  if (Ns == 0) return 0;
-  stretch_accept_kernel<<<(Ns + 127) / 128, 128, 0, as_stream(stream)>>>(
-      coords, lp, P, s_idx, q, new_lp, zz, lnu, Ns, accepted);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
-
-int nb_param_map(const double* pars, int W, int P, const nb_parmap* map_host, int n_out,
-                 double* out, const nb_prior* priors_host, int n_priors, double* prior_out,
-                 void* stream) {
-  if (!pars || W < 0 || P < 1 || n_out < 0 || n_out > NB_MAX_MAP || n_priors < 0 ||
-      n_priors > NB_MAX_PRIORS || (n_out > 0 && (!map_host || !out)) ||
-      (n_priors > 0 && !priors_host))
-    return NB_EINVAL;
-  ParamMapArgs a;
-  for (int k = 0; k < n_out; ++k) {
-    a.map[k] = map_host[k];
-    if (a.map[k].src >= P || a.map[k].fn < 0 || a.map[k].fn > NB_FN_EXP ||
-        a.map[k].dst_off < 0 || a.map[k].dst_stride < 0)
-      return NB_EINVAL;
-  }
-  for (int k = 0; k < n_priors; ++k) {
-    a.pri[k] = priors_host[k];
-    if (a.pri[k].par < 0 || a.pri[k].par >= P || a.pri[k].kind < 0 ||
-        a.pri[k].kind > NB_PRIOR_LOGUNIFORM)
-      return NB_EINVAL;
-  }
-  if (W == 0) return 0;
-  a.n_out = n_out; a.n_pri = n_priors; a.W = W; a.P = P;
-  a.pars = pars; a.out = out; a.prior_out = prior_out;
-  param_map_kernel<<<(W + 63) / 64, 64, 0, as_stream(stream)>>>(a);
-  NB_CHECK_LAUNCH();
-  return 0;
 }
 
 static int fill_param_map(ParamMapArgs& a, const double* pars, int W, int P,
@@ -2038,41 +1929,85 @@ int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch
   return 0;
 }
 
-int nb_stretch_move(const double* coords, int P, int Ns, int split, const int* step,
-                    const int* s_idx, const int* c_idx, const double* zz, double* q,
-                    void* stream) {
-  if (!coords || !step || !s_idx || !c_idx || !zz || !q || P < 1 || Ns < 0 || split < 0 ||
-      split > 1)
+int nb_ssc_table(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
+                 const double* invdlx_s, int Ns, double* Ft, double* Lt, double* coef,
+                 long long Rp, void* stream) {
+  if (!gam || !Eph || !eps0 || !invdlx_s || !Ft || !Lt || !coef || N < 2 || N_E < 1 || Ns < 2 ||
+      Rp < (long long)N * N_E || (Rp & 127))
     return NB_EINVAL;
-  if (Ns == 0) return 0;
-  int n = Ns * P;
-  stretch_move_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(coords, P, Ns, split, step,
-                                                                      s_idx, c_idx, zz, q);
+  ssc_table_kernel<<<(unsigned)((Rp + 127) / 128), 128, 0, as_stream(stream)>>>(
+      gam, N, Eph, N_E, eps0, invdlx_s, Ns, Ft, Lt, coef, Rp);
   NB_CHECK_LAUNCH();
   return 0;
 }
 
-int nb_stretch_update(double* coords, double* lp, double* blobs, int nb, int W, int P, int Ns,
-                      int split, int* step, const int* s_idx, const double* zz,
-                      const double* lnu, const double* q, const double* new_lp,
-                      const double* new_blobs, int* n_accepted, double* chain,
-                      double* chain_lp, double* chain_blobs, void* stream) {
-  if (!coords || !lp || !step || !s_idx || !zz || !lnu || !q || !new_lp || !n_accepted ||
-      W < 1 || P < 1 || Ns < 0 || split < 0 || split > 1 || nb < 0 ||
-      (nb > 0 && (!blobs || !new_blobs)))
+int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const double* invdlx_s,
+                double* sxn, double* sds, int spitch, void* stream) {
+  if (!src_host || n_src < 1 || n_src > NB_SSC_MAX_SRC || W < 0 || Ns < 2 || !invdlx_s || !sxn ||
+      !sds || spitch < Ns)
     return NB_EINVAL;
-  cudaStream_t st = as_stream(stream);
-  if (Ns > 0) {
-    stretch_update_kernel<<<(Ns * 32 + 255) / 256, 256, 0, st>>>(
-        coords, lp, blobs, nb, P, Ns, split, step, s_idx, zz, lnu, q, new_lp, new_blobs,
-        n_accepted);
-    NB_CHECK_LAUNCH();
+  SscSeedArgs a;
+  for (int k = 0; k < n_src; ++k) {
+    if (!src_host[k].src || src_host[k].off < 0 || src_host[k].ld < src_host[k].off + Ns)
+      return NB_EINVAL;
+    a.src[k] = src_host[k].src;
+    a.ld[k] = src_host[k].ld;
+    a.off[k] = src_host[k].off;
+    a.fac[k] = src_host[k].fac;
   }
-  if (split == 1) {
-    stretch_store_kernel<<<1, 1024, 0, st>>>(coords, lp, blobs, nb, W, P, step, chain, chain_lp,
-                                             nb > 0 ? chain_blobs : nullptr);
-    NB_CHECK_LAUNCH();
+  a.n_src = n_src; a.W = W; a.Ns = Ns; a.spitch = spitch; a.invdlx_s = invdlx_s;
+  a.sxn = sxn; a.sds = sds;
+  if (W == 0) return 0;
+  if (W > 65535) return NB_ETOOLARGE;
+  dim3 grid((spitch + 127) / 128, W);
+  ssc_seed_kernel<<<grid, 128, 0, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ssc_inner(const double* Ft, const double* Lt, const double* coef, long long Rp, int Ns,
+                 const double* sxn, const double* sds, int spitch, int W, const double* dlx_s,
+                 double* inner, void* stream) {
+  if (!Ft || !Lt || !coef || !sxn || !sds || !dlx_s || !inner || Rp < 128 || (Rp & 127) ||
+      Ns < 2 || spitch < Ns || W < 0)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  if (Rp / 128 > 65535) return NB_ETOOLARGE;
+  SscInnerArgs a;
+  a.Ft = Ft; a.Lt = Lt; a.coef = coef; a.Rp = Rp; a.Ns = Ns; a.sxn = sxn; a.sds = sds;
+  a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
+  constexpr int WT = 16;
+  size_t smem = (size_t)WT * Ns * sizeof(double2) + WT * sizeof(double);
+  if (smem > 200 * 1024) return NB_ETOOLARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ssc_inner_kernel<WT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
   }
+  // walker groups on the fast grid axis: the CTAs that share a row tile run together, so
+  // the table streams from HBM once and is re-read from L2
+  dim3 grid((W + WT - 1) / WT, (unsigned)(Rp / 128));
+  ssc_inner_kernel<WT><<<grid, 128, smem, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const double* xn,
+                 const double* ds1, int wpitch, const double* dlx, const double* invdlx,
+                 const double* coef_e, double* out, int out_ld, int out_off, void* stream) {
+  if (!inner || !xn || !ds1 || !dlx || !invdlx || !coef_e || !out || N < 2 || N_E < 1 || W < 0 ||
+      Rp < (long long)N * N_E || wpitch < N || out_off < 0 || out_ld < out_off + N_E)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  SscOuterArgs a;
+  a.inner = inner; a.Rp = Rp; a.N = N; a.N_E = N_E; a.W = W; a.xn = xn; a.ds1 = ds1;
+  a.wpitch = wpitch; a.dlx = dlx; a.invdlx = invdlx; a.coef_e = coef_e; a.out = out;
+  a.out_ld = out_ld; a.out_off = out_off;
+  long long warps = (long long)W * N_E;
+  ssc_outer_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(a);
+  NB_CHECK_LAUNCH();
   return 0;
 }
 
@@ -2083,31 +2018,7 @@ int nb_stretch_update_packed(const nb_stretch* mv, const double* pack, int ld, v
       ld < mv->nb + 1 + mv->P)
     return NB_EINVAL;
   if (mv->Ns == 0) return 0;
-  UpdateWait uw;
-  uw.world = 0;
-  uw.flags = nullptr;
-  uw.gen = nullptr;
-  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(*mv, pack, ld,
-                                                                                uw);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
-int nb_stretch_update_packed_wait(const nb_stretch* mv, const nb_peers* peers, void* stream) {
-  if (!mv || !peers || peers->world < 1 || peers->world > NB_MAX_PEERS || peers->rank < 0 ||
-      peers->rank >= peers->world || !peers->pack[peers->rank] || !peers->flags[peers->rank] ||
-      !peers->gen || !mv->coords || !mv->lp || !mv->step || !mv->sync || !mv->s_idx ||
-      !mv->zz || !mv->lnu || !mv->n_accepted || mv->P < 1 || mv->Ns < 0 || mv->W < mv->Ns ||
-      mv->split < 0 || mv->split > 1 || mv->nb < 0 || (mv->nb > 0 && !mv->blobs) ||
-      peers->ld < mv->nb + 1 + mv->P)
-    return NB_EINVAL;
-  if (mv->Ns == 0) return 0;
-  UpdateWait uw;
-  uw.world = peers->world;
-  uw.flags = peers->flags[peers->rank];
-  uw.gen = peers->gen;
-  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(
-      *mv, peers->pack[peers->rank], peers->ld, uw);
+  stretch_update_packed_kernel<<<(mv->Ns + 3) / 4, 128, 0, as_stream(stream)>>>(*mv, pack, ld);
   NB_CHECK_LAUNCH();
   return 0;
 }

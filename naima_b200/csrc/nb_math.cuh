@@ -358,6 +358,53 @@ NB_HD double interval_fast(double xy1, double xy2, double bp1, double dlx) {
   return v;
 }
 
+// Sentinel slope for intervals with a zero end point.  Tables (nb_table_finalize) and the
+// self-Compton seed operands store it instead of the +-inf / NaN of ln(0/K).  Its
+// reciprocal is subnormal, which the hardware seed (rcp.approx.ftz.f64) flushes to zero:
+// (x2 y2 - x1 y1) * 0 -- the interval contributes exactly nothing, as utils.py:347 demands,
+// without a zero test in the lean cell.  Table and walker sentinels may add up (1.5 * 2^1023
+// is still finite).  The careful cell (interval_fast) zeroes such intervals by its own test.
+constexpr double NB_BIG_SLOPE = 6.741349255733685e307;  // 1.5 * 2^1022
+
+NB_HD unsigned nb_hiword(double v) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned)__double2hiint(v);
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return (unsigned)(b >> 32);
+#endif
+}
+
+// interval_fast classifies a slope as regular when 1e-10 < |b + 1| < inf, tested on the high
+// word: (hi & 0x7fffffff) - NB_REG_LO < NB_REG_RANGE (unsigned)
+constexpr unsigned NB_REG_LO = 0x3DDB7CE0u;
+constexpr unsigned NB_REG_RANGE = 0x7FF00000u - 0x3DDB7CE0u;
+
+// The lean cell: acc += (xy2 - xy1) / bp1 with the reciprocal from the hardware seed and one
+// cubic step folded into the accumulation -- 8 fp64 instructions, one MUFU and three integer
+// instructions, no select.  It does NOT handle irregular slopes (|b + 1| <= 1e-10, NaN, inf):
+// `worst` keeps the running maximum of the classification word, and the caller re-integrates
+// with interval_fast when worst >= NB_REG_RANGE at the end (rare: tables with sign changes,
+// NaN parameters).  Zero end points must carry the NB_BIG_SLOPE sentinel.
+NB_HD void cell_lean(double xy1, double xy2, double bp1, double& acc, unsigned& worst) {
+  const unsigned t = (nb_hiword(bp1) & 0x7fffffffu) - NB_REG_LO;
+  worst = (t > worst) ? t : worst;
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(bp1));
+  const double e = fma(-bp1, r, 1.0);
+  const double p = fma(e, e, e);
+  const double dr = (xy2 - xy1) * r;
+  acc += dr;
+  acc = fma(dr, p, acc);
+#else
+  double r = 1.0 / bp1;
+  if (fabs(r) < 2.2250738585072014e-308) r = 0.0;  // the seed's flush-to-zero
+  acc += (xy2 - xy1) * r;
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // synchrotron AKP10 Eq. D7
 // ---------------------------------------------------------------------------
@@ -448,6 +495,13 @@ NB_HD double ic_mono_f(double gam, double photE0, double Eph) {
                (1.0 / 2.0) * (bq * bq) * (1 - q) / (1 + b * q);
   double g = fic * heaviside(1 - q) * heaviside(q - 1.0 / (4 * (gam * gam)));
   return (g != g) ? 0.0 : g;
+}
+
+// slope term ln(y2/y1)/ln(x2/x1) of a tabulated factor between neighbouring nodes, with the
+// finite sentinel for zero end points (see NB_BIG_SLOPE); NaN (sign change) stays NaN and
+// selects the careful cell
+NB_HD double slope_or_sentinel(double y1, double y2, double invdlx) {
+  return (y1 == 0.0 || y2 == 0.0) ? NB_BIG_SLOPE : log(y2 / y1) * invdlx;
 }
 
 // ---------------------------------------------------------------------------
@@ -787,34 +841,32 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
   }
 }
 
-// fast contraction with the walker's operands evaluated on the fly from the log-space
-// distribution (no set-up kernel, no operand arrays): xg / lnx / dlx / invdlx are the
-// grid's tables
+// lean contraction (cell_lean): same operands as contract_lane_fast; returns the running
+// maximum of the slope classification word (>= NB_REG_RANGE: some interval was irregular and
+// the caller must redo the range with contract_lane_fast)
 template <int RT>
-NB_HD void contract_lane_selfprep(const PdLog& S, const double* xg, const double* lnx,
-                                  const double* dlx, const double* invdlx, const double* sK,
+NB_HD unsigned contract_lane_lean(const double* xnw, const double* dsw, const double* sK,
                                   const double* sL, int pitch, int i0, int i1, double* acc) {
   double prev[RT];
-  double x1 = xg[i0];
-  PdNode nd1 = pd_log_node_tab(S, x1, lnx[i0]);
-  double n1 = x1 * pd_log_value_fast(S, nd1);
+  unsigned worst = 0u;
+  const double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
+  double n2 = xnw[i0 + 1], d = dsw[i0];
+#pragma unroll 2
   for (int i = i0; i < i1; ++i) {
-    const double x2 = xg[i + 1];
-    const PdNode nd2 = pd_log_node_tab(S, x2, lnx[i + 1]);
-    const double n2 = x2 * pd_log_value_fast(S, nd2);
-    const double d = pd_log_ds1(S, nd1, nd2, invdlx[i]);
-    const double dl = dlx[i];
+    const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
+    const double n2n = xnw[in + 1], dn = dsw[in];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      double xy2 = n2 * sK[r * pitch + i + 1];
-      double bp1 = d + sL[r * pitch + i];
-      acc[r] += interval_fast(prev[r], xy2, bp1, dl);
+      const double xy2 = n2 * sK[r * pitch + i + 1];
+      cell_lean(prev[r], xy2, d + sL[r * pitch + i], acc[r], worst);
       prev[r] = xy2;
     }
-    nd1 = nd2;
+    n2 = n2n;
+    d = dn;
   }
+  return worst;
 }
 
 // exact contraction: reference operation order per interval (nw = n itself)
@@ -845,6 +897,17 @@ NB_HD void syn_node(double g, double B, double* iec, double* cb) {
   double i = 1.0 / Ec;
   *iec = i;
   *cb = cbrt(i);
+}
+
+// the same split into a per-walker and a per-node factor: Ec = kB g^2, so
+// 1/Ec = (1/kB) gm2[j] and cbrt(1/Ec) = cbrt(1/kB) g23[j] with the grid's walker-independent
+// tables gm2 = g^-2, g23 = cbrt(g^-2) -- two multiplications per node instead of a division
+// and a cbrt (agrees with syn_node to 2 ulp)
+NB_HD void syn_walker(double B, double* ikB, double* cbk) {
+  double kB = 3 * E_ESU * HBAR_CGS * B;
+  kB /= 2 * (M_E_G * C_CGS);
+  *ikB = 1.0 / kB;
+  *cbk = cbrt(*ikB);
 }
 
 // rational part of Gtilde with one reciprocal square root:
@@ -892,7 +955,10 @@ NB_HD int syn_first_node(const double* gam, int N, double B, double E_erg) {
 }
 
 // synchrotron lane: integral of x*n*Gtilde(E/Ec) over intervals [i0,i1) with
-// ln(y2/y1) = ln(n2/n1) + ln(R2/R1) - (x2 - x1)
+// ln(y2/y1) = ln(n2/n1) + ln(R2/R1) - (x2 - x1).  Two intervals per iteration: the two new
+// nodes' rational / exponential chains are independent of each other and of the carried node,
+// so they overlap in the pipeline (the kernel is latency bound); the accumulation order is
+// that of the one-interval loop.
 NB_HD double syn_lane(double E, double cbE, const double* s_iec, const double* s_cb,
                       const double* s_xn, const double* s_ds, const double* s_idl,
                       const double* s_dl, int i0, int i1) {
@@ -900,15 +966,27 @@ NB_HD double syn_lane(double E, double cbE, const double* s_iec, const double* s
   double x1 = E * s_iec[i0];
   double R1 = gtilde_rational_fast(cbE * s_cb[i0]);
   double xy1 = s_xn[i0] * (R1 * exp_neg(x1));
-  for (int i = i0; i < i1; ++i) {
-    double x2 = E * s_iec[i + 1];
-    double R2 = gtilde_rational_fast(cbE * s_cb[i + 1]);
-    double xy2 = s_xn[i + 1] * (R2 * exp_neg(x2));
-    double bp1 = s_ds[i] + (log_ratio(R1, R2) - (x2 - x1)) * s_idl[i];
+  int i = i0;
+  for (; i + 1 < i1; i += 2) {
+    const double x2 = E * s_iec[i + 1], x3 = E * s_iec[i + 2];
+    const double R2 = gtilde_rational_fast(cbE * s_cb[i + 1]);
+    const double R3 = gtilde_rational_fast(cbE * s_cb[i + 2]);
+    const double xy2 = s_xn[i + 1] * (R2 * exp_neg(x2));
+    const double xy3 = s_xn[i + 2] * (R3 * exp_neg(x3));
+    const double bpa = s_ds[i] + (log_ratio(R1, R2) - (x2 - x1)) * s_idl[i];
+    const double bpb = s_ds[i + 1] + (log_ratio(R2, R3) - (x3 - x2)) * s_idl[i + 1];
+    acc += interval_fast(xy1, xy2, bpa, s_dl[i]);
+    acc += interval_fast(xy2, xy3, bpb, s_dl[i + 1]);
+    x1 = x3;
+    R1 = R3;
+    xy1 = xy3;
+  }
+  if (i < i1) {
+    const double x2 = E * s_iec[i + 1];
+    const double R2 = gtilde_rational_fast(cbE * s_cb[i + 1]);
+    const double xy2 = s_xn[i + 1] * (R2 * exp_neg(x2));
+    const double bp1 = s_ds[i] + (log_ratio(R1, R2) - (x2 - x1)) * s_idl[i];
     acc += interval_fast(xy1, xy2, bp1, s_dl[i]);
-    x1 = x2;
-    R1 = R2;
-    xy1 = xy2;
   }
   return acc;
 }

@@ -41,6 +41,9 @@ DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 # reference operation order (log10/pow per interval) instead of the hoisted
 # contraction; settable at run time (tests exercise both)
 EXACT = False
+# hoisted contraction: lean cell (8 fp64 instructions per interval, irregular slopes detected
+# and redone with the careful cell) where the table allows it; False: careful cell everywhere
+LEAN = True
 
 
 def device():
@@ -96,7 +99,11 @@ class Grid:
         inv[: self.N - 1] = 1.0 / dlx[: self.N - 1]
         lnx = np.zeros(self.pitch)
         lnx[: self.N] = np.log(self.x)
-        self._host = (pad, dlx, inv, lnx)
+        # synchrotron node tables: 1/Ec = (1/kB) x^-2, cbrt(1/Ec) = cbrt(1/kB) cbrt(x^-2)
+        gm2 = np.zeros(self.pitch)
+        gm2[: self.N] = 1.0 / (self.x * self.x)
+        g23 = np.cbrt(gm2)
+        self._host = (pad, dlx, inv, lnx, gm2, g23)
         self._dev = None
         if species == "electron":  # e = (gam * mec2[erg]) * (erg -> eV); n per unit gam
             self.e_mul1, self.e_mul2, self.n_scale = mec2_erg, erg_eV, mec2_eV
@@ -115,6 +122,8 @@ class Grid:
     dlx_d = property(lambda self: self._device()[1])
     invdlx_d = property(lambda self: self._device()[2])
     lnx_d = property(lambda self: self._device()[3])
+    gm2_d = property(lambda self: self._device()[4])
+    g23_d = property(lambda self: self._device()[5])
 
 
 _GRIDS = OrderedDict()
@@ -211,11 +220,18 @@ class Table:
         self.K = zeros(R, grid.pitch)
         self.lrs = zeros(R, grid.pitch)
         self.coef = None
+        self.row_j0 = None  # first non-zero node per row (leading zeros are skipped)
+        self.clean = False  # no negative / non-finite entry: the lean cell applies
 
     def finalize(self, coef):
         g = self.grid
         check(lib().nb_table_finalize(ptr(self.K), self.R, g.N, g.pitch, ptr(g.invdlx_d),
                                       ptr(self.lrs), stream()), "nb_table_finalize")
+        self.row_j0 = zeros(self.R, dtype=torch.int32)
+        flags = zeros(1, dtype=torch.int32)
+        check(lib().nb_table_scan(ptr(self.K), self.R, g.N, g.pitch, ptr(self.row_j0), ptr(flags),
+                                  stream()), "nb_table_scan")
+        self.clean = int(flags.item()) == 0
         self.coef = to_dev(coef)
         return self
 
@@ -337,10 +353,11 @@ def contract(table, prep, out=None, exact=None):
     out = empty(prep.W, table.R) if out is None else out
     if exact and prep.nraw is None:
         raise ValueError("exact contraction needs pd_prep(need_raw=True)")
-    check(lib().nb_contract(ptr(table.K), ptr(table.lrs), table.R, g.N, g.pitch, 0,
-                            ptr(prep.nraw if exact else prep.xn), ptr(prep.ds1), g.pitch, prep.W,
-                            ptr(g.dlx_d), ptr(g.x_d), ptr(table.coef), ptr(out),
-                            1 if exact else 0, stream()), "nb_contract")
+    mode = 1 if exact else (2 if (LEAN and table.clean) else 0)
+    check(lib().nb_contract_ex(ptr(table.K), ptr(table.lrs), table.R, g.N, g.pitch,
+                               ptr(table.row_j0), ptr(prep.nraw if exact else prep.xn),
+                               ptr(prep.ds1), g.pitch, prep.W, ptr(g.dlx_d), ptr(g.x_d),
+                               ptr(table.coef), ptr(out), mode, stream()), "nb_contract_ex")
     return out
 
 
@@ -348,10 +365,79 @@ def synchrotron(grid, prep, B_d, E_erg_d, out=None):
     """Synchrotron._spectrum (radiative.py:282-342): out[w][e] in 1/(s eV)."""
     N_E = E_erg_d.numel()
     out = empty(prep.W, N_E) if out is None else out
-    check(lib().nb_synchrotron(ptr(grid.x_d), grid.N, ptr(prep.xn), ptr(prep.ds1), grid.pitch,
-                               ptr(grid.invdlx_d), ptr(grid.dlx_d), ptr(B_d), prep.W,
-                               ptr(E_erg_d), N_E, ptr(out), stream()), "nb_synchrotron")
+    check(lib().nb_synchrotron(ptr(grid.x_d), grid.N, ptr(grid.gm2_d), ptr(grid.g23_d),
+                               ptr(prep.xn), ptr(prep.ds1), grid.pitch, ptr(grid.invdlx_d),
+                               ptr(grid.dlx_d), ptr(B_d), prep.W, ptr(E_erg_d), N_E, ptr(out),
+                               out.stride(0), stream()), "nb_synchrotron")
     return out
+
+
+# ------------------------------------------------------------------------------
+# synchrotron self-Compton: IC on a per-walker tabulated seed, hoisted
+# ------------------------------------------------------------------------------
+class SscTable:
+    """f_AA81(gam_g, eps0_s, Eph_e) (radiative.py:621-636), s-major, with its log-slopes
+    along the seed-energy axis: walker independent, built once per (grid, photon energies,
+    seed energies).  Row r = e * N + g, row pitch Rp (multiple of 128)."""
+
+    def __init__(self, grid, E_eV, seed_E_eV):
+        E_eV = np.ascontiguousarray(E_eV, dtype=float)
+        eps0 = np.ascontiguousarray(seed_E_eV, dtype=float) / mec2_eV
+        self.grid, self.N_E, self.Ns = grid, E_eV.size, eps0.size
+        if self.Ns < 2:
+            raise ValueError("a tabulated seed needs at least two energies")
+        self.R = self.N_E * grid.N
+        self.Rp = (self.R + 127) & ~127
+        self.spitch = even(self.Ns)
+        Eph = E_eV * eV_erg / mec2_erg
+        dl = np.zeros(self.spitch)
+        dl[: self.Ns - 1] = np.log(eps0[1:] / eps0[:-1])
+        inv = np.zeros(self.spitch)
+        inv[: self.Ns - 1] = 1.0 / dl[: self.Ns - 1]
+        self.eps0_d, self.Eph_d = to_dev(eps0), to_dev(Eph)
+        self.dlx_s_d, self.invdlx_s_d = to_dev(dl), to_dev(inv)
+        self.coef_e_d = to_dev(Eph / E_eV)  # lum = Eph * integral; spec = lum / E (:684-687)
+        self.Ft = empty(self.Ns, self.Rp)
+        self.Lt = empty(self.Ns, self.Rp)
+        self.coef = empty(self.Rp)
+        check(lib().nb_ssc_table(ptr(grid.x_d), grid.N, ptr(self.Eph_d), self.N_E,
+                                 ptr(self.eps0_d), ptr(self.invdlx_s_d), self.Ns, ptr(self.Ft),
+                                 ptr(self.Lt), ptr(self.coef), self.Rp, stream()), "nb_ssc_table")
+
+
+def ssc_table(grid, E_eV, seed_E_eV):
+    key = ("ssc", grid.key, _ekey(E_eV), _ekey(seed_E_eV))
+    return _cache_get(_TABLES, key, lambda: SscTable(grid, E_eV, seed_E_eV), _TABLES_MAX)
+
+
+def make_ssc_sources(sources):
+    """sources: list of (src tensor [W][ld], off, fac)."""
+    from ._lib import nb_ssc_src
+
+    arr = (nb_ssc_src * len(sources))()
+    for k, (src, off, fac) in enumerate(sources):
+        arr[k].src, arr[k].ld, arr[k].off, arr[k].fac = src.data_ptr(), src.stride(0), off, fac
+    return arr
+
+
+def ssc_seed(tb, sources, W, sxn, sds):
+    """Seed density operands of W walkers from luminosities: nb_ssc_seed."""
+    arr = sources if isinstance(sources, ctypes.Array) else make_ssc_sources(sources)
+    check(lib().nb_ssc_seed(arr, len(arr), W, tb.Ns, ptr(tb.invdlx_s_d), ptr(sxn), ptr(sds),
+                            tb.spitch, stream()), "nb_ssc_seed")
+
+
+def ssc_inner(tb, sxn, sds, W, inner):
+    check(lib().nb_ssc_inner(ptr(tb.Ft), ptr(tb.Lt), ptr(tb.coef), tb.Rp, tb.Ns, ptr(sxn),
+                             ptr(sds), tb.spitch, W, ptr(tb.dlx_s_d), ptr(inner), stream()),
+          "nb_ssc_inner")
+
+
+def ssc_outer(tb, inner, prep, out, out_off=0):
+    g = tb.grid
+    check(lib().nb_ssc_outer(ptr(inner), tb.Rp, g.N, tb.N_E, prep.W, ptr(prep.xn), ptr(prep.ds1),
+                             g.pitch, ptr(g.dlx_d), ptr(g.invdlx_d), ptr(tb.coef_e_d), ptr(out),
+                             out.stride(0), out_off, stream()), "nb_ssc_outer")
 
 
 def ic_seed_spectrum(grid, prep, E_eV, seed_E_eV, phn_d, per_walker, out, out_off):
@@ -391,12 +477,6 @@ def combine(terms, W, N_E, unit_fac_d, flux_out=None, data=None, prior_d=None, l
             ptr(unit_fac_d), ptr(d.flux), ptr(d.err_lo), ptr(d.err_hi), ptr(d.ul), ptr(d.cl),
             ptr(prior_d), ptr(flux_out), flux_ld, ptr(lnp_out), stream()),
             "nb_combine_lnprob_update_push")
-        return
-    if peers is not None:  # records straight into this rank's slice, then pushed to the peers
-        check(lib().nb_combine_lnprob_push(
-            ctypes.byref(peers), nb, arr, len(arr), W, N_E, ptr(unit_fac_d), ptr(d.flux),
-            ptr(d.err_lo), ptr(d.err_hi), ptr(d.ul), ptr(d.cl), ptr(prior_d), stream()),
-            "nb_combine_lnprob_push")
         return
     if mv is not None:
         check(lib().nb_combine_lnprob_update(

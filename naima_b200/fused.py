@@ -201,17 +201,63 @@ class SymFlux:
         if o.sed != self.sed or not np.array_equal(o.E.to("eV").value, self.E.to("eV").value):
             raise TraceError("cannot add fluxes on different energy grids / representations")
         o.unit._factor_to(self.unit)
-        return SymFlux(self.groups + o.groups, self.E, self.unit, self.sed, self.base_unit)
+        f = o.base_unit._factor_to(self.base_unit)  # groups are held in units of base_unit
+        og = o.groups if f == 1.0 else [(c, d, sc * f) for c, d, sc in o.groups]
+        return SymFlux(self.groups + og, self.E, self.unit, self.sed, self.base_unit)
 
     __radd__ = __add__
 
+    def _scaled(self, k, unit_op):
+        """Product with a scalar (plain number or scalar Quantity) k; unit_op(unit, k.unit)."""
+        if isinstance(k, (SymPar, SymFlux)):
+            raise TraceError("product of a flux with a free parameter or another flux")
+        if isinstance(k, Unit):
+            kv, ku = 1.0, k
+        elif isinstance(k, Quantity):
+            if np.ndim(k.value) != 0:
+                raise TraceError("flux times array")
+            kv, ku = float(k.value), k.unit
+        elif np.ndim(k) == 0:
+            kv, ku = float(k), None
+        else:
+            raise TraceError("flux times array")
+        return kv, ku
+
     def __mul__(self, o):
-        if np.ndim(o) == 0 and not isinstance(o, (Quantity, Unit, SymPar)):
-            return SymFlux([(c, d, s * float(o)) for c, d, s in self.groups], self.E, self.unit,
-                           self.sed, self.base_unit)
-        raise TraceError("unsupported product with a flux")
+        kv, ku = self._scaled(o, None)
+        unit = self.unit if ku is None else self.unit * ku
+        base = self.base_unit if ku is None else self.base_unit * ku
+        return SymFlux([(c, d, s * kv) for c, d, s in self.groups], self.E, unit, self.sed, base)
 
     __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        kv, ku = self._scaled(o, None)
+        unit = self.unit if ku is None else self.unit / ku
+        base = self.base_unit if ku is None else self.base_unit / ku
+        return SymFlux([(c, d, s / kv) for c, d, s in self.groups], self.E, unit, self.sed, base)
+
+    def check_seed_density(self, name, energy):
+        """Usable as the photon density of a tabulated IC seed field on `energy`
+        (radiative.py:509-519 conventions)?"""
+        if self.sed:
+            raise TraceError("seed photon field given as an SED of the fit parameters")
+        if self.unit.physical_type != "differential number density":
+            raise TypeError("{0}-density should be given in units of differential number "
+                            "density".format(name))
+        if not np.array_equal(np.atleast_1d(self.E.to("eV").value),
+                              np.atleast_1d(Quantity(energy).to("eV").value)):
+            raise TraceError("seed photon density is not evaluated at the seed energies")
+
+    def seed_sources(self):
+        """[(component, factor)]: density [1/(mec2 cm3)] = sum factor * spectrum[1/(s eV)]."""
+        f = self.base_unit._factor_to("1/(eV cm3)") * eng.mec2_eV
+        return [(c, sc / d * f) for c, d, sc in self.groups]
+
+
+def comp_B(comp):
+    from . import models as M
+    return M._val(comp.B, "G")
 
 
 def eng_nonzero(distance):
@@ -266,7 +312,6 @@ class LikelihoodPlan:
         self.data = data
         self.use_graph = use_graph
         self.selfprep = selfprep
-        self.selfprep_kinds = ("syn",)
         flux, blobs, sp = trace(model, prior, data, self.P)
         self.flux, self.blobs, self.prior = flux, blobs, sp
         E = Quantity(data["energy"])
@@ -314,6 +359,7 @@ class LikelihoodPlan:
         from . import models as M
 
         self.pds, self.preps, self.comps = [], [], []
+        self.aux = []      # auxiliary synchrotron launches (seed fields of the "ssc" components)
         self.scalars = []  # per-walker scalar columns: SymPar or float
 
         def pd_index(pd):
@@ -346,15 +392,42 @@ class LikelihoodPlan:
                 c["prep"] = prep_index(ipd, grid, False)
                 c["B"] = scalar_index(M._val(comp.B, "G"))
             elif isinstance(comp, M.InverseCompton):
-                c["kind"] = "table"
                 c["prep"] = prep_index(ipd, grid, exact)
-                seeds = []
+                seeds, sym = [], []
                 for name, sd in comp.seed_photon_fields.items():
+                    if sd.get("symbolic"):
+                        sym.append(sd)
+                        continue
                     if sd["type"] == "array" and sd["photon_density"].ndim == 2:
-                        raise TraceError("per-walker seed photon fields are not traced")
+                        raise TraceError("per-walker seed photon fields given as arrays are "
+                                         "not traced")
                     seeds.append(comp._seed_tuple(sd))
-                c["table"] = eng.ic_table(grid, self.E_eV, tuple(seeds))
-                c["rows"] = [(s * self.N_E, None) for s in range(len(seeds))]
+                if sym and exact:
+                    raise TraceError("seed fields computed from the fit parameters are traced "
+                                     "in the hoisted mode only")
+                # seed fields that depend on the fit parameters (synchrotron self-Compton):
+                # one "ssc" component each, fed by auxiliary synchrotron launches on the seed
+                # energies; summed after the tabulated seeds of the same InverseCompton
+                extra = []
+                for sd in sym:
+                    seed_E = np.atleast_1d(Quantity(sd["energy"]).to("eV").value).astype(float)
+                    srcs = []
+                    for scomp, fac in sd["photon_density"].seed_sources():
+                        if not isinstance(scomp, M.Synchrotron):
+                            raise TraceError("seed photon fields computed from %s are not "
+                                             "traced" % type(scomp).__name__)
+                        srcs.append((self._aux_index(scomp, seed_E, pd_index, prep_index,
+                                                     scalar_index), fac))
+                    extra.append({"group": gi, "div": div / scale, "obj": comp, "kind": "ssc",
+                                  "prep": c["prep"], "sources": srcs,
+                                  "tb": eng.ssc_table(grid, self.E_eV, seed_E)})
+                if seeds:
+                    c["kind"] = "table"
+                    c["table"] = eng.ic_table(grid, self.E_eV, tuple(seeds))
+                    c["rows"] = [(s * self.N_E, None) for s in range(len(seeds))]
+                    self.comps.append(c)
+                self.comps.extend(extra)
+                continue
             elif isinstance(comp, M.Bremsstrahlung):
                 c["kind"] = "table"
                 c["prep"] = prep_index(ipd, grid, exact)
@@ -378,14 +451,13 @@ class LikelihoodPlan:
             else:
                 raise TraceError("unsupported radiative class %r" % type(comp).__name__)
             self.comps.append(c)
-        # components whose kernels derive the walker's operands themselves (no set-up
-        # launch in front of them); the reference-order (exact) mode keeps the operand arrays
-        # Synchrotron only: its CTAs own one walker, so the operands cost one pass over the
-        # nodes; the contraction would repeat them in every row-tile CTA (+30 % work,
-        # measured slower than reading the arrays of the set-up kernel)
+        # Synchrotron derives the walker's operands itself (no set-up launch in front of it:
+        # its CTAs own one walker, so the operands cost one pass over the nodes); the
+        # reference-order (exact) mode keeps the operand arrays
         for c in self.comps:
-            c["selfprep"] = (self.selfprep and not exact and self.P <= 32
-                             and c["kind"] in self.selfprep_kinds)
+            c["selfprep"] = (self.selfprep and not exact and self.P <= 32 and c["kind"] == "syn")
+        for a in self.aux:
+            a["selfprep"] = a["selfprep"] and self.selfprep and not exact
         # blobs
         self.blob_specs = []
         for b in self.blobs:
@@ -398,6 +470,17 @@ class LikelihoodPlan:
             self.blob_cols.append((off, width))
             off += width
         self.row_width = off
+
+    def _aux_index(self, comp, E_eV, pd_index, prep_index, scalar_index):
+        """Auxiliary synchrotron spectrum of `comp` on photon energies E_eV [1/(s eV)]."""
+        for i, a in enumerate(self.aux):
+            if a["obj"] is comp and np.array_equal(a["E_eV"], E_eV):
+                return i
+        ipd = pd_index(comp.particle_distribution)
+        self.aux.append({"kind": "syn", "obj": comp, "E_eV": np.ascontiguousarray(E_eV),
+                         "prep": prep_index(ipd, comp._grid(), False),
+                         "B": scalar_index(comp_B(comp)), "selfprep": self.P <= 32})
+        return len(self.aux) - 1
 
     def _blob_spec(self, b, pd_index):
         if isinstance(b, SymBlob):
@@ -476,18 +559,33 @@ class LikelihoodPlan:
             ex.preps.append(p)
         terms = []
         ex.outs = []
-        n_groups = len(self.comps)
-        for c in self.comps:
-            if c["kind"] == "syn":
+        ncomp = len(self.comps)
+        for ic, c in enumerate(self.comps):
+            # a group (one radiative component's flux()) closes with its last term
+            last_of_group = ic == ncomp - 1 or self.comps[ic + 1]["group"] != c["group"]
+            if c["kind"] in ("syn", "ssc"):
                 out = eng.zeros(W, self.N_E)
-                terms.append((out, 0, True, c["div"], None))
+                terms.append((out, 0, last_of_group, c["div"], None))
             else:
                 out = eng.zeros(W, c["table"].R)
                 rows = c["rows"]
                 for k, (off, sc) in enumerate(rows):
-                    terms.append((out, off, k == len(rows) - 1, c["div"],
+                    terms.append((out, off, last_of_group and k == len(rows) - 1, c["div"],
                                   scalar_col(sc) if sc is not None else None))
             ex.outs.append(out)
+        # auxiliary synchrotron spectra (seed luminosities) and the self-Compton work buffers
+        ex.aux_outs = [eng.zeros(W, a["E_eV"].size) for a in self.aux]
+        ex.aux_E = [eng.to_dev(a["E_eV"] * eng.eV_erg) for a in self.aux]
+        ex.ssc = {}
+        for ic, c in enumerate(self.comps):
+            if c["kind"] != "ssc":
+                continue
+            tb = c["tb"]
+            ex.ssc[ic] = dict(
+                sxn=eng.zeros(W, tb.spitch), sds=eng.zeros(W, tb.spitch),
+                inner=eng.empty(W, tb.Rp),
+                sources=eng.make_ssc_sources([(ex.aux_outs[ia], 0, fac)
+                                              for ia, fac in c["sources"]]))
         ex.terms = eng.make_terms(terms)
         # one record per walker: [model flux (N_E) | further blobs], so that a sampler
         # moves a walker's blobs with one row copy (row pitch = self.row_width)
@@ -517,6 +615,7 @@ class LikelihoodPlan:
             ex.pd_desc.append(d)
         # operand arrays are only needed by components that do not prepare their own
         needed = set(c["prep"] for c in self.comps if not c["selfprep"])
+        needed |= set(a["prep"] for a in self.aux if not a["selfprep"])
         # jobs of the fused per-walker set-up kernel
         jobs = []
         for ip, (prd, p) in enumerate(zip(self.preps, ex.preps)):
@@ -623,88 +722,65 @@ class LikelihoodPlan:
                                         ex.map, ex.n_map, eng.ptr(ex.pm2), ex.pri, 0, None,
                                         ex.blob_jobs, ex.n_blob_jobs, st), "nb_walker_prep_move")
 
-    def _launch_comp(self, ex, c, out, src):
+    def _launch_syn(self, ex, c, E_erg, out, src):
+        """Synchrotron of component / auxiliary descriptor c on photon energies E_erg."""
         L, W = lib(), ex.W
         p = ex.preps[c["prep"]]
         g = p.grid
         if c["selfprep"]:
             d = ex.pd_desc[c["prep"]]
-            if c["kind"] == "syn":
-                check(L.nb_synchrotron_fused(
-                    ctypes.byref(src), ctypes.byref(d), ex.scalar_entry[c["B"]],
-                    eng.ptr(g.x_d), g.N, eng.ptr(g.dlx_d), W, eng.ptr(ex.E_erg), self.N_E,
-                    eng.ptr(out), eng.stream()), "nb_synchrotron_fused")
-            else:
-                tb = c["table"]
-                check(L.nb_contract_fused(
-                    ctypes.byref(src), ctypes.byref(d), eng.ptr(tb.K), eng.ptr(tb.lrs), tb.R,
-                    g.N, g.pitch, W, eng.ptr(g.dlx_d), eng.ptr(g.x_d), eng.ptr(tb.coef),
-                    eng.ptr(out), eng.stream()), "nb_contract_fused")
-        elif c["kind"] == "syn":
-            eng.synchrotron(g, p, ex.scalar_col(c["B"]), ex.E_erg, out=out)
+            check(L.nb_synchrotron_fused(
+                ctypes.byref(src), ctypes.byref(d), ex.scalar_entry[c["B"]], eng.ptr(g.x_d), g.N,
+                eng.ptr(g.gm2_d), eng.ptr(g.g23_d), eng.ptr(g.dlx_d), W, eng.ptr(E_erg),
+                E_erg.numel(), eng.ptr(out), out.stride(0), eng.stream()), "nb_synchrotron_fused")
         else:
-            eng.contract(c["table"], p, out=out)
+            eng.synchrotron(g, p, ex.scalar_col(c["B"]), E_erg, out=out)
 
-    def _enqueue(self, ex, mv=None, fuse_update=True, peers=None):
-        """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
-        (an nb_stretch describing a device-resident ensemble) the parameters are the
-        stretch-move proposals of the active half, computed by the set-up kernel, and
-        (fuse_update) the combine kernel also accepts/rejects them and appends the chain."""
-        L, W = lib(), ex.W
-        n = 0
-        if mv is None and ex.pack is not None:
-            raise ValueError("a packed executable is driven by device-side proposals only")
-
+    def _nodes(self, ex, mv):
+        """The launches of one likelihood evaluation before the combine kernel, as a DAG:
+        [(name, launch function, [names it depends on])], in a valid launch order with the
+        longest chain (self-Compton) first."""
         src = self._src(ex, mv)
-
-        def prep():
-            self._launch_prep(ex, mv)
-
-        def launch(c, out):
-            self._launch_comp(ex, c, out, src)
-
-        # The set-up kernel and the radiative components fork onto side streams (parallel
-        # branches of the captured graph) and join before the combine.  Components that
-        # still consume operand arrays must follow the set-up kernel.
-        comps = list(zip(self.comps, ex.outs))
-        main = torch.cuda.current_stream()
-        dependent = [x for x in comps if not x[0]["selfprep"]]
-        free = [x for x in comps if x[0]["selfprep"]]
-        branches = [[prep] + [lambda c=c, o=o: launch(c, o) for c, o in dependent[:1]]]
-        branches += [[lambda c=c, o=o: launch(c, o)] for c, o in free]
+        nodes = []
+        for ia, a in enumerate(self.aux):
+            nodes.append(("aux_syn%d" % ia,
+                          lambda a=a, ia=ia: self._launch_syn(ex, a, ex.aux_E[ia],
+                                                              ex.aux_outs[ia], src),
+                          [] if a["selfprep"] else ["walker_prep"]))
+        nodes.append(("walker_prep", lambda: self._launch_prep(ex, mv), []))
+        if any(n[2] for n in nodes[:-1]):  # an auxiliary launch needs the operand arrays
+            nodes.insert(0, nodes.pop())
         if ex.n_blob_jobs:
-            branches.append([lambda: self._launch_blob_prep(ex, mv)])
-        extra_dep = dependent[1:]
-        joins = []
-        if len(branches) > 1 or extra_dep:
-            while len(self._side) < len(branches) + len(extra_dep):
-                self._side.append(torch.cuda.Stream())
-            fork = torch.cuda.Event()
-            fork.record(main)
-            for br, side in zip(branches[1:], self._side):
-                side.wait_event(fork)
-                with torch.cuda.stream(side):
-                    for f in br:
-                        f()
-                    done = torch.cuda.Event()
-                    done.record(side)
-                joins.append(done)
-        for f in branches[0]:
-            f()
-        if extra_dep:  # further operand-consuming components: fork after the set-up
-            after = torch.cuda.Event()
-            after.record(main)
-            for (c, o), side in zip(extra_dep, self._side[len(branches) - 1:]):
-                side.wait_event(after)
-                with torch.cuda.stream(side):
-                    launch(c, o)
-                    done = torch.cuda.Event()
-                    done.record(side)
-                joins.append(done)
-        for done in joins:
-            main.wait_event(done)
-        n += 1 + len(comps) + (1 if ex.n_blob_jobs else 0)
-        L, st = lib(), eng.stream()
+            nodes.append(("blob_prep", lambda: self._launch_blob_prep(ex, mv), []))
+        for ic, (c, out) in enumerate(zip(self.comps, ex.outs)):
+            if c["kind"] == "ssc":
+                tb, b = c["tb"], ex.ssc[ic]
+                nodes.append(("ssc_seed%d" % ic,
+                              lambda tb=tb, b=b: eng.ssc_seed(tb, b["sources"], ex.W, b["sxn"],
+                                                              b["sds"]),
+                              ["aux_syn%d" % ia for ia, _ in c["sources"]]))
+                nodes.append(("ssc_inner%d" % ic,
+                              lambda tb=tb, b=b: eng.ssc_inner(tb, b["sxn"], b["sds"], ex.W,
+                                                               b["inner"]),
+                              ["ssc_seed%d" % ic]))
+                nodes.append(("ssc_outer%d" % ic,
+                              lambda tb=tb, b=b, c=c, out=out: eng.ssc_outer(
+                                  tb, b["inner"], ex.preps[c["prep"]], out),
+                              ["ssc_inner%d" % ic, "walker_prep"]))
+            elif c["kind"] == "syn":
+                nodes.append(("syn%d" % ic,
+                              lambda c=c, out=out: self._launch_syn(ex, c, ex.E_erg, out, src),
+                              [] if c["selfprep"] else ["walker_prep"]))
+            else:
+                nodes.append(("table%d" % ic,
+                              lambda c=c, out=out: eng.contract(c["table"], ex.preps[c["prep"]],
+                                                                out=out),
+                              ["walker_prep"]))
+        return nodes
+
+    def _launch_combine(self, ex, mv=None, fuse_update=True, peers=None):
+        L, st, W = lib(), eng.stream(), ex.W
+        n = 0
         for spec, buf in zip(self._flat_blob_specs(), ex.blob_bufs):
             if spec["kind"] != "pdist":
                 continue  # particle energies are jobs of nb_walker_prep
@@ -718,23 +794,116 @@ class LikelihoodPlan:
                     prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
                     mv=mv if fuse_update else None, pars_d=ex.pars, flux_ld=ex.row_ld,
                     lnp_ld=ex.lnp.stride(0), peers=peers, nb=self.row_width)
-        n += 1
+        return n + 1
+
+    def _enqueue(self, ex, mv=None, fuse_update=True, peers=None):
+        """The launch sequence of one likelihood evaluation of ex.W walkers.  With `mv`
+        (an nb_stretch describing a device-resident ensemble) the parameters are the
+        stretch-move proposals of the active half, computed by the set-up kernel, and
+        (fuse_update) the combine kernel also accepts/rejects them and appends the chain.
+        Independent launches go to side streams (parallel branches of the captured graph):
+        a node continues the stream of a dependency whose stream is still free, else it
+        forks; everything joins before the combine."""
+        if mv is None and ex.pack is not None:
+            raise ValueError("a packed executable is driven by device-side proposals only")
+        nodes = self._nodes(ex, mv)
+        main = torch.cuda.current_stream()
+        streams, tails = [main], [None]  # stream k, name of the last node launched on it
+        where, done = {}, {}
+        fork = torch.cuda.Event()
+        fork.record(main)  # before the first launch: side branches depend on nothing earlier
+        for name, fn, deps in nodes:
+            k = None
+            for d in deps:  # continue a dependency's stream when nothing followed it there
+                if tails[where[d]] == d:
+                    k = where[d]
+                    break
+            if k is None:
+                free = [i for i, t in enumerate(tails) if t is None]
+                if free:
+                    k = free[0]
+                else:
+                    k = len(streams)
+                    if k - 1 >= len(self._side):
+                        self._side.append(torch.cuda.Stream())
+                    streams.append(self._side[k - 1])
+                    tails.append(None)
+            st = streams[k]
+            if k != 0 and tails[k] is None:
+                st.wait_event(fork)
+            for d in deps:
+                if where[d] != k:
+                    st.wait_event(done[d])
+            with torch.cuda.stream(st):
+                fn()
+                ev = torch.cuda.Event()
+                ev.record(st)
+            where[name], done[name], tails[k] = k, ev, name
+        for k in range(1, len(streams)):
+            if tails[k] is not None:
+                main.wait_event(done[tails[k]])
+        n = len(nodes) + self._launch_combine(ex, mv, fuse_update, peers)
         self.launches_per_eval = n
         return n
 
     def stages(self, ex):
         """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
         stream (no forking): measurement aid for bench.py / tools/timeline.py."""
-        out = [("walker_prep", lambda: self._launch_prep(ex, None))]
-        if ex.n_blob_jobs:
-            out.append(("blob_prep", lambda: self._launch_blob_prep(ex, None)))
-        for i, (c, o) in enumerate(zip(self.comps, ex.outs)):
-            name = ("syn%d" if c["kind"] == "syn" else "table%d") % i
-            out.append((name, lambda c=c, o=o: self._launch_comp(ex, c, o, ex.src)))
-        out.append(("combine", lambda: eng.combine(
-            ex.terms, ex.W, self.N_E, self.unit_fac_d, flux_out=ex.row, data=self.ddata,
-            prior_d=ex.prior if self.prior is not None else None, lnp_out=ex.lnp,
-            flux_ld=ex.row_ld, lnp_ld=ex.lnp.stride(0))))
+        nodes = self._nodes(ex, None)
+        # the DAG order may put a selfprep root first; any topological order is valid here
+        out, seen = [], set()
+        pending = list(nodes)
+        while pending:
+            for i, (name, fn, deps) in enumerate(pending):
+                if all(d in seen for d in deps):
+                    out.append((name, fn))
+                    seen.add(name)
+                    pending.pop(i)
+                    break
+            else:
+                raise RuntimeError("cyclic launch graph")
+        out.append(("combine", lambda: self._launch_combine(ex)))
+        return out
+
+    def kernel_figures(self, ex):
+        """Per stage of stages(ex): kernel name, cells and ALGORITHMIC bytes per launch
+         and the reference-operation-order flops per cell of SURVEY 8d
+        -- the inputs of bench.py's roofline objects."""
+        Wh, N_E = ex.W, self.N_E
+        out = {}
+        for i, c in enumerate(self.comps):
+            g = ex.preps[c["prep"]].grid
+            if c["kind"] == "syn":
+                out["syn%d" % i] = {
+                    "kernel": "synchrotron_fused_kernel", "cells_per_launch": Wh * N_E * (g.N - 1),
+                    "algorithmic_bytes_per_launch": 8 * (5 * g.N + N_E + Wh * (self.P + N_E)),
+                    "ref_order_flops_per_cell": 320}
+            elif c["kind"] == "ssc":
+                tb = c["tb"]
+                out["ssc_inner%d" % i] = {
+                    "kernel": "ssc_inner_kernel (self-Compton, %d x %d rows, %d seed energies)"
+                              % (N_E, g.N, tb.Ns),
+                    "cells_per_launch": Wh * tb.R * (tb.Ns - 1),
+                    "algorithmic_bytes_per_launch":
+                        8 * (2 * tb.Ns * tb.R + Wh * (2 * tb.Ns + tb.R)),
+                    "ref_order_flops_per_cell": 295, "is_ic": True}
+            else:
+                tb = c["table"]
+                kind = type(c["obj"]).__name__
+                out["table%d" % i] = {
+                    "kernel": "contract_kernel (%s, %d x %d rows)" % (kind, tb.n_comp, N_E),
+                    "cells_per_launch": Wh * tb.R * (g.N - 1),
+                    "algorithmic_bytes_per_launch":
+                        8 * (2 * tb.R * g.N + 2 * Wh * g.N + g.N + tb.R + Wh * tb.R),
+                    "ref_order_flops_per_cell": 164, "is_ic": kind == "InverseCompton"}
+        for ia, a in enumerate(self.aux):
+            g = ex.preps[a["prep"]].grid
+            ne = a["E_eV"].size
+            out["aux_syn%d" % ia] = {
+                "kernel": "synchrotron_fused_kernel (seed luminosities)",
+                "cells_per_launch": Wh * ne * (g.N - 1),
+                "algorithmic_bytes_per_launch": 8 * (5 * g.N + ne + Wh * (self.P + ne)),
+                "ref_order_flops_per_cell": 320}
         return out
 
     def executable(self, W, pack=None):

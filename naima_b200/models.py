@@ -105,6 +105,11 @@ def _validate_ene(ene):
     return ene
 
 
+def _is_symflux(x):
+    from .fused import SymFlux
+    return isinstance(x, SymFlux)
+
+
 def _val(x, unit=None):
     """Plain float/ndarray of a parameter (Quantity converted to `unit`)."""
     if _is_sym(x):
@@ -498,6 +503,15 @@ class InverseCompton(BaseElectron):
                         validate_scalar("{0}-u".format(name), uu, domain="positive",
                                         physical_type="pressure")
                         seed["u"] = Quantity(uu)
+                elif _is_symflux(uu):
+                    # seed density computed from the fit parameters (synchrotron
+                    # self-Compton, examples/CrabNebula_SynSSC.py:24-36): traced
+                    seed["type"] = "array"
+                    seed["energy"] = validate_array("{0}-energy".format(name), T,
+                                                    domain="positive", physical_type="energy")
+                    uu.check_seed_density(name, seed["energy"])
+                    seed["photon_density"] = uu
+                    seed["symbolic"] = True
                 else:
                     seed["type"] = "array"
                     T = Quantity(np.atleast_1d(T.value), T.unit)
@@ -521,6 +535,10 @@ class InverseCompton(BaseElectron):
                 raise TypeError("Unable to process seed photon field: {0}".format(inseed))
             result[name] = seed
         return result
+
+    def _symbolic(self):
+        return super()._symbolic() or any(sd.get("symbolic")
+                                          for sd in self.seed_photon_fields.values())
 
     def _seed_tuple(self, seed):
         if seed["type"] == "thermal":
@@ -555,7 +573,7 @@ class InverseCompton(BaseElectron):
             if W == 1 and Wb > 1:
                 par_d = par_d.expand(Wb, par_d.shape[1]).contiguous()
                 W = Wb
-        pr = eng.pd_prep(g, kind, par_d, W, need_raw=bool(batched) or None)
+        pr = eng.pd_prep(g, kind, par_d, W, need_raw=(bool(batched) and eng.EXACT) or None)
         S = len(names)
         out = eng.empty(W, S * N_E)
         if shared:
@@ -570,9 +588,18 @@ class InverseCompton(BaseElectron):
         for k in batched:
             sd = self.seed_photon_fields[names[k]]
             phn = np.ascontiguousarray(sd["photon_density"].to("1/(eV cm3)").value) * eng.mec2_eV
-            eng.ic_seed_spectrum(g, pr, E_eV, sd["energy"].to("eV").value, eng.to_dev(phn),
-                                 True, out, k * N_E)
-            out[:, k * N_E:(k + 1) * N_E] /= eng.to_dev(E_eV)
+            seed_E = sd["energy"].to("eV").value
+            if eng.EXACT:  # reference operation order, one serial inner trapezoid per node
+                eng.ic_seed_spectrum(g, pr, E_eV, seed_E, eng.to_dev(phn), True, out, k * N_E)
+                out[:, k * N_E:(k + 1) * N_E] /= eng.to_dev(E_eV)
+                continue
+            # hoisted: walker-independent f_AA81 table, lean inner contraction, outer trapezoid
+            tb = eng.ssc_table(g, E_eV, seed_E)
+            sxn, sds = eng.empty(W, tb.spitch), eng.empty(W, tb.spitch)
+            eng.ssc_seed(tb, [(eng.to_dev(phn), 0, 1.0)], W, sxn, sds)
+            inner = eng.empty(W, tb.Rp)
+            eng.ssc_inner(tb, sxn, sds, W, inner)
+            eng.ssc_outer(tb, inner, pr, out, k * N_E)
         self._specic_dev = (out, N_E, names)
         terms = [(out, k * N_E, k == S - 1, 1.0, None) for k in range(S)]
         return terms, W

@@ -99,34 +99,31 @@ class ShardedSampler(EnsembleSampler):
 class ShardedDeviceEnsemble(DeviceEnsemble):
     """Device-resident ensemble step with the half-ensemble's proposals sharded over ranks.
 
-    Per half-step, on every rank:
-      set-up kernel (+ the proposals [lo, lo + per) of the half, computed in place)
-      -> radiative components -> combine, writing packed records
-         [blob record | lnprob | proposal] straight into this rank's slice of the gather buffer
-      -> ONE in-place all-gather of the slices (NCCL over NVLink)
-      -> accept step + chain append for all proposals (replicated, identical on every rank).
-    The whole ensemble step (both halves, both collectives) is one CUDA-graph replay."""
+    transport "fused" (default when symmetric memory can be set up): the ensemble state
+    (coords, lp, blob records) and the chain live in symmetric memory on every rank; the
+    combine kernel's accept step writes every rank's copy of the walkers it decides (one
+    multimem.st per element through the NVSwitch when `multicast`, else one store per peer)
+    and its last CTA raises per-rank flags that the next half-step's kernels wait on.  The
+    sharded step has exactly the launches of the single-GPU step and no collective.
+
+    transport "nccl": per half-step every rank's combine kernel writes packed records
+    [blob record | lnprob | proposal] into its slice of a gather buffer, ONE in-place
+    all-gather (NCCL over NVLink) exchanges the slices and a replicated accept kernel runs
+    identically on every rank.  The north_star's "single all-gather per step" design; kept
+    as the fallback and as the cross-check of the fused transport.
+
+    Either way the whole ensemble step is one CUDA-graph replay and the chain is bitwise
+    identical to the single-GPU chain (tests/multi/check_sharded.py)."""
 
     def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
                  use_graph=True, transport="auto", multicast=True):
-        """transport: "fused" -- replicated state in symmetric memory: the combine kernel's
-        accept step writes every rank's copy of the walkers' state and chain rows (one
-        multimem.st per element through the NVSwitch when `multicast`, else one store per
-        peer) and raises per-rank flags that the next half-step's kernels wait on; the
-        sharded step has exactly the launches of the single-GPU step (measured 140 us/step on
-        8 B200s against 165 for "nccl" and 115 on one GPU); "auto" (default) -- "fused" when
-        symmetric memory can be set up, else "nccl";
-        "p2p" -- the combine kernel stores the packed records into every
-        peer's buffer over NVLink itself and the accept kernel waits on per-rank flags
-        (symmetric memory; no collective launch; with `multicast` one multimem.st per
-        element through the NVSwitch instead of one store per peer); "nccl" -- one in-place
-        all-gather per half-step (default: measured a few us per step faster on 2 and 8
-        B200s); "auto" -- p2p when symmetric memory can be set up, else nccl."""
         self.multicast = multicast
         from . import engine as eng
 
         if seed is None:
             raise ValueError("ShardedDeviceEnsemble needs an explicit seed shared by all ranks")
+        if transport not in ("auto", "fused", "nccl"):
+            raise ValueError("transport must be 'auto', 'fused' or 'nccl'")
         self.group = group
         self.rank, self.world = world_info(group)
         super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=True, use_graph=use_graph)
@@ -155,30 +152,11 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
                                  use_graph=use_graph)
         if self.transport == "fused":
             self.ex = plan.executable(self.per)
-            self.exs = [self.ex, self.ex]
             self.kernel_launches_per_step = 2 * plan.launches_per_eval
             return
-        if self.world > 1 and transport == "p2p":
-            try:
-                self._setup_p2p()
-                self.transport = "p2p"
-            except Exception as e:  # no symmetric memory on this build / topology
-                if transport == "p2p":
-                    raise
-                import warnings
-
-                warnings.warn("naima_b200: peer-to-peer transport unavailable (%r); using the "
-                              "NCCL all-gather" % (e,))
-        if self.transport == "p2p":
-            # two record buffers, alternating between the red and the blue half-step
-            self.exs = [plan.executable(self.per, pack=self.packs[k][lo:lo + self.per])
-                        for k in range(2)]
-            self.ex = self.exs[0]
-        else:
-            self.pack_full = eng.zeros(self.Ns, self.ld)
-            self.pack_local = self.pack_full[lo:lo + self.per]
-            self.ex = plan.executable(self.per, pack=self.pack_local)
-            self.exs = [self.ex, self.ex]
+        self.pack_full = eng.zeros(self.Ns, self.ld)
+        self.pack_local = self.pack_full[lo:lo + self.per]
+        self.ex = plan.executable(self.per, pack=self.pack_local)
         self.kernel_launches_per_step = 2 * (plan.launches_per_eval + 1)
 
     def _setup_fused(self):
@@ -290,45 +268,6 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             mv.wait_world = self.world
         return mv
 
-    def _setup_p2p(self):
-        """Symmetric buffers: [2][Ns][ld] records and [world] flags, mapped on every rank."""
-        import torch
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
-
-        from . import engine as eng
-        from ._lib import NB_MAX_PEERS, nb_peers
-
-        if self.world > NB_MAX_PEERS:
-            raise ValueError("more ranks than NB_MAX_PEERS")
-        group = self.group if self.group is not None else dist.group.WORLD
-        dev = eng.device()
-        n = self.Ns * self.ld
-        self._sym_pack = symm.empty(2 * n, dtype=torch.float64, device=dev)
-        self._sym_pack.zero_()
-        self._sym_flags = symm.empty(NB_MAX_PEERS, dtype=torch.int64, device=dev)
-        self._sym_flags.zero_()
-        h_pack = symm.rendezvous(self._sym_pack, group)
-        h_flags = symm.rendezvous(self._sym_flags, group)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-        self._handles = (h_pack, h_flags)
-        self.packs = [self._sym_pack[k * n:(k + 1) * n].view(self.Ns, self.ld) for k in range(2)]
-        self.gen = eng.zeros(1, dtype=torch.int64)
-        self.ticket = eng.zeros(1, dtype=torch.int32)
-        self.peers = []
-        for k in range(2):
-            pr = nb_peers()
-            pr.world, pr.rank, pr.i0, pr.ld = self.world, self.rank, self.rank * self.per, self.ld
-            for r in range(self.world):
-                pr.pack[r] = int(h_pack.buffer_ptrs[r]) + 8 * k * n
-                pr.flags[r] = int(h_flags.buffer_ptrs[r])
-            pr.gen, pr.ticket = self.gen.data_ptr(), self.ticket.data_ptr()
-            mc = int(getattr(h_pack, "multicast_ptr", 0) or 0) if self.multicast else 0
-            pr.mc_pack = (mc + 8 * k * n) if mc else None
-            self.peers.append(pr)
-        self.uses_multicast = bool(self.multicast and getattr(h_pack, "multicast_ptr", 0))
-
     def set_state(self, coords, log_prob=None, rows=None):
         """Evaluate the initial ensemble sharded (unless given), then replicate."""
         from . import engine as eng
@@ -367,13 +306,6 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
                 continue
             mv = self._stretch(split)
             mv.i0, mv.pars_ld = self.rank * self.per, self.ld
-            if self.transport == "p2p":
-                self.plan._enqueue(self.exs[split], mv=mv, fuse_update=False,
-                                   peers=self.peers[split])
-                check(L.nb_stretch_update_packed_wait(
-                    ctypes.byref(self._stretch(split)), ctypes.byref(self.peers[split]),
-                    eng.stream()), "nb_stretch_update_packed_wait")
-                continue
             self.plan._enqueue(self.ex, mv=mv, fuse_update=False)
             if self.world > 1:
                 _dist().all_gather_into_tensor(self.pack_full, self.pack_local, group=self.group)

@@ -28,15 +28,30 @@ __all__ = ["EnsembleSampler", "State", "DeviceEnsemble", "PlanSampler"]
 class State:
     """emcee.State: coords [W,P], log_prob [W], blobs, random_state."""
 
+    # PlanSampler extras: the walkers' device blob records and a token saying that the
+    # device-resident ensemble still holds exactly this state (continuation without
+    # re-evaluating or re-uploading it)
+    _rows = None
+    _token = None
+
     def __init__(self, coords, log_prob=None, blobs=None, random_state=None, copy=False):
         if isinstance(coords, State):
             log_prob, blobs, random_state = coords.log_prob, coords.blobs, coords.random_state
+            self._rows, self._token = coords._rows, coords._token
             coords = coords.coords
         dc = (lambda x: np.array(x, copy=True)) if copy else (lambda x: x)
         self.coords = dc(np.atleast_2d(np.asarray(coords, dtype=float)))
         self.log_prob = None if log_prob is None else dc(np.asarray(log_prob, dtype=float))
         self.blobs = blobs
         self.random_state = random_state
+
+    @classmethod
+    def _make(cls, coords, log_prob, blobs, random_state, rows=None, token=None):
+        """Constructor without the input normalisation (the sampling loop's own arrays)."""
+        st = object.__new__(cls)
+        st.coords, st.log_prob, st.blobs, st.random_state = coords, log_prob, blobs, random_state
+        st._rows, st._token = rows, token
+        return st
 
     def __iter__(self):
         # emcee allows `pos, lnp, rstate[, blobs] = state`
@@ -278,11 +293,27 @@ class BlobBatch:
     """Per-walker blobs of a batched evaluation, materialised lazily: indexing
     with a walker index yields the reference's blob tuple for that walker."""
 
-    def __init__(self, plan, flux, blob_arrays):
-        self.plan, self.flux, self.blob_arrays = plan, flux, blob_arrays
+    def __init__(self, plan, flux=None, blob_arrays=None, rows=None):
+        """Either (flux, blob_arrays) or `rows`: per-walker records [W][plan.row_width]
+        that are split on first access."""
+        self.plan, self._flux, self._arrays, self._rows = plan, flux, blob_arrays, rows
+
+    def _split(self):
+        if self._flux is None:
+            self._flux, self._arrays = self.plan.split_rows(self._rows)
+
+    @property
+    def flux(self):
+        self._split()
+        return self._flux
+
+    @property
+    def blob_arrays(self):
+        self._split()
+        return self._arrays
 
     def __len__(self):
-        return self.flux.shape[0]
+        return (self._rows if self._flux is None else self._flux).shape[0]
 
     def __getitem__(self, w):
         return _LazyBlob(self, w)
@@ -489,6 +520,7 @@ class DeviceEnsemble:
         self.c_idx[:nsteps].copy_(eng.to_dev(c_idx, dtype=torch.int32))
         self.zz[:nsteps].copy_(eng.to_dev(zz))
         self.lnu[:nsteps].copy_(eng.to_dev(lnu))
+        self._sync_ranks()  # no peer is still writing rows of the previous block
         self.step.zero_()
 
     def run_loaded(self, nsteps):
@@ -542,11 +574,15 @@ class DeviceEnsemble:
                 zz=pin(nn, 2, Ns), lnu=pin(nn, 2, Ns), chain=pin(nn, W, self.P),
                 lp=pin(nn, W), rows=pin(nn, W, max(self.nb, 1)))
             self._pin_np = {k: v.numpy() for k, v in self._pin.items()}
+        self._sync_ranks()  # every rank has read the previous chunk's rows back
         self.step.zero_()
 
-    def enqueue_steps(self, t0, t1):
+    def enqueue_steps(self, t0, t1, dst=None):
         """Steps [t0, t1) of the current chunk: draw on the host, upload from pinned
         memory, replay, read the chain rows back into pinned memory -- all asynchronous.
+        dst: optional (chain, lp, rows|None) pinned host tensors of t1 - t0 steps that
+        receive the rows instead of this ensemble's staging buffers (the public sampler
+        passes slices of its own storage: no host copy afterwards).
         Returns (event, rng0) with the generator state before the block."""
         import torch
 
@@ -560,10 +596,12 @@ class DeviceEnsemble:
             dev[t0:t1].copy_(pn[name][t0:t1], non_blocking=True)
         self.run_loaded(n)
         self._wait_pushes()  # replicated-state sharding: the peers' rows of these steps
-        pn["chain"][t0:t1].copy_(self.chain[t0:t1], non_blocking=True)
-        pn["lp"][t0:t1].copy_(self.chain_lp[t0:t1], non_blocking=True)
-        if self.nb and self.read_rows:
-            pn["rows"][t0:t1].copy_(self.chain_blobs[t0:t1], non_blocking=True)
+        d_chain, d_lp, d_rows = dst if dst is not None else (
+            pn["chain"][t0:t1], pn["lp"][t0:t1], pn["rows"][t0:t1])
+        d_chain.copy_(self.chain[t0:t1], non_blocking=True)
+        d_lp.copy_(self.chain_lp[t0:t1], non_blocking=True)
+        if self.nb and self.read_rows and d_rows is not None:
+            d_rows.copy_(self.chain_blobs[t0:t1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return ev, rng0
@@ -644,6 +682,31 @@ class PlanSampler(EnsembleSampler):
     def reset(self):
         super().reset()
         self._rows = None
+        self._store_t = None  # pinned torch tensors behind _chain / _log_prob / _rows
+
+    def _grow(self, n):
+        """Storage for n more steps in PINNED host memory: the device copies each block's
+        chain rows, log-probabilities and blob records straight into it."""
+        import torch
+
+        if getattr(self, "_host_loop", False):
+            return super()._grow(n)
+        de = self._device()
+        tot = self.iteration + n
+        nbw = max(de.nb, 1) if self.read_rows else 0
+        new = (torch.empty(tot, self.nwalkers, self.ndim, dtype=torch.float64).pin_memory(),
+               torch.empty(tot, self.nwalkers, dtype=torch.float64).pin_memory(),
+               torch.empty(tot, self.nwalkers, nbw, dtype=torch.float64).pin_memory()
+               if nbw else None)
+        views = [None if t is None else t.numpy() for t in new]
+        it = self.iteration
+        if it:
+            views[0][:it] = self._chain[:it]
+            views[1][:it] = self._log_prob[:it]
+            if views[2] is not None and self._rows is not None:
+                views[2][:it] = self._rows[:it]
+        self._store_t = new
+        self._chain, self._log_prob, self._rows = views
 
     def _log_prob(self, p):
         lnp, rows = self.plan.eval_rows(p)
@@ -670,6 +733,7 @@ class PlanSampler(EnsembleSampler):
         if self.nwalkers % 2 or self.nwalkers < 2 * self.ndim or self.ndim > 32:
             # odd ensembles / live_dangerously / more parameters than the fused proposal
             # kernel maps (NB_MAX_MOVE_PAR): the host-driven loop handles them
+            self._host_loop = True
             yield from super().sample(initial_state, log_prob0=log_prob0, rstate0=rstate0,
                                       blobs0=blobs0, iterations=iterations,
                                       skip_initial_state_check=skip_initial_state_check,
@@ -685,28 +749,33 @@ class PlanSampler(EnsembleSampler):
             raise ValueError("At least one parameter value was infinite or NaN")
         if rstate0 is not None:
             self.random_state = rstate0
-        if log_prob0 is not None:
-            state.log_prob = np.asarray(log_prob0, dtype=float)
-        # the device loop needs the walkers' blob records: evaluate the ensemble once
-        lnp, rows = self.plan.eval_rows(state.coords)
-        if state.log_prob is None:
-            state.log_prob = lnp
-        if np.shape(state.log_prob) != (self.nwalkers,):
-            raise ValueError("incompatible input dimensions")
-        if np.any(np.isnan(state.log_prob)):
-            raise ValueError("The initial log_prob was NaN")
         de = self._device()
-        de.set_state(state.coords, state.log_prob, rows)
+        # continuation: the device-resident ensemble still holds exactly this state (the
+        # last State of a completed sample() call on this sampler) -- nothing to evaluate
+        # or upload
+        token, self._dev_token = getattr(self, "_dev_token", None), None
+        resident = (token is not None and state._token is token and log_prob0 is None
+                    and blobs0 is None)
+        if not resident:
+            if log_prob0 is not None:
+                state.log_prob = np.asarray(log_prob0, dtype=float)
+            rows = state._rows
+            if rows is None or state.log_prob is None or log_prob0 is not None:
+                # the device loop needs the walkers' blob records: evaluate the ensemble once
+                lnp, rows = self.plan.eval_rows(state.coords)
+                if state.log_prob is None:
+                    state.log_prob = lnp
+            if np.shape(state.log_prob) != (self.nwalkers,):
+                raise ValueError("incompatible input dimensions")
+            if np.any(np.isnan(state.log_prob)):
+                raise ValueError("The initial log_prob was NaN")
+            de.set_state(state.coords, state.log_prob, rows)
         iterations = int(iterations)
         if store:
             self._grow(iterations)
-            keep = getattr(self, "_rows", None)
-            self._rows = np.empty((self.iteration + iterations if self.read_rows else 0,
-                                   self.nwalkers, max(de.nb, 1)))
-            if keep is not None and self.iteration and self.read_rows:
-                self._rows[:self.iteration] = keep[:self.iteration]
         prev = state.coords
         done = 0
+        make = State._make
         while done < iterations:
             nchunk = min(self.chunk, iterations - done)
             de.begin_chunk(nchunk)
@@ -716,47 +785,54 @@ class PlanSampler(EnsembleSampler):
             while t_out < nchunk:
                 while t_enq < nchunk and len(pending) < 2:
                     t1 = min(t_enq + self.block, nchunk)
-                    ev, rng0 = de.enqueue_steps(t_enq, t1)
+                    dst = None
+                    if store:  # the device writes into the sampler's (pinned) storage
+                        i0 = self.iteration + (t_enq - t_out)
+                        st = self._store_t
+                        dst = (st[0][i0:i0 + t1 - t_enq], st[1][i0:i0 + t1 - t_enq],
+                               None if st[2] is None else st[2][i0:i0 + t1 - t_enq])
+                    ev, rng0 = de.enqueue_steps(t_enq, t1, dst=dst)
                     pending.append((t_enq, t1, ev, rng0))
                     t_enq = t1
                 t0, t1, ev, rng0 = pending.pop(0)
                 ev.synchronize()
-                hp = de._pin_np
                 nblk = t1 - t0
-                if store:  # straight into the sampler's storage, no temporaries
+                if store:
                     it0 = self.iteration
-                    self._chain[it0:it0 + nblk] = hp["chain"][t0:t1]
-                    self._log_prob[it0:it0 + nblk] = hp["lp"][t0:t1]
                     chain, lps = self._chain[it0:it0 + nblk], self._log_prob[it0:it0 + nblk]
-                    recs = None
-                    if de.nb and self.read_rows:
-                        self._rows[it0:it0 + nblk] = hp["rows"][t0:t1]
-                        recs = self._rows[it0:it0 + nblk]
+                    recs = self._rows[it0:it0 + nblk] if (de.nb and self.read_rows) else None
                 else:
+                    hp = de._pin_np
                     chain, lps = hp["chain"][t0:t1].copy(), hp["lp"][t0:t1].copy()
                     recs = hp["rows"][t0:t1].copy() if (de.nb and self.read_rows) else None
-                if np.any(np.isnan(lps)):
+                if np.isnan(lps).any():
                     raise ValueError("Probability function returned NaN")
-                moved = np.any(np.concatenate([prev[None], chain[:-1]]) != chain, axis=2)
-                for k in range(t1 - t0):
-                    coords = chain[k]
+                moved = np.empty((nblk, self.nwalkers), dtype=bool)
+                np.any(prev[None] != chain[:1], axis=2, out=moved[:1])
+                if nblk > 1:
+                    np.any(chain[:-1] != chain[1:], axis=2, out=moved[1:])
+                prev = chain[-1]
+                for k in range(nblk):
                     self._accepted += moved[k]
-                    prev = coords
                     blobs = None
                     if recs is not None:
-                        flux, arrays = self.plan.split_rows(recs[k])
-                        blobs = BlobBatch(self.plan, flux, arrays)
-                    if store and blobs is not None:
-                        self._blobs.append(blobs)
+                        blobs = BlobBatch(self.plan, rows=recs[k])
+                        if store:
+                            self._blobs.append(blobs)
                     self.iteration += 1
                     last = done + t0 + k + 1 == iterations
-                    out = State(coords, log_prob=lps[k], blobs=blobs, copy=False,
-                                random_state=self._random.get_state() if last else None)
+                    if last:
+                        self._dev_token = token = object()
+                    out = make(chain[k].copy(), lps[k].copy(), blobs,
+                               self._random.get_state() if last else None,
+                               None if recs is None else recs[k], token if last else None)
                     self._previous_state = out
                     try:
-                        yield State(out, copy=True)
+                        yield out
                     except GeneratorExit:
-                        # the consumer stopped here: rewind the stream to this step
+                        # the consumer stopped here: rewind the stream to this step (the
+                        # device ensemble is ahead: it no longer holds this state)
+                        self._dev_token = None
                         self._random.set_state(de.rng_state_after(rng0, k + 1))
                         raise
                 t_out = t1

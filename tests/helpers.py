@@ -111,22 +111,7 @@ def oracle_SynIC(seeds=None):
     return model, prior
 
 
-def oracle_data(data):
-    """Plain-float view of a validated naima_b200 data table for the oracle:
-    model values are 1/(s cm2 eV) * unit_fac -> the table's flux unit."""
-    from naima_b200 import units as u
-
-    E = u.Quantity(data["energy"])
-    fl = u.Quantity(data["flux"])
-    E_eV = E.to("eV").value
-    if fl.unit.physical_type == "flux":  # SED: erg/(cm2 s)
-        fac = (u.Quantity(E_eV**2, "eV2") * u.Quantity(1.0, "1/(s cm2 eV)")).to(fl.unit).value
-    else:
-        fac = u.Quantity(np.ones(E_eV.size), "1/(s cm2 eV)").to(fl.unit).value
-    return dict(E_eV=E_eV, unit_fac=fac, flux=fl.value,
-                flux_error_lo=u.Quantity(data["flux_error_lo"]).to(fl.unit).value,
-                flux_error_hi=u.Quantity(data["flux_error_hi"]).to(fl.unit).value,
-                ul=np.asarray(data["ul"], dtype=bool), cl=np.asarray(data["cl"], dtype=float))
+from oracle.bench_models import oracle_data  # noqa: E402,F401
 
 
 def oracle_lnprob_batch(P, odata, model, prior):

@@ -123,28 +123,52 @@ void emu_pd_prep_log(int kind, const double* p, const double* x, int N, double m
 void emu_finalize(const double* K, int R, int N, int pitch, const double* invdlx, double* lrs) {
   for (int r = 0; r < R; ++r)
     for (int j = 0; j < pitch; ++j)
-      lrs[r * pitch + j] =
-          (j < N - 1) ? log(K[r * pitch + j + 1] / K[r * pitch + j]) * invdlx[j] : 0.0;
+      lrs[r * pitch + j] = (j < N - 1) ? slope_or_sentinel(K[r * pitch + j], K[r * pitch + j + 1],
+                                                           invdlx[j])
+                                       : 0.0;
 }
 
-// contract_kernel<RT=1>, one walker; lane decomposition + shuffle tree
+// contract_kernel<RT=1>, one walker; lane decomposition + shuffle tree.  mode 0: careful
+// cell, 1: reference operation order, 2: lean cell with the per-row fall-back; skip != 0:
+// start at the row's first live column like the kernel does with row_j0
 void emu_contract(const double* K, const double* lrs, int R, int N, int pitch, const double* xn,
-                  const double* ds1, const double* dlx, const double* xgrid, int exact,
-                  double* out) {
-  int nint = N - 1, m = odd_chunk(nint);
+                  const double* ds1, const double* dlx, const double* xgrid, int mode, int skip,
+                  double* out, int* n_fallback) {
+  int nint = N - 1;
+  if (n_fallback) *n_fallback = 0;
   for (int r = 0; r < R; ++r) {
+    const double* Kr = K + (size_t)r * pitch;
+    const double* Lr = lrs + (size_t)r * pitch;
+    int jt = 0;
+    if (skip) {
+      int j0 = N;
+      for (int j = 0; j < N; ++j)
+        if (Kr[j] != 0.0) { j0 = j; break; }
+      jt = (j0 - 1 > 0 ? j0 - 1 : 0) & ~1;
+    }
+    if (jt >= nint) { out[r] = 0.0; continue; }
+    int m = odd_chunk(nint - jt);
     double part[32];
-    for (int lane = 0; lane < 32; ++lane) {
-      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
-      double acc = 0.0;
-      if (i0 < nint) {
-        if (exact)
-          contract_lane_exact<1>(xn, xgrid, K + (size_t)r * pitch, pitch, i0, i1, &acc);
-        else
-          contract_lane_fast<1>(xn, ds1, dlx, K + (size_t)r * pitch, lrs + (size_t)r * pitch,
-                                pitch, i0, i1, &acc);
+    unsigned worst[32];
+    for (int pass = 0; pass < 2; ++pass) {
+      bool redo = false;
+      for (int lane = 0; lane < 32; ++lane) {
+        int i0 = jt + lane * m, i1 = i0 + m < nint ? i0 + m : nint;
+        double acc = 0.0;
+        worst[lane] = 0u;
+        if (i0 < nint) {
+          if (mode == 1)
+            contract_lane_exact<1>(xn, xgrid, Kr, pitch, i0, i1, &acc);
+          else if (mode == 2 && pass == 0)
+            worst[lane] = contract_lane_lean<1>(xn, ds1, Kr, Lr, pitch, i0, i1, &acc);
+          else
+            contract_lane_fast<1>(xn, ds1, dlx, Kr, Lr, pitch, i0, i1, &acc);
+        }
+        part[lane] = acc;
+        redo = redo || worst[lane] >= NB_REG_RANGE;
       }
-      part[lane] = acc;
+      if (!redo) break;
+      if (n_fallback && pass == 0) ++*n_fallback;
     }
     out[r] = tree32(part);
   }
@@ -156,7 +180,13 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
                      int N_E, double* out) {
   double* iec = (double*)malloc(sizeof(double) * N);
   double* cb = (double*)malloc(sizeof(double) * N);
-  for (int j = 0; j < N; ++j) syn_node(gam[j], B, &iec[j], &cb[j]);
+  double ikB, cbk;
+  syn_walker(B, &ikB, &cbk);
+  for (int j = 0; j < N; ++j) {  // the kernels' node tables gm2 = g^-2, g23 = cbrt(g^-2)
+    double gm2 = 1.0 / (gam[j] * gam[j]);
+    iec[j] = ikB * gm2;
+    cb[j] = cbk * cbrt(gm2);
+  }
   int nint = N - 1;
   for (int e = 0; e < N_E; ++e) {
     double tot = 0.0;
@@ -183,29 +213,6 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
   free(cb);
 }
 
-// contract_fused_kernel<RT=1>, one walker: operands derived on the fly from the grid's
-// ln x table (contract_lane_selfprep), lane decomposition + shuffle tree
-void emu_contract_selfprep(int kind, const double* p, double m1, double m2, double ns,
-                           const double* K, const double* lrs, int R, int N, int pitch,
-                           const double* x, const double* lnx, const double* dlx,
-                           const double* invdlx, double* out) {
-  PdLog S = pd_log_setup(kind, p, ns);
-  pd_log_setup_grid(S, m1, m2);
-  int nint = N - 1, m = odd_chunk(nint);
-  for (int r = 0; r < R; ++r) {
-    double part[32];
-    for (int lane = 0; lane < 32; ++lane) {
-      int i0 = lane * m, i1 = i0 + m < nint ? i0 + m : nint;
-      double acc = 0.0;
-      if (i0 < nint)
-        contract_lane_selfprep<1>(S, x, lnx, dlx, invdlx, K + (size_t)r * pitch,
-                                  lrs + (size_t)r * pitch, pitch, i0, i1, &acc);
-      part[lane] = acc;
-    }
-    out[r] = tree32(part);
-  }
-}
-
 // synchrotron_fused_kernel for one walker: node set-up from the ln x table, then the
 // same pair-of-warps integration as emu_synchrotron
 void emu_synchrotron_fused(int kind, const double* p, double m1, double m2, double ns,
@@ -225,6 +232,62 @@ void emu_synchrotron_fused(int kind, const double* p, double m1, double m2, doub
   emu_synchrotron(gam, N, xn, ds1, invdlx, dlx, B, E_erg, N_E, out);
   free(xn);
   free(ds1);
+}
+
+// ssc_table_kernel + ssc_seed_kernel + ssc_inner_kernel + ssc_outer_kernel for one walker:
+// phn[Ns] seed density in 1/(mec2 cm3), xn/ds1 the electron operands on gam[N];
+// out[e] = Eph/E * integral (E_eV given for the last factor); n_fallback counts rows redone
+// with the careful cell
+void emu_ssc(const double* gam, int N, const double* Eph, const double* E_eV, int N_E,
+             const double* eps0, const double* phn, int Ns, const double* xn, const double* ds1,
+             const double* dlx, const double* invdlx, double* out, int* n_fallback) {
+  double* dls = (double*)malloc(sizeof(double) * Ns);
+  double* inv = (double*)malloc(sizeof(double) * Ns);
+  double* sds = (double*)malloc(sizeof(double) * Ns);
+  double* F = (double*)malloc(sizeof(double) * Ns);
+  double* L = (double*)malloc(sizeof(double) * Ns);
+  double* inner = (double*)malloc(sizeof(double) * N);
+  for (int s = 0; s < Ns - 1; ++s) {
+    dls[s] = log(eps0[s + 1] / eps0[s]);
+    inv[s] = 1.0 / dls[s];
+    sds[s] = slope_or_sentinel(phn[s], phn[s + 1], inv[s]);
+  }
+  if (n_fallback) *n_fallback = 0;
+  for (int e = 0; e < N_E; ++e) {
+    for (int j = 0; j < N; ++j) {
+      for (int s = 0; s < Ns; ++s) F[s] = ic_mono_f(gam[j], eps0[s], Eph[e]);
+      for (int s = 0; s < Ns - 1; ++s) L[s] = slope_or_sentinel(F[s], F[s + 1], inv[s]);
+      double acc = 0.0, prev = phn[0] * F[0];
+      unsigned worst = 0u;
+      for (int s = 0; s < Ns - 1; ++s) {
+        double xy2 = phn[s + 1] * F[s + 1];
+        cell_lean(prev, xy2, sds[s] + L[s], acc, worst);
+        prev = xy2;
+      }
+      if (worst >= NB_REG_RANGE) {
+        if (n_fallback) ++*n_fallback;
+        acc = 0.0;
+        double xy1 = phn[0] * F[0];
+        for (int s = 0; s < Ns - 1; ++s) {
+          double xy2 = phn[s + 1] * F[s + 1];
+          acc += interval_fast(xy1, xy2, sds[s] + L[s], dls[s]);
+          xy1 = xy2;
+        }
+      }
+      inner[j] = acc * ((3.0 / 4.0) * SIGT * 29979245800.0 / (gam[j] * gam[j]));
+    }
+    double part[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      double acc = 0.0;
+      for (int j = lane; j < N - 1; j += 32) {
+        double bp1 = ds1[j] + log(inner[j + 1] / inner[j]) * invdlx[j];
+        acc += interval_fast(xn[j] * inner[j], xn[j + 1] * inner[j + 1], bp1, dlx[j]);
+      }
+      part[lane] = acc;
+    }
+    out[e] = Eph[e] / E_eV[e] * tree32(part);
+  }
+  free(dls); free(inv); free(sds); free(F); free(L); free(inner);
 }
 
 // combine_lnprob_kernel

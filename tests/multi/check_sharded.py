@@ -18,7 +18,8 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 import naima_b200 as nb
-from naima_b200 import parallel, workloads as wl
+import bench_workloads as wl
+from naima_b200 import parallel
 
 W, nsteps, seed = 64 * world, 12, 5
 xt, gt = wl.c3_tables(wl.c3_device_flux)
@@ -31,7 +32,7 @@ ref.set_state(p0)
 rchain, rlp, rrows = ref.run(nsteps)
 racc = ref.acceptance_counts.copy()
 
-variants = (("nccl", False), ("p2p", False), ("p2p", True), ("fused", False), ("fused", True))
+variants = (("nccl", False), ("fused", False), ("fused", True))
 only = os.environ.get("NB_CHECK_TRANSPORTS")  # e.g. "nccl,fused" to shorten a many-GPU run
 if only:
     variants = tuple(v for v in variants if v[0] in only.split(","))

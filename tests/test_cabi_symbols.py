@@ -35,8 +35,8 @@ def test_header_declares_the_path():
                  "nb_ic_planck_table", "nb_ic_seed_table", "nb_ic_seed_spectrum",
                  "nb_brems_table", "nb_pp_analytic_table", "nb_pp_lut_table",
                  "nb_table_finalize", "nb_contract", "nb_synchrotron", "nb_combine_lnprob",
-                 "nb_param_map", "nb_stretch_propose", "nb_stretch_accept", "nb_stretch_move",
-                 "nb_stretch_update", "nb_version", "nb_strerror"):
+                 "nb_walker_prep", "nb_walker_prep_move", "nb_combine_lnprob_update",
+                 "nb_synchrotron_fused", "nb_version", "nb_strerror"):
         assert name in fns, name
 
 
@@ -53,8 +53,7 @@ def test_ctypes_binding_matches_header(built_lib):
         assert name in fns, "binding for undeclared function %s" % name
         assert len(argtypes) == fns[name], (name, len(argtypes), fns[name])
     unbound = set(fns) - set(_lib.PROTOTYPES) - {"nb_version", "nb_strerror",
-                                                  "nb_contract_smem_bytes",
-                                                  "nb_ic_seed_table_batched"}
+                                                  "nb_contract_smem_bytes"}
     assert not unbound, unbound
     L = _lib.lib()  # loads without a GPU and sets every prototype
     assert L.nb_version() >= 100

@@ -35,14 +35,17 @@ def nb():
     return naima_b200
 
 
-@pytest.fixture(params=[False, True], ids=["hoisted", "exact"])
+@pytest.fixture(params=["lean", "careful", "exact"])
 def mode(request, nb):
+    """The contraction's three cells: hoisted with the lean cell (default), hoisted with the
+    careful cell everywhere, reference operation order.  Yields True for the exact mode."""
     from naima_b200 import engine
 
-    old = engine.EXACT
-    engine.EXACT = request.param
-    yield request.param
-    engine.EXACT = old
+    old = engine.EXACT, engine.LEAN
+    engine.EXACT = request.param == "exact"
+    engine.LEAN = request.param == "lean"
+    yield engine.EXACT
+    engine.EXACT, engine.LEAN = old
 
 
 ENERGY = np.logspace(0, 15, 1000)  # eV
@@ -578,11 +581,10 @@ def test_priors(nb):
     assert_allclose(lnp[fin], want[fin], rtol=LNP_RTOL)
 
 
-@pytest.mark.parametrize("kinds", [(), ("syn",), ("syn", "table")],
-                         ids=["operand-arrays", "syn-selfprep", "all-selfprep"])
+@pytest.mark.parametrize("kinds", [(), ("syn",)], ids=["operand-arrays", "syn-selfprep"])
 def test_selfprep_kernels_vs_oracle(nb, kinds):
-    """nb_contract_fused / nb_synchrotron_fused (operands derived inside the component
-    kernels) against the oracle, for every launch configuration of the plan."""
+    """nb_synchrotron_fused (operands derived inside the kernel) and nb_synchrotron (operand
+    arrays of the set-up kernel) against the oracle, through the plan."""
     suz, hess = rxj_tables()
     data = nb.validate_data_table([suz, hess])
     rng = np.random.default_rng(11)

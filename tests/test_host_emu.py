@@ -215,10 +215,11 @@ def test_pd_prep_log_vs_reference_order(emu, pd):
 
 
 @pytest.mark.parametrize("pd", PDS[:5], ids=lambda p: p.kind)
-@pytest.mark.parametrize("exact", [0, 1])
-def test_contract_ic(emu, pd, exact):
-    """Hoisted (fast) and reference-order (exact) contraction vs the oracle's
-    trapz_loglog(n_e * K, gam) for IC on three grey bodies."""
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["careful", "exact", "lean"])
+def test_contract_ic(emu, pd, mode):
+    """Hoisted (careful / lean cell, leading zeros skipped) and reference-order (exact)
+    contraction vs the oracle's trapz_loglog(n_e * K, gam) for IC on three grey bodies."""
+    exact = int(mode == 1)
     gam = o.electron_grid(100e9, 1e15, 100)
     N = gam.size
     pitch = (N + 1) & ~1
@@ -242,15 +243,23 @@ def test_contract_ic(emu, pd, exact):
     dlx = np.zeros(N)
     dlx[:-1] = np.log(gam[1:] / gam[:-1])
     out = np.empty(R)
+    nfb = ctypes.c_int(0)
     with np.errstate(all="ignore"):
         emu.emu_contract(P(K), P(lrs), R, N, pitch, P(nraw if exact else xn), P(ds1), P(dlx),
-                         P(gam), exact, P(out))
+                         P(gam), mode, int(mode != 1), P(out), ctypes.byref(nfb))
         ref = o.trapz_loglog(o.nelec(pd, gam) * Kref, gam)
     assert np.all(np.isfinite(ref))
     nz = ref != 0
     assert nz.sum() > R // 2
     assert_allclose(out[nz], ref[nz], rtol=1e-12 if exact else 2e-10, atol=0)
     assert np.all(out[~nz] == 0)
+    if mode == 2:  # clean table, regular slopes: the lean cell alone, and it agrees with
+        assert nfb.value == 0  # the careful cell to rounding
+        out0 = np.empty(R)
+        with np.errstate(all="ignore"):
+            emu.emu_contract(P(K), P(lrs), R, N, pitch, P(xn), P(ds1), P(dlx), P(gam), 0, 0,
+                             P(out0), None)
+        assert_allclose(out[nz], out0[nz], rtol=1e-13)
 
 
 def test_contract_negative_table(emu):
@@ -275,13 +284,18 @@ def test_contract_negative_table(emu):
         emu.emu_finalize(P(K), R, N, pitch, P(invdlx), P(lrs))
     dlx = np.zeros(N)
     dlx[:-1] = np.log(x[1:] / x[:-1])
-    for exact in (0, 1):
+    for mode in (0, 1, 2):
+        exact = mode == 1
         out = np.empty(R)
+        nfb = ctypes.c_int(0)
         with np.errstate(all="ignore"):
             emu.emu_contract(P(K), P(lrs), R, N, pitch, P(nraw if exact else xn),
-                             P(ds1_e if exact else ds1), P(dlx), P(x), exact, P(out))
+                             P(ds1_e if exact else ds1), P(dlx), P(x), mode, int(mode != 1),
+                             P(out), ctypes.byref(nfb))
             ref = o.trapz_loglog(o.Jprot(pd, x) * K[:, :N], x)
         assert_allclose(out, ref, rtol=1e-12 if exact else 1e-9, atol=0)
+        if mode == 2:  # the rows with sign changes were detected and redone carefully
+            assert nfb.value == 2
 
 
 @pytest.mark.parametrize("pd", PDS[:4], ids=lambda p: p.kind)
@@ -335,37 +349,9 @@ def test_combine_lnprob(emu, rxj_data):
 
 @pytest.mark.parametrize("pd", PDS, ids=lambda p: p.kind)
 def test_selfprep_kernels(emu, pd):
-    """The self-contained kernels' math (operands from the grid's ln x table, no set-up
-    arrays): nb_contract_fused against the oracle's IC integral, nb_synchrotron_fused against
-    the oracle's synchrotron spectrum, for every particle distribution."""
-    gam = o.electron_grid(100e9, 1e15, 100)
-    N = gam.size
-    pitch = (N + 1) & ~1
-    lnx = np.log(gam)
-    dlx = np.zeros(N)
-    dlx[:-1] = np.log(gam[1:] / gam[:-1])
-    invdlx = np.zeros(N)
-    invdlx[:-1] = 1.0 / dlx[:-1]
-    Eph = np.logspace(8, 14.5, 9) / o.mec2_eV
-    with np.errstate(all="ignore"):
-        Kref = np.concatenate([o.iso_ic_on_planck(gam, T, Eph) for T in (2.72548, 3000.0)], axis=0)
-    R = Kref.shape[0]
-    K = np.zeros((R, pitch))
-    K[:, :N] = Kref
-    lrs = np.zeros((R, pitch))
-    out = np.empty(R)
-    with np.errstate(all="ignore"):
-        emu.emu_finalize(P(K), R, N, pitch, P(invdlx), P(lrs))
-        emu.emu_contract_selfprep(KINDS[pd.kind], P(pdpar(pd)), ctypes.c_double(o.mec2_erg),
-                                  ctypes.c_double(o.erg_eV), ctypes.c_double(o.mec2_eV), P(K),
-                                  P(lrs), R, N, pitch, P(gam), P(lnx), P(dlx), P(invdlx), P(out))
-        ref = o.trapz_loglog(o.nelec(pd, gam) * Kref, gam)
-    nz = ref != 0
-    assert nz.sum() > R // 2
-    big = ref > ref.max() * 1e-200  # below: the reference itself runs through subnormals
-    assert_allclose(out[big], ref[big], rtol=2e-10)
-    assert np.all(out[~nz] == 0)
-    # synchrotron on the default grid
+    """The self-contained synchrotron kernel's math (operands from the grid's ln x table, no
+    set-up arrays; per-node 1/Ec and cbrt(1/Ec) from the walker-independent g^-2 tables)
+    against the oracle's synchrotron spectrum, for every particle distribution."""
     gam = o.electron_grid(1e9, 1e9 * o.mec2_eV, 100)
     N = gam.size
     lnx = np.log(gam)
@@ -385,3 +371,36 @@ def test_selfprep_kernels(emu, pd):
         ref = o.synchrotron_spectrum(pd, E_eV, B)
         big = ref > ref.max() * 1e-200
         assert_allclose(out[big], ref[big], rtol=5e-10)
+
+
+def test_ssc_hoisted(emu):
+    """Self-Compton seed (examples/CrabNebula_SynSSC.py shapes, reduced grid): the hoisted
+    two-level integral (f_AA81 table with sentinel slopes, lean inner cell with the careful
+    fall-back, outer trapezoid) against the oracle's iso_ic_on_monochromatic path."""
+    pd = o.PDist("ExponentialCutoffBrokenPowerLaw", 3.699e36, 1e12, 0.265e12, 1.5, 3.233,
+                 1863e12, 2.0)
+    gam = o.electron_grid(1e8, 50e15, 12)
+    N = gam.size
+    Esy = np.logspace(-7, 9, 33)
+    lsy = o.synchrotron_spectrum(pd, Esy, 125e-6, Eemin_eV=1e8, Eemax_eV=50e15, nEed=12)
+    Rpwn = 2.1 * 3.0856775814913673e18
+    phn_eV = lsy / (4 * np.pi * Rpwn**2 * o.c_cgs) * 2.24  # 1/(eV cm3)
+    phn_eV[-3:] = 0.0  # a seed field that underflows at its high-energy end: zero nodes
+    E_eV = np.logspace(5, 15, 13)
+    Eph = E_eV * o.eV_erg / o.mec2_erg
+    eps0 = Esy / o.mec2_eV
+    phn = phn_eV * o.mec2_eV
+    invdlx, xn, ds1, _ = _prep(emu, pd, gam, o.mec2_erg, o.erg_eV, o.mec2_eV, exact=False)
+    dlx = np.zeros(N)
+    dlx[:-1] = np.log(gam[1:] / gam[:-1])
+    out = np.empty(E_eV.size)
+    nfb = ctypes.c_int(0)
+    with np.errstate(all="ignore"):
+        emu.emu_ssc(P(gam), N, P(Eph), P(E_eV), E_eV.size, P(eps0), P(phn), eps0.size, P(xn),
+                    P(ds1), P(dlx), P(invdlx), P(out), ctypes.byref(nfb))
+        ref = o.ic_seed_spectrum(pd, ("array", Esy, phn_eV), E_eV, gam)
+    nz = ref > ref.max() * 1e-200
+    assert nz.sum() >= 8
+    assert_allclose(out[nz], ref[nz], rtol=1e-9)
+    assert np.all(out[ref == 0] == 0)
+    assert nfb.value < 0.05 * N * E_eV.size  # the lean cell carries (almost) all rows

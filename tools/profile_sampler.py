@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 import naima_b200 as nb
-from naima_b200 import workloads as wl
+import bench_workloads as wl
 
 W = 256
 xt, gt = wl.c3_tables(wl.c3_device_flux)

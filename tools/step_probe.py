@@ -13,7 +13,8 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 import naima_b200 as nb
-from naima_b200 import parallel, workloads as wl
+import bench_workloads as wl
+from naima_b200 import parallel
 
 W = 256 * world
 xt, gt = wl.c3_tables(wl.c3_device_flux)

@@ -11,7 +11,7 @@ import torch
 
 import naima_b200 as nb
 from naima_b200 import engine as eng
-from naima_b200 import workloads as wl
+import bench_workloads as wl
 from naima_b200._lib import check, lib
 
 W = 256
