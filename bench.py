@@ -515,12 +515,14 @@ def run_native(args):
         sampler = nb.PlanSampler(W, wk.P, plan, seed=wl.SEED, block=block,
                                  transport=args.transport)  # sharded over the ranks when N > 1
         sampler._device().before_step = flush
-        h2d_step, d2h_step = sampler._device().io_bytes_per_step()  # rank 0 (reads the blobs)
-        if world > 1:
-            d2h_step += (world - 1) * 8 * W * (wk.P + 1)  # the other ranks: chain + lnprob
-            h2d_step *= world
+        # per step and rank: the draws go up, the chain row and the log-probabilities come
+        # down; the blob records (model flux + blobs of every walker) stay in HBM until
+        # get_blobs() / a State's blobs are looked at
+        h2d_step, d2h_step = sampler._device().io_bytes_per_step(rows_to_host=False)
+        h2d_step, d2h_step = h2d_step * world, d2h_step * world
         api = ("naima_b200.PlanSampler.sample (the sampler get_sampler()/run_sampler() build "
-               "for a traced model; one State per step on the host)")
+               "for a traced model; one State per step on the host, blob records fetched "
+               "from HBM on demand)")
         state = sampler.run_mcmc(p0, max(args.warmup, 3))
         torch.cuda.synchronize()
         if world > 1:

@@ -300,6 +300,8 @@ class BlobBatch:
 
     def _split(self):
         if self._flux is None:
+            if isinstance(self._rows, _DeviceRows):
+                self._rows = self._rows.fetch()
             self._flux, self._arrays = self.plan.split_rows(self._rows)
 
     @property
@@ -317,6 +319,17 @@ class BlobBatch:
 
     def __getitem__(self, w):
         return _LazyBlob(self, w)
+
+
+class _DeviceRows:
+    """Blob records [W][row_width] of one stored step, still on the device."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.shape = tuple(tensor.shape)
+
+    def fetch(self):
+        return self.tensor.cpu().numpy()
 
 
 class _LazyBlob:
@@ -391,6 +404,8 @@ class DeviceEnsemble:
         one batched call unless given."""
         from . import engine as eng
 
+        import torch
+
         coords = np.ascontiguousarray(coords, dtype=float)
         if log_prob is None or (self.nb and rows is None):
             log_prob, rows = self.plan.eval_rows(coords)
@@ -398,8 +413,9 @@ class DeviceEnsemble:
             raise ValueError("The initial log_prob was NaN")
         self.coords.copy_(eng.to_dev(coords))
         self.lp.copy_(eng.to_dev(np.ascontiguousarray(log_prob, dtype=float)))
-        if self.nb:
-            self.blobs.copy_(eng.to_dev(np.ascontiguousarray(rows, dtype=float)))
+        if self.nb:  # records: a host array or a tensor that already lives on the device
+            self.blobs.copy_(rows if isinstance(rows, torch.Tensor)
+                             else eng.to_dev(np.ascontiguousarray(rows, dtype=float)))
         self.n_acc.zero_()
 
     def _draw_step(self, s_idx, c_idx, zz, lnu):
@@ -577,12 +593,14 @@ class DeviceEnsemble:
         self._sync_ranks()  # every rank has read the previous chunk's rows back
         self.step.zero_()
 
-    def enqueue_steps(self, t0, t1, dst=None):
+    def enqueue_steps(self, t0, t1, dst=None, rows_dev=None):
         """Steps [t0, t1) of the current chunk: draw on the host, upload from pinned
         memory, replay, read the chain rows back into pinned memory -- all asynchronous.
         dst: optional (chain, lp, rows|None) pinned host tensors of t1 - t0 steps that
         receive the rows instead of this ensemble's staging buffers (the public sampler
-        passes slices of its own storage: no host copy afterwards).
+        passes slices of its own storage: no host copy afterwards).  rows_dev: optional
+        DEVICE tensor of t1 - t0 steps that receives the blob records instead of the host
+        (they then stay in HBM until somebody asks for them).
         Returns (event, rng0) with the generator state before the block."""
         import torch
 
@@ -600,7 +618,9 @@ class DeviceEnsemble:
             pn["chain"][t0:t1], pn["lp"][t0:t1], pn["rows"][t0:t1])
         d_chain.copy_(self.chain[t0:t1], non_blocking=True)
         d_lp.copy_(self.chain_lp[t0:t1], non_blocking=True)
-        if self.nb and self.read_rows and d_rows is not None:
+        if self.nb and rows_dev is not None:
+            rows_dev.copy_(self.chain_blobs[t0:t1], non_blocking=True)
+        elif self.nb and self.read_rows and d_rows is not None:
             d_rows.copy_(self.chain_blobs[t0:t1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -615,10 +635,11 @@ class DeviceEnsemble:
         self._random.set_state(keep)
         return out
 
-    def io_bytes_per_step(self):
+    def io_bytes_per_step(self, rows_to_host=None):
         """(host->device, device->host) bytes moved per ensemble step by enqueue_steps."""
+        rows_to_host = self.read_rows if rows_to_host is None else rows_to_host
         h2d = 2 * self.Ns * (4 + 4 + 8 + 8)
-        d2h = 8 * self.W * (self.P + 1 + (self.nb if self.read_rows else 0))
+        d2h = 8 * self.W * (self.P + 1 + (self.nb if rows_to_host else 0))
         return h2d, d2h
 
     def run(self, nsteps):
@@ -681,32 +702,69 @@ class PlanSampler(EnsembleSampler):
 
     def reset(self):
         super().reset()
-        self._rows = None
-        self._store_t = None  # pinned torch tensors behind _chain / _log_prob / _rows
+        self._store_t = None   # pinned torch tensors behind _chain / _log_prob
+        self._rows_dev = None  # [capacity][W][nb] blob records of the stored steps, in HBM
+        self._rows_host = None  # (n, host copy of the first n steps' records), on demand
 
     def _grow(self, n):
-        """Storage for n more steps in PINNED host memory: the device copies each block's
-        chain rows, log-probabilities and blob records straight into it."""
+        """Storage for n more steps.  Chain and log-probabilities: PINNED host memory that the
+        device copies each block's rows straight into (capacity doubles, so that continuing a
+        run rarely re-pins).  Blob records: a device buffer -- the per-walker model fluxes and
+        blobs of every step stay in HBM and come to the host when get_blobs() / a State's
+        blobs are looked at."""
         import torch
 
         if getattr(self, "_host_loop", False):
             return super()._grow(n)
+        from . import engine as eng
+
         de = self._device()
         tot = self.iteration + n
-        nbw = max(de.nb, 1) if self.read_rows else 0
-        new = (torch.empty(tot, self.nwalkers, self.ndim, dtype=torch.float64).pin_memory(),
-               torch.empty(tot, self.nwalkers, dtype=torch.float64).pin_memory(),
-               torch.empty(tot, self.nwalkers, nbw, dtype=torch.float64).pin_memory()
-               if nbw else None)
-        views = [None if t is None else t.numpy() for t in new]
-        it = self.iteration
-        if it:
-            views[0][:it] = self._chain[:it]
-            views[1][:it] = self._log_prob[:it]
-            if views[2] is not None and self._rows is not None:
-                views[2][:it] = self._rows[:it]
-        self._store_t = new
-        self._chain, self._log_prob, self._rows = views
+        cap = 0 if self._store_t is None else self._store_t[0].shape[0]
+        if tot > cap:
+            cap = max(tot, 2 * cap, 64)
+            new = (torch.empty(cap, self.nwalkers, self.ndim, dtype=torch.float64,
+                               pin_memory=True),
+                   torch.empty(cap, self.nwalkers, dtype=torch.float64, pin_memory=True))
+            views = [t.numpy() for t in new]
+            it = self.iteration
+            if it:
+                views[0][:it] = self._chain[:it]
+                views[1][:it] = self._log_prob[:it]
+            self._store_t = new
+            self._chain_full, self._log_prob_full = views
+            if de.nb and self.read_rows:
+                rows = eng.empty(cap, self.nwalkers, de.nb)
+                if it and self._rows_dev is not None:
+                    rows[:it].copy_(self._rows_dev[:it])
+                self._rows_dev = rows
+        # the base class slices [discard:iteration] of these
+        self._chain, self._log_prob = self._chain_full, self._log_prob_full
+
+    def _rows_upto(self, n):
+        """Host copy of the blob records of the first n stored steps (one D2H, cached)."""
+        if self._rows_dev is None:
+            return None
+        if self._rows_host is None or self._rows_host[0] < n:
+            import torch
+
+            torch.cuda.current_stream().synchronize()
+            self._rows_host = (n, self._rows_dev[:n].cpu().numpy())
+        return self._rows_host[1]
+
+    def get_blobs(self, flat=False, thin=1, discard=0):
+        if getattr(self, "_host_loop", False):
+            return super().get_blobs(flat=flat, thin=thin, discard=discard)
+        rows = self._rows_upto(self.iteration)
+        if rows is None:
+            return None
+        steps = range(discard + thin - 1, self.iteration, thin)
+        out = np.empty((len(steps), self.nwalkers), dtype=object)
+        for i, t in enumerate(steps):
+            batch = BlobBatch(self.plan, rows=rows[t])
+            for w in range(self.nwalkers):
+                out[i, w] = batch[w]
+        return out.reshape(-1) if flat else out
 
     def _log_prob(self, p):
         lnp, rows = self.plan.eval_rows(p)
@@ -785,13 +843,14 @@ class PlanSampler(EnsembleSampler):
             while t_out < nchunk:
                 while t_enq < nchunk and len(pending) < 2:
                     t1 = min(t_enq + self.block, nchunk)
-                    dst = None
+                    dst = rows_dev = None
                     if store:  # the device writes into the sampler's (pinned) storage
                         i0 = self.iteration + (t_enq - t_out)
                         st = self._store_t
-                        dst = (st[0][i0:i0 + t1 - t_enq], st[1][i0:i0 + t1 - t_enq],
-                               None if st[2] is None else st[2][i0:i0 + t1 - t_enq])
-                    ev, rng0 = de.enqueue_steps(t_enq, t1, dst=dst)
+                        dst = (st[0][i0:i0 + t1 - t_enq], st[1][i0:i0 + t1 - t_enq], None)
+                        if self._rows_dev is not None:
+                            rows_dev = self._rows_dev[i0:i0 + t1 - t_enq]
+                    ev, rng0 = de.enqueue_steps(t_enq, t1, dst=dst, rows_dev=rows_dev)
                     pending.append((t_enq, t1, ev, rng0))
                     t_enq = t1
                 t0, t1, ev, rng0 = pending.pop(0)
@@ -800,7 +859,7 @@ class PlanSampler(EnsembleSampler):
                 if store:
                     it0 = self.iteration
                     chain, lps = self._chain[it0:it0 + nblk], self._log_prob[it0:it0 + nblk]
-                    recs = self._rows[it0:it0 + nblk] if (de.nb and self.read_rows) else None
+                    recs = None
                 else:
                     hp = de._pin_np
                     chain, lps = hp["chain"][t0:t1].copy(), hp["lp"][t0:t1].copy()
@@ -814,18 +873,19 @@ class PlanSampler(EnsembleSampler):
                 prev = chain[-1]
                 for k in range(nblk):
                     self._accepted += moved[k]
-                    blobs = None
+                    blobs = rows_k = None
                     if recs is not None:
-                        blobs = BlobBatch(self.plan, rows=recs[k])
-                        if store:
-                            self._blobs.append(blobs)
+                        blobs, rows_k = BlobBatch(self.plan, rows=recs[k]), recs[k]
+                    elif store and self._rows_dev is not None:
+                        rows_k = self._rows_dev[self.iteration]  # device view, fetched lazily
+                        blobs = BlobBatch(self.plan, rows=_DeviceRows(rows_k))
                     self.iteration += 1
                     last = done + t0 + k + 1 == iterations
                     if last:
                         self._dev_token = token = object()
                     out = make(chain[k].copy(), lps[k].copy(), blobs,
                                self._random.get_state() if last else None,
-                               None if recs is None else recs[k], token if last else None)
+                               rows_k, token if last else None)
                     self._previous_state = out
                     try:
                         yield out

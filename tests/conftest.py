@@ -42,3 +42,9 @@ def rxj_data():
 @pytest.fixture(scope="session")
 def lut_probe():
     return dict(np.load(os.path.join(GOLDEN, "pp_lut_probe.npz")))
+
+
+@pytest.fixture(scope="session")
+def ref_units():
+    """Outputs of the reference's unit-bound functions (tests/golden/make_golden_units.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "ref_exec_units.npz")))

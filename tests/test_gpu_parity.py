@@ -432,6 +432,50 @@ def test_flux_parity_ssc(nb):
         assert_allclose(got[w], want, rtol=FLUX_RTOL)
 
 
+def test_ref_exec_unit_bound_vectors(nb, ref_units, mode):
+    """The CUDA path against per-energy outputs of the reference's own unit-bound functions
+    (tests/golden/make_golden_units.py): Synchrotron._spectrum, _calc_specic on
+    monochromatic / tabulated / grey-body seeds, Bremsstrahlung._spectrum."""
+    from naima_b200 import models as M
+    from naima_b200 import units as u
+
+    r = ref_units
+
+    def close(got, want, rtol=FLUX_RTOL):
+        live = want > np.max(want) * 1e-250
+        assert live.sum() > 0.4 * want.size
+        assert_allclose(np.asarray(got)[live], want[live], rtol=rtol)
+        assert np.all(np.abs(np.asarray(got)[~live]) <= np.max(want) * 1e-240)
+
+    ecpl = M.ExponentialCutoffPowerLaw(1.3e33 / u.eV, 1e13 * u.eV, 2.41, 4.8e13 * u.eV, 1.0)
+    bpl = M.BrokenPowerLaw(2e30 / u.eV, 2e13 * u.eV, 1e12 * u.eV, 1.5, 2.5)
+    E = r["syn_E_eV"] * u.eV
+    for tag, pd in (("ecpl", ecpl), ("bpl", bpl)):
+        for Bn, B in (("3uG", 3.24e-6), ("1mG", 1e-3)):
+            got = M.Synchrotron(pd, B=B * u.G).flux(E, distance=0).value
+            close(got, r["syn_spec_%s_%s" % (tag, Bn)])
+    E = r["ic_E_eV"] * u.eV
+    kw = dict(Eemin=1e11 * u.eV, Eemax=1e15 * u.eV, nEed=60)
+    seeds = [["mono", 0.00235 * u.eV, 0.261 * u.eV / u.cm**3],
+             ["tab", r["icm_seed_E_eV"] * u.eV, u.Quantity(r["icm_seed_n"], "1/(eV cm3)")],
+             ["FIR", 26.5 * u.K, 0.415 * u.eV / u.cm**3],
+             ["star", 25000 * u.K, 3.0 * u.eV / u.cm**3, 2.1 * u.rad]]
+    ic = M.InverseCompton(ecpl, seed_photon_fields=seeds, **kw)
+    ic.flux(E, distance=0)
+    for k, sd in enumerate(seeds):
+        close(ic.specic[k].value, r["ic_specic_" + sd[0]])
+    # the tabulated seed with a per-walker density (the hoisted self-Compton kernels)
+    if not mode:
+        n2 = np.vstack([r["icm_seed_n"], 2.0 * r["icm_seed_n"]])
+        ic2 = M.InverseCompton(ecpl, seed_photon_fields=[
+            ["tab", r["icm_seed_E_eV"] * u.eV, u.Quantity(n2, "1/(eV cm3)")]], **kw)
+        got = ic2.flux(E, distance=0).value
+        close(got[0], r["ic_specic_tab"])
+        close(got[1], 2.0 * r["ic_specic_tab"])
+    br = M.Bremsstrahlung(ecpl, n0=3.0 / u.cm**3, Eemin=1e8 * u.eV, nEed=40)
+    close(br.flux(r["br_E_eV"] * u.eV, distance=0).value, r["br_spec"])
+
+
 # ------------------------------------------------------------------------------
 # 3. likelihood
 # ------------------------------------------------------------------------------

@@ -224,3 +224,67 @@ def test_ref_exec_piondecay_parts(ref_exec):
         np.testing.assert_array_equal(pp.Amax(Tp), r["pp_Amax"])
         np.testing.assert_array_equal(pp.calc_Egmax(Tp), r["pp_Egmax"])
         np.testing.assert_array_equal(pp.nuclear_factor(Tp), r["pp_nuc"])
+
+
+# ------------------------------------------------------------------------------
+# unit-bound reference functions, executed from the reference source under a units
+# stand-in (tests/golden/make_golden_units.py): per-energy pins for the synchrotron
+# spectrum, IC on monochromatic / tabulated seeds (a7) and bremsstrahlung
+# ------------------------------------------------------------------------------
+UNITS_RTOL = 2e-13  # unit-conversion factors round differently (e.g. eV -> erg -> mec2)
+
+PD_ECPL = ("ExponentialCutoffPowerLaw", 1.3e33, 1e13, 2.41, 4.8e13, 1.0)
+PD_BPL = ("BrokenPowerLaw", 2e30, 2e13, 1e12, 1.5, 2.5)
+
+
+def _close(got, want, rtol=UNITS_RTOL):
+    got, want = np.asarray(got), np.asarray(want)
+    assert np.array_equal(want == 0, got == 0)
+    assert np.array_equal(np.isfinite(want), np.isfinite(got))
+    m = np.isfinite(want) & (want != 0)
+    assert m.sum() > 0.3 * want.size
+    assert_allclose(got[m], want[m], rtol=rtol)
+
+
+def test_ref_exec_synchrotron_spectrum(ref_units):
+    """Synchrotron._spectrum (radiative.py:282-342) per photon energy."""
+    r = ref_units
+    for tag, pdargs in (("ecpl", PD_ECPL), ("bpl", PD_BPL)):
+        pd = o.PDist(*pdargs)
+        _close(o.nelec(pd, r["syn_gam_" + tag]), r["syn_nelec_" + tag], 1e-14)
+        for Bn, B in (("3uG", 3.24e-6), ("1mG", 1e-3)):
+            with np.errstate(all="ignore"):
+                got = o.synchrotron_spectrum(pd, r["syn_E_eV"], B)
+            _close(got, r["syn_spec_%s_%s" % (tag, Bn)])
+
+
+def test_ref_exec_ic_monochromatic_and_tabulated_seed(ref_units):
+    """InverseCompton._iso_ic_on_monochromatic and _calc_specic (radiative.py:609-687):
+    the pin of SURVEY row a7 (mono / array seed; the SSC path integrates the same kernel)."""
+    r = ref_units
+    gam, Eph, E = r["ic_gam"], r["icm_Eph"], r["ic_E_eV"]
+    with np.errstate(all="ignore"):
+        _close(o.iso_ic_on_monochromatic(gam, np.array([0.00235]) / o.mec2_eV,
+                                         np.array([0.261]) * o.eV_erg / o.mec2_erg, Eph),
+               r["icm_mono"])
+        _close(o.iso_ic_on_monochromatic(gam, r["icm_seed_E_eV"] / o.mec2_eV,
+                                         r["icm_seed_n"] * o.mec2_eV, Eph), r["icm_array"])
+        pd = o.PDist(*PD_ECPL)
+        seeds = {"mono": ("mono", 0.00235, 0.261 * o.eV_erg),
+                 "tab": ("array", r["icm_seed_E_eV"], r["icm_seed_n"]),
+                 "FIR": ("thermal", 26.5, 0.415 * o.eV_erg),
+                 "star": ("thermal", 25000.0, 3.0 * o.eV_erg, 2.1)}
+        for name, seed in seeds.items():
+            _close(o.ic_seed_spectrum(pd, seed, E, gam), r["ic_specic_" + name])
+
+
+def test_ref_exec_bremsstrahlung(ref_units):
+    """Bremsstrahlung cross sections and spectrum (radiative.py:838-989) per energy."""
+    r = ref_units
+    g2, eps = r["br_gam"][:, None], r["br_eps"]
+    with np.errstate(all="ignore"):
+        _close(o._sigma_1(g2, eps), r["br_sigma_1"], 1e-15)
+        _close(o._sigma_2(g2, eps), r["br_sigma_2"], 1e-15)
+        _close(o._sigma_ee(g2, eps) / o.mec2_eV, r["br_sigma_ee"], 1e-15)
+        _close(o.bremsstrahlung_spectrum(o.PDist(*PD_ECPL), r["br_E_eV"], n0=3.0, Eemin_eV=1e8,
+                                         nEed=40), r["br_spec"])

@@ -1,6 +1,9 @@
 """Summarise an .ncu-rep (ncu --set full) into a small markdown + json file under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/r1_prof4.ncu-rep profiles/r01_ncu_contract
+    python tools/ncu_summary.py gpurun_out/r1_prof4.ncu-rep profiles/r01_ncu_contract [cells]
+
+`cells`: algorithmic cells of the profiled launch (stored so that bench.py can tell whether
+its own launch has the profiled shape before quoting the executed-instruction counts).
 """
 import collections
 import csv
@@ -38,6 +41,18 @@ for d in data:
     for k in KEYS:
         if k in idx:
             rec[k] = [d[idx[k]], units[idx[k]]]
+    # executed fp64 thread-instructions (roofline section of --set full): DADD + DMUL + DFMA
+    fp64 = 0.0
+    for h in hdr:
+        if "sass_thread_inst_executed_op_d" in h and h.endswith("_pred_on.sum") and \
+                any(op in h for op in ("op_dadd", "op_dmul", "op_dfma")):
+            try:
+                v = float(d[idx[h]])
+            except ValueError:
+                continue
+            rec[h] = [d[idx[h]], units[idx[h]]]
+            fp64 += v
+    rec["fp64_thread_insts"] = fp64 or None
     rec["dram_bytes_per_launch"] = (
         to_bytes(*rec["dram__bytes_read.sum"]) + to_bytes(*rec["dram__bytes_write.sum"]))
     st = sorted([(float(d[idx[h]]), h) for h in stall if d[idx[h]] not in ("", "n/a")],
@@ -62,7 +77,8 @@ if hi:
             op = s[1] if s[0].startswith("@") else s[0]
             mix[op] += int(r[ix])
 tot = sum(mix.values()) or 1
-json.dump({"report": rep, "launches": summ,
+cells = float(sys.argv[3]) if len(sys.argv) > 3 else None  # algorithmic cells per launch
+json.dump({"report": rep, "launches": summ, "cells_per_launch": cells,
            "opcode_mix_first_launch": {k: v for k, v in mix.most_common(16)}},
           open(out + ".json", "w"), indent=1)
 with open(out + ".md", "w") as f:
