@@ -289,13 +289,14 @@ int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch
  * The same integral as nb_ic_seed_spectrum (radiative.py:609-655 + 684) for seed
  * densities that differ per walker (examples/CrabNebula_SynSSC.py:24-28), with the
  * walker-independent factor f_AA81(gam_g, eps0_s, Eph_e) tabulated once:
- *   nb_ssc_table   Ft[s][r], Lt[s][r] (log-slope along s, sentinel for zero end points),
+ *   nb_ssc_table   KL[s][r] = (F[s+1][r], log-slope of F over interval s; sentinel for zero
+ *                  end points) as interleaved pairs of doubles, s < Ns-1, and F0[r] = F[0][r];
  *                  r = e*N + g, row pitch Rp (multiple of 128, >= N_E*N); coef[r] =
  *                  3/4 sigma_T c / gam_g^2.  invdlx_s[s] = 1/ln(eps0[s+1]/eps0[s]).
  *   nb_ssc_seed    sxn[w][s] = sum_k fac_k * src_k[w][off_k + s]  (dn/dE in 1/(mec2 cm3)
  *                  from luminosities in 1/(s eV): Lsy / (4 pi R^2 c) * 2.24 * mec2[eV]),
  *                  sds[w][s] = its slope term ln(sxn[s+1]/sxn[s]) * invdlx_s[s].
- *   nb_ssc_inner   inner[w][r] = coef[r] * trapz_loglog_s(Ft[:, r] * sxn[w, :] / eps0, eps0)
+ *   nb_ssc_inner   inner[w][r] = coef[r] * trapz_loglog_s(F[:, r] * sxn[w, :] / eps0, eps0)
  *                  -- lean cell, rows with an irregular slope redone with the careful cell.
  *   nb_ssc_outer   out[w][out_off + e] = coef_e[e] * trapz_loglog_g(n_e[w, :] * inner[w, e, :],
  *                  gam) with the electron operands xn / ds1 of nb_pd_prep; coef_e = Eph/E_eV. */
@@ -306,11 +307,11 @@ typedef struct nb_ssc_src {
   double fac;
 } nb_ssc_src;
 int nb_ssc_table(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
-                 const double* invdlx_s, int Ns, double* Ft, double* Lt, double* coef,
+                 const double* invdlx_s, int Ns, double* KL, double* F0, double* coef,
                  long long Rp, void* stream);
 int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const double* invdlx_s,
                 double* sxn, double* sds, int spitch, void* stream);
-int nb_ssc_inner(const double* Ft, const double* Lt, const double* coef, long long Rp, int Ns,
+int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long long Rp, int Ns,
                  const double* sxn, const double* sds, int spitch, int W, const double* dlx_s,
                  double* inner, void* stream);
 int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const double* xn,

@@ -350,7 +350,7 @@ struct ContractArgs {
 constexpr unsigned NB_SPIN_LIMIT = 1u << 28;  // ~ a second of polling: trap instead of hanging
 
 template <int RT, int MODE>
-__global__ void __launch_bounds__(256) contract_kernel(ContractArgs a) {
+__global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(ContractArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EXACT = MODE == 1;
   double* sK = reinterpret_cast<double*>(smem_raw);
@@ -1098,33 +1098,30 @@ __global__ void ssc_table_kernel(const double* __restrict__ gam, int N,
                                  const double* __restrict__ Eph, int N_E,
                                  const double* __restrict__ eps0,
                                  const double* __restrict__ invdlx_s, int Ns,
-                                 double* __restrict__ Ft, double* __restrict__ Lt,
+                                 double2* __restrict__ KL, double* __restrict__ F0,
                                  double* __restrict__ coef, long long Rp) {
+  // KL[s][r] = (F[s+1][r], log-slope of F over interval s): what cell s of row r needs, in
+  // one 128-bit load; F0[r] = F[0][r]
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Rp) return;
   const long long R = (long long)N_E * N;
   if (r >= R) {  // padding rows: zero integrand, sentinel slope
-    for (int s = 0; s < Ns; ++s) {
-      Ft[s * Rp + r] = 0.0;
-      Lt[s * Rp + r] = NB_BIG_SLOPE;
-    }
+    for (int s = 0; s < Ns - 1; ++s) KL[s * Rp + r] = make_double2(0.0, NB_BIG_SLOPE);
+    F0[r] = 0.0;
     coef[r] = 0.0;
     return;
   }
   const int e = (int)(r / N), j = (int)(r - (long long)e * N);
   const double g = gam[j], ep = Eph[e];
   double f1 = ic_mono_f(g, eps0[0], ep);
-  Ft[r] = f1;
+  F0[r] = f1;
   for (int s = 1; s < Ns; ++s) {
     const double f2 = ic_mono_f(g, eps0[s], ep);
-    Ft[s * Rp + r] = f2;
-    Lt[(s - 1) * Rp + r] = slope_or_sentinel(f1, f2, invdlx_s[s - 1]);
+    KL[(s - 1) * Rp + r] = make_double2(f2, slope_or_sentinel(f1, f2, invdlx_s[s - 1]));
     f1 = f2;
   }
-  Lt[(long long)(Ns - 1) * Rp + r] = 0.0;
   coef[r] = (3.0 / 4.0) * SIGT * 29979245800.0 / (g * g);
 }
-
 
 struct SscSeedArgs {
   const double* src[NB_SSC_MAX_SRC];  // luminosities [W][ld] in 1/(s eV)
@@ -1151,10 +1148,10 @@ __global__ void ssc_seed_kernel(const __grid_constant__ SscSeedArgs a) {
 }
 
 struct SscInnerArgs {
-  const double* Ft;
-  const double* Lt;
+  const double2* KL;   // [Ns-1][Rp]
+  const double* F0;    // [Rp]
   const double* coef;  // [Rp]
-  long long Rp;        // row pitch of the s-major tables (multiple of 128)
+  long long Rp;        // row pitch of the s-major table (multiple of 128)
   int Ns;
   const double* sxn;
   const double* sds;
@@ -1164,9 +1161,10 @@ struct SscInnerArgs {
 };
 
 // thread = one (e, g) row, WT walkers in registers; the walkers' seed operands sit in shared
-// memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell
+// memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell.  The row's
+// table entries stream from L2 two intervals ahead of their use.
 template <int WT>
-__global__ void __launch_bounds__(128) ssc_inner_kernel(const __grid_constant__ SscInnerArgs a) {
+__global__ void __launch_bounds__(128, 4) ssc_inner_kernel(const __grid_constant__ SscInnerArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_op = reinterpret_cast<double2*>(smem_raw);           // [Ns][WT]
   double* s_x0 = reinterpret_cast<double*>(s_op + (size_t)WT * a.Ns);  // [WT]
@@ -1184,22 +1182,23 @@ __global__ void __launch_bounds__(128) ssc_inner_kernel(const __grid_constant__ 
                                                       : 0.0;
   __syncthreads();
   const long long r = (long long)blockIdx.y * blockDim.x + threadIdx.x;  // < Rp by construction
-  const double* Kc = a.Ft + r;
-  const double* Lc = a.Lt + r;
+  const double2* KLc = a.KL + r;
   double acc[WT], prev[WT];
   unsigned worst = 0u;
-  const double k1 = Kc[0];
+  const double k1 = a.F0[r];
 #pragma unroll
   for (int w = 0; w < WT; ++w) {
     acc[w] = 0.0;
     prev[w] = s_x0[w] * k1;
   }
-  double k2 = Kc[a.Rp], l = Lc[0];
+  const int nint = Ns - 1;
+  double2 kla = KLc[0], klb = KLc[(nint > 1 ? 1 : 0) * a.Rp];
   const double2* op_s = s_op;
 #pragma unroll 2
-  for (int s = 0; s < Ns - 1; ++s, op_s += WT) {
-    const int sn = (s + 1 < Ns - 1) ? s + 1 : s;  // the last prefetch repeats (unused)
-    const double k2n = Kc[(long long)(sn + 1) * a.Rp], ln = Lc[(long long)sn * a.Rp];
+  for (int s = 0; s < nint; ++s, op_s += WT) {
+    const int sp = (s + 2 < nint) ? s + 2 : nint - 1;  // the last prefetches repeat (unused)
+    const double2 kln = KLc[(long long)sp * a.Rp];
+    const double k2 = kla.x, l = kla.y;
 #pragma unroll
     for (int w = 0; w < WT; ++w) {
       const double2 op = op_s[w];
@@ -1207,8 +1206,8 @@ __global__ void __launch_bounds__(128) ssc_inner_kernel(const __grid_constant__ 
       cell_lean(prev[w], xy2, op.y + l, acc[w], worst);
       prev[w] = xy2;
     }
-    k2 = k2n;
-    l = ln;
+    kla = klb;
+    klb = kln;
   }
   const double cf = a.coef[r];
   if (worst >= NB_REG_RANGE) {
@@ -1216,11 +1215,12 @@ __global__ void __launch_bounds__(128) ssc_inner_kernel(const __grid_constant__ 
     // NaN operands): redo the row with the careful cell
 #pragma unroll 1
     for (int w = 0; w < WT; ++w) {
-      double xy1 = s_x0[w] * Kc[0], t = 0.0;
-      for (int s = 0; s < Ns - 1; ++s) {
+      double xy1 = s_x0[w] * k1, t = 0.0;
+      for (int s = 0; s < nint; ++s) {
         const double2 op = s_op[s * WT + w];
-        const double xy2 = op.x * Kc[(long long)(s + 1) * a.Rp];
-        t += interval_fast(xy1, xy2, op.y + Lc[(long long)s * a.Rp], a.dlx_s[s]);
+        const double2 kl = KLc[(long long)s * a.Rp];
+        const double xy2 = op.x * kl.x;
+        t += interval_fast(xy1, xy2, op.y + kl.y, a.dlx_s[s]);
         xy1 = xy2;
       }
       if (w0 + w < a.W) a.inner[(size_t)(w0 + w) * a.Rp + r] = t * cf;
@@ -1564,7 +1564,7 @@ int nb_contract_ex(const double* K, const double* lrs, int R, int N, int pitch,
   // one wave (148 SMs x CTAs that fit by shared memory, at most 3 by registers) -- a second
   // partial wave costs more than longer CTAs
   int resident = (int)((227LL * 1024) / (smem + 1024));
-  if (resident > 3) resident = 3;
+  if (resident > (exact ? 2 : 3)) resident = exact ? 2 : 3;  // registers (launch bounds)
   if (resident < 1) resident = 1;
   int row_tiles = (R + RT - 1) / RT;
   int wpc = 8;
@@ -1930,13 +1930,13 @@ int nb_ic_seed_spectrum(const double* gam, int N, const double* nraw, int wpitch
 }
 
 int nb_ssc_table(const double* gam, int N, const double* Eph, int N_E, const double* eps0,
-                 const double* invdlx_s, int Ns, double* Ft, double* Lt, double* coef,
+                 const double* invdlx_s, int Ns, double* KL, double* F0, double* coef,
                  long long Rp, void* stream) {
-  if (!gam || !Eph || !eps0 || !invdlx_s || !Ft || !Lt || !coef || N < 2 || N_E < 1 || Ns < 2 ||
-      Rp < (long long)N * N_E || (Rp & 127))
+  if (!gam || !Eph || !eps0 || !invdlx_s || !KL || !F0 || !coef || N < 2 || N_E < 1 || Ns < 2 ||
+      Rp < (long long)N * N_E || (Rp & 127) || ((uintptr_t)KL & 15))
     return NB_EINVAL;
   ssc_table_kernel<<<(unsigned)((Rp + 127) / 128), 128, 0, as_stream(stream)>>>(
-      gam, N, Eph, N_E, eps0, invdlx_s, Ns, Ft, Lt, coef, Rp);
+      gam, N, Eph, N_E, eps0, invdlx_s, Ns, reinterpret_cast<double2*>(KL), F0, coef, Rp);
   NB_CHECK_LAUNCH();
   return 0;
 }
@@ -1965,17 +1965,17 @@ int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const doub
   return 0;
 }
 
-int nb_ssc_inner(const double* Ft, const double* Lt, const double* coef, long long Rp, int Ns,
+int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long long Rp, int Ns,
                  const double* sxn, const double* sds, int spitch, int W, const double* dlx_s,
                  double* inner, void* stream) {
-  if (!Ft || !Lt || !coef || !sxn || !sds || !dlx_s || !inner || Rp < 128 || (Rp & 127) ||
-      Ns < 2 || spitch < Ns || W < 0)
+  if (!KL || !F0 || !coef || !sxn || !sds || !dlx_s || !inner || Rp < 128 || (Rp & 127) ||
+      Ns < 2 || spitch < Ns || W < 0 || ((uintptr_t)KL & 15))
     return NB_EINVAL;
   if (W == 0) return 0;
   if (Rp / 128 > 65535) return NB_ETOOLARGE;
   SscInnerArgs a;
-  a.Ft = Ft; a.Lt = Lt; a.coef = coef; a.Rp = Rp; a.Ns = Ns; a.sxn = sxn; a.sds = sds;
-  a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
+  a.KL = reinterpret_cast<const double2*>(KL); a.F0 = F0; a.coef = coef; a.Rp = Rp; a.Ns = Ns;
+  a.sxn = sxn; a.sds = sds; a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
   constexpr int WT = 16;
   size_t smem = (size_t)WT * Ns * sizeof(double2) + WT * sizeof(double);
   if (smem > 200 * 1024) return NB_ETOOLARGE;

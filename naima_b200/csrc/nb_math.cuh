@@ -813,31 +813,47 @@ NB_HD int odd_chunk2(int nint) {
   return m;
 }
 
+// Walker operands come from global memory (L2): the loop runs NB_PF intervals behind its
+// loads -- a rotating window of NB_PF prefetched (x*n, slope[, dlx]) triples, indexed
+// statically through the unrolled body -- so that their latency hides behind NB_PF * RT cells
+// even when few warps are resident.
+constexpr int NB_PF = 4;
+
 // fast contraction: RT table rows (sK/sL, row pitch `pitch`) against one walker
 template <int RT>
 NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double* dlx,
                               const double* sK, const double* sL, int pitch, int i0, int i1,
                               double* acc) {
   double prev[RT];
-  double n1 = xnw[i0];
+  const double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
-  // walker operands come from global memory: fetch those of interval i + 1 before the
-  // RT cells of interval i so that their latency hides behind ~250 instructions
-  double n2 = xnw[i0 + 1], d = dsw[i0], dl = dlx[i0];
-  for (int i = i0; i < i1; ++i) {
-    const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
-    const double n2n = xnw[in + 1], dn = dsw[in], dln = dlx[in];
+  double n2v[NB_PF], dv[NB_PF], dlv[NB_PF];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      double xy2 = n2 * sK[r * pitch + i + 1];
-      double bp1 = d + sL[r * pitch + i];
-      acc[r] += interval_fast(prev[r], xy2, bp1, dl);
-      prev[r] = xy2;
+  for (int k = 0; k < NB_PF; ++k) {
+    const int ik = (i0 + k < i1) ? i0 + k : i1 - 1;  // clamped: loads past the range repeat
+    n2v[k] = xnw[ik + 1];
+    dv[k] = dsw[ik];
+    dlv[k] = dlx[ik];
+  }
+  for (int i = i0; i < i1; i += NB_PF) {
+#pragma unroll
+    for (int k = 0; k < NB_PF; ++k) {
+      if (i + k < i1) {
+        const double n2 = n2v[k], d = dv[k], dl = dlv[k];
+        const int ip = (i + k + NB_PF < i1) ? i + k + NB_PF : i1 - 1;
+        n2v[k] = xnw[ip + 1];
+        dv[k] = dsw[ip];
+        dlv[k] = dlx[ip];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const double xy2 = n2 * sK[r * pitch + i + k + 1];
+          const double bp1 = d + sL[r * pitch + i + k];
+          acc[r] += interval_fast(prev[r], xy2, bp1, dl);
+          prev[r] = xy2;
+        }
+      }
     }
-    n2 = n2n;
-    d = dn;
-    dl = dln;
   }
 }
 
@@ -852,19 +868,29 @@ NB_HD unsigned contract_lane_lean(const double* xnw, const double* dsw, const do
   const double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
-  double n2 = xnw[i0 + 1], d = dsw[i0];
-#pragma unroll 2
-  for (int i = i0; i < i1; ++i) {
-    const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
-    const double n2n = xnw[in + 1], dn = dsw[in];
+  double n2v[NB_PF], dv[NB_PF];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const double xy2 = n2 * sK[r * pitch + i + 1];
-      cell_lean(prev[r], xy2, d + sL[r * pitch + i], acc[r], worst);
-      prev[r] = xy2;
+  for (int k = 0; k < NB_PF; ++k) {
+    const int ik = (i0 + k < i1) ? i0 + k : i1 - 1;
+    n2v[k] = xnw[ik + 1];
+    dv[k] = dsw[ik];
+  }
+  for (int i = i0; i < i1; i += NB_PF) {
+#pragma unroll
+    for (int k = 0; k < NB_PF; ++k) {
+      if (i + k < i1) {
+        const double n2 = n2v[k], d = dv[k];
+        const int ip = (i + k + NB_PF < i1) ? i + k + NB_PF : i1 - 1;
+        n2v[k] = xnw[ip + 1];
+        dv[k] = dsw[ip];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const double xy2 = n2 * sK[r * pitch + i + k + 1];
+          cell_lean(prev[r], xy2, d + sL[r * pitch + i + k], acc[r], worst);
+          prev[r] = xy2;
+        }
+      }
     }
-    n2 = n2n;
-    d = dn;
   }
   return worst;
 }

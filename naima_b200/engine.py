@@ -52,6 +52,42 @@ def device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+class capture_graph:
+    """``with capture_graph() as g:`` -- capture the launches of the block into a
+    torch.cuda.CUDAGraph on a side stream.  The cyclic garbage collector is paused for the
+    duration: a collection that happens to run inside a capture can free pinned-memory or
+    graph objects of earlier plans, and those runtime calls are not permitted while a
+    stream is capturing (the capture dies with cudaErrorStreamCaptureInvalidated)."""
+
+    def __enter__(self):
+        import gc
+
+        self._gc = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        self.graph = torch.cuda.CUDAGraph()
+        self._s = torch.cuda.Stream()
+        self._s.wait_stream(torch.cuda.current_stream())
+        self._sc = torch.cuda.stream(self._s)
+        self._sc.__enter__()
+        self._gc_ctx = torch.cuda.graph(self.graph, stream=self._s,
+                                        capture_error_mode="thread_local")
+        self._gc_ctx.__enter__()
+        return self.graph
+
+    def __exit__(self, *exc):
+        import gc
+
+        try:
+            self._gc_ctx.__exit__(*exc)
+        finally:
+            self._sc.__exit__(*exc)
+            if self._gc:
+                gc.enable()
+        torch.cuda.current_stream().wait_stream(self._s)
+        return False
+
+
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -397,12 +433,12 @@ class SscTable:
         self.eps0_d, self.Eph_d = to_dev(eps0), to_dev(Eph)
         self.dlx_s_d, self.invdlx_s_d = to_dev(dl), to_dev(inv)
         self.coef_e_d = to_dev(Eph / E_eV)  # lum = Eph * integral; spec = lum / E (:684-687)
-        self.Ft = empty(self.Ns, self.Rp)
-        self.Lt = empty(self.Ns, self.Rp)
+        self.KL = empty(self.Ns - 1, self.Rp, 2)  # (F[s+1][r], slope[s][r]) pairs
+        self.F0 = empty(self.Rp)
         self.coef = empty(self.Rp)
         check(lib().nb_ssc_table(ptr(grid.x_d), grid.N, ptr(self.Eph_d), self.N_E,
-                                 ptr(self.eps0_d), ptr(self.invdlx_s_d), self.Ns, ptr(self.Ft),
-                                 ptr(self.Lt), ptr(self.coef), self.Rp, stream()), "nb_ssc_table")
+                                 ptr(self.eps0_d), ptr(self.invdlx_s_d), self.Ns, ptr(self.KL),
+                                 ptr(self.F0), ptr(self.coef), self.Rp, stream()), "nb_ssc_table")
 
 
 def ssc_table(grid, E_eV, seed_E_eV):
@@ -428,7 +464,7 @@ def ssc_seed(tb, sources, W, sxn, sds):
 
 
 def ssc_inner(tb, sxn, sds, W, inner):
-    check(lib().nb_ssc_inner(ptr(tb.Ft), ptr(tb.Lt), ptr(tb.coef), tb.Rp, tb.Ns, ptr(sxn),
+    check(lib().nb_ssc_inner(ptr(tb.KL), ptr(tb.F0), ptr(tb.coef), tb.Rp, tb.Ns, ptr(sxn),
                              ptr(sds), tb.spitch, W, ptr(tb.dlx_s_d), ptr(inner), stream()),
           "nb_ssc_inner")
 

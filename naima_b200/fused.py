@@ -662,13 +662,8 @@ class LikelihoodPlan:
         self._enqueue(ex)
         torch.cuda.synchronize()
         if self.use_graph:
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                with torch.cuda.graph(g, stream=s):
-                    self._enqueue(ex)
-            torch.cuda.current_stream().wait_stream(s)
+            with eng.capture_graph() as g:
+                self._enqueue(ex)
             ex.graph = g
         return ex
 

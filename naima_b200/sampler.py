@@ -550,13 +550,10 @@ class DeviceEnsemble:
             self._enqueue_step()
             torch.cuda.synchronize()
             self._sync_ranks()  # nobody is still pushing into the state restored below
-            g = torch.cuda.CUDAGraph()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                with torch.cuda.graph(g, stream=s):
-                    self._enqueue_step()
-            torch.cuda.current_stream().wait_stream(s)
+            from . import engine as eng
+
+            with eng.capture_graph() as g:
+                self._enqueue_step()
             self._graph = g
             self.coords.copy_(c0)
             self.lp.copy_(l0)

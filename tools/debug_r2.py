@@ -35,6 +35,43 @@ if what == "c5nan":
         lp = ens.chain_lp[:30].cpu().numpy()
         t, w = np.argwhere(np.isnan(lp))[0]
         print("first NaN at step", t, "walker", w, "state", ens.chain[t, w].cpu().numpy())
+elif what == "c5step":
+    wk = wl.WORKLOADS["C5"]
+    data = nb.validate_data_table(wk.tables())
+    plan = nb.LikelihoodPlan(wk.model, wk.prior, data, wk.P)
+    ens = nb.DeviceEnsemble(plan, 512, seed=wl.SEED, use_graph=False)
+    ens.set_state(wk.walkers(512))
+    ens.load_draws(30)
+    ex = ens.ex
+    found = False
+    for t in range(30):
+        for split in range(2):
+            plan._enqueue(ex, mv=ens._stretch(split))
+            torch.cuda.synchronize()
+            lnp = ex.lnp.cpu().numpy()
+            bad = np.flatnonzero(np.isnan(lnp))
+            if bad.size:
+                w = int(bad[0])
+                q = ex.pars[w].cpu().numpy()
+                row = ex.row[w].cpu().numpy()
+                print("NaN at step", t, "split", split, "proposal row", w, "q =", repr(q))
+                print("prior", ex.prior[w].item(), "flux nan", np.isnan(row[:plan.N_E]).sum(),
+                      "flux inf", np.isinf(row[:plan.N_E]).sum())
+                print("flux", row[:plan.N_E])
+                out = ex.outs[0][w].cpu().numpy()
+                print("contract out nan", np.isnan(out).sum(), out[:6])
+                p = ex.preps[plan.comps[0]["prep"]]
+                xn, ds = p.xn[w].cpu().numpy(), p.ds1[w].cpu().numpy()
+                print("xn nan/inf", np.isnan(xn).sum(), np.isinf(xn).sum(), xn[:4], xn[-4:])
+                print("ds1 nan/inf", np.isnan(ds).sum(), np.isinf(ds).sum(), ds[:4], ds[-4:])
+                print("pm", ex.pm.cpu().numpy().reshape(-1)[w * 8:(w + 1) * 8])
+                l2, f2, _ = plan(q[None, :])
+                print("same proposal through plan():", l2, "flux nan", np.isnan(f2).sum())
+                found = True
+                break
+        if found:
+            break
+    print("done, found =", found)
 elif what == "profile":
     name = sys.argv[2] if len(sys.argv) > 2 else "C3"
     wk = wl.WORKLOADS[name]
