@@ -234,11 +234,24 @@ def _prefit(p0, data, model, prior):
     def nll(*args):
         return -lnprob(*args)[0]
 
+    # the simplex's candidate points of an iteration go through the likelihood kernels in
+    # one batch: the traced plan when the callbacks can be traced, the batched callbacks when
+    # they are batch-aware, else one call per point as in the reference
+    nll_batch = None
+    try:
+        plan = LikelihoodPlan(model, None, data, len(p0))
+        nll_batch = lambda X: -plan(X, want_blobs=False)[0]  # noqa: E731
+    except TraceError:
+        if _batch_safe(p0, data, model, flat_prior):
+            nll_batch = lambda X: -np.asarray(  # noqa: E731
+                lnprob(X, data, model, flat_prior)[0], dtype=float)
+
     log.info("Finding Maximum Likelihood parameters through Nelder-Mead fitting...")
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         result = minimize(nll, p0, args=(data, model, flat_prior), method="Nelder-Mead",
-                          options={"maxfev": 500, "xtol": 1e-1, "ftol": 1e-3})
+                          options={"maxfev": 500, "xtol": 1e-1, "ftol": 1e-3},
+                          batch_func=nll_batch)
         ll_prior = lnprob(result["x"], data, model, prior)[0]
     if (result["success"] or result["status"] == 1) and not np.isinf(ll_prior):
         if result["status"] != 1:

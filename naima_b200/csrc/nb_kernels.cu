@@ -18,6 +18,7 @@
 // All arithmetic is IEEE fp64; no tensor cores (there is no dense contraction).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cuda/ptx>
 
@@ -41,6 +42,17 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Spin loops on flags that another GPU (or a bulk copy) raises carry a watchdog: after
+// NB_WATCHDOG_NS of waiting the kernel traps -- a dead peer then surfaces as a CUDA error on
+// this rank instead of hanging every GPU of the job.
+constexpr unsigned long long NB_WATCHDOG_NS = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Replicated ensemble state (walker sharding with peer pushes): spin until every rank's
 // flag has reached this rank's generation count, i.e. all pushes of the previous
 // half-step have landed in our copy.  Called by whole CTAs before they read coords.
@@ -48,13 +60,20 @@ __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv) {
   if (mv.wait_flags == nullptr) return;
   if ((int)threadIdx.x < mv.wait_world) {
     const unsigned long long need = *mv.wait_gen;
-    unsigned long long v;
-    do {
+    unsigned long long v, t0 = 0;
+    unsigned spins = 0;
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
                    : "=l"(v)
                    : "l"(mv.wait_flags + threadIdx.x)
                    : "memory");
-    } while (v < need);
+      if (v >= need) break;
+      if ((++spins & 1023u) == 0u) {  // look at the clock every 1024 polls
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > NB_WATCHDOG_NS) __trap();  // a peer never arrived
+      }
+    }
   }
   __syncthreads();
 }
@@ -347,7 +366,6 @@ struct ContractArgs {
   int w_per_cta;
 };
 
-constexpr unsigned NB_SPIN_LIMIT = 1u << 28;  // ~ a second of polling: trap instead of hanging
 
 template <int RT, int MODE>
 __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(ContractArgs a) {
@@ -402,10 +420,19 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(Contra
     }
     __syncthreads();
   }
-  for (unsigned spin = 0; !ptx::mbarrier_try_wait_parity(bar, 0);)
-    if (++spin > NB_SPIN_LIMIT) __trap();  // a bulk copy that never completes: fail loudly
+  {  // a bulk copy that never completes (bad pointer, lost transaction): fail loudly
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; !ptx::mbarrier_try_wait_parity(bar, 0);) {
+      if ((++spins & 1023u) == 0u) {
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > NB_WATCHDOG_NS) __trap();
+      }
+    }
+  }
 
   const int m = odd_chunk(nint - jt);
+  const bool deep = m >= 16;  // long lane ranges: run four intervals behind the operand loads
   const int i0 = jt + lane * m;
   const int i1 = min(i0 + m, nint);
 
@@ -417,18 +444,23 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(Contra
     if (MODE == 2) {
       const double* dsw = a.ds1 + (size_t)w * a.wpitch;
       unsigned worst = 0u;
-      if (i0 < nint) worst = contract_lane_lean<RT>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc);
+      if (i0 < nint)
+        worst = deep ? contract_lane_lean<RT, 4>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc)
+                     : contract_lane_lean<RT, 1>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc);
       if (__any_sync(0xffffffffu, worst >= NB_REG_RANGE)) {  // irregular slope somewhere: redo
 #pragma unroll
         for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-        if (i0 < nint) contract_lane_fast<RT>(xnw, dsw, a.dlx, sK, sL, a.pitch, i0, i1, acc);
+        if (i0 < nint) contract_lane_fast<RT, 1>(xnw, dsw, a.dlx, sK, sL, a.pitch, i0, i1, acc);
       }
     } else if (i0 < nint) {
       if (EXACT)
         contract_lane_exact<RT>(xnw, a.xgrid, sK, a.pitch, i0, i1, acc);
+      else if (deep)
+        contract_lane_fast<RT, 4>(xnw, a.ds1 + (size_t)w * a.wpitch, a.dlx, sK, sL, a.pitch, i0,
+                                  i1, acc);
       else
-        contract_lane_fast<RT>(xnw, a.ds1 + (size_t)w * a.wpitch, a.dlx, sK, sL, a.pitch, i0, i1,
-                               acc);
+        contract_lane_fast<RT, 1>(xnw, a.ds1 + (size_t)w * a.wpitch, a.dlx, sK, sL, a.pitch, i0,
+                                  i1, acc);
     }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -1164,7 +1196,8 @@ struct SscInnerArgs {
 // memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell.  The row's
 // table entries stream from L2 two intervals ahead of their use.
 template <int WT>
-__global__ void __launch_bounds__(128, 4) ssc_inner_kernel(const __grid_constant__ SscInnerArgs a) {
+__global__ void __launch_bounds__(128, WT >= 16 ? 4 : 6) ssc_inner_kernel(
+    const __grid_constant__ SscInnerArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_op = reinterpret_cast<double2*>(smem_raw);           // [Ns][WT]
   double* s_x0 = reinterpret_cast<double*>(s_op + (size_t)WT * a.Ns);  // [WT]
@@ -1965,6 +1998,29 @@ int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const doub
   return 0;
 }
 
+}  // extern "C"
+
+template <int WT>
+static int launch_ssc_inner(const SscInnerArgs& a, cudaStream_t st) {
+  size_t smem = (size_t)WT * a.Ns * sizeof(double2) + WT * sizeof(double);
+  if (smem > 200 * 1024) return NB_ETOOLARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ssc_inner_kernel<WT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  // walker groups on the fast grid axis: the CTAs that share a row tile run together, so
+  // the table streams from HBM once and is re-read from L2
+  dim3 grid((a.W + WT - 1) / WT, (unsigned)(a.Rp / 128));
+  ssc_inner_kernel<WT><<<grid, 128, smem, st>>>(a);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" {
+
 int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long long Rp, int Ns,
                  const double* sxn, const double* sds, int spitch, int W, const double* dlx_s,
                  double* inner, void* stream) {
@@ -1976,22 +2032,14 @@ int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long lo
   SscInnerArgs a;
   a.KL = reinterpret_cast<const double2*>(KL); a.F0 = F0; a.coef = coef; a.Rp = Rp; a.Ns = Ns;
   a.sxn = sxn; a.sds = sds; a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
-  constexpr int WT = 16;
-  size_t smem = (size_t)WT * Ns * sizeof(double2) + WT * sizeof(double);
-  if (smem > 200 * 1024) return NB_ETOOLARGE;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ssc_inner_kernel<WT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  // walkers per thread: 16 (one table load per 16 cells, 4 CTAs per SM); NB_SSC_WT=8 in the
+  // environment selects 8 (6 CTAs per SM, twice the table traffic) for comparison
+  static int wt = 0;
+  if (wt == 0) {
+    const char* e = getenv("NB_SSC_WT");
+    wt = (e && atoi(e) == 8) ? 8 : 16;
   }
-  // walker groups on the fast grid axis: the CTAs that share a row tile run together, so
-  // the table streams from HBM once and is re-read from L2
-  dim3 grid((W + WT - 1) / WT, (unsigned)(Rp / 128));
-  ssc_inner_kernel<WT><<<grid, 128, smem, as_stream(stream)>>>(a);
-  NB_CHECK_LAUNCH();
-  return 0;
+  return wt == 8 ? launch_ssc_inner<8>(a, as_stream(stream)) : launch_ssc_inner<16>(a, as_stream(stream));
 }
 
 int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const double* xn,

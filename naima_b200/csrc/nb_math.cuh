@@ -813,14 +813,13 @@ NB_HD int odd_chunk2(int nint) {
   return m;
 }
 
-// Walker operands come from global memory (L2): the loop runs NB_PF intervals behind its
-// loads -- a rotating window of NB_PF prefetched (x*n, slope[, dlx]) triples, indexed
-// statically through the unrolled body -- so that their latency hides behind NB_PF * RT cells
-// even when few warps are resident.
-constexpr int NB_PF = 4;
-
-// fast contraction: RT table rows (sK/sL, row pitch `pitch`) against one walker
-template <int RT>
+// Walker operands come from global memory (L2).  Two loop shapes: PF == 1 fetches the
+// operands of interval i + 1 before the RT cells of interval i (short lane ranges: the
+// 13-interval ranges of the 370-node IC grid); PF == 4 runs four intervals behind its loads
+// -- a rotating window of prefetched (x*n, slope[, dlx]) triples, indexed statically through
+// the unrolled body -- so that their latency hides behind 4 * RT cells even when few warps
+// are resident (long ranges: 869-node grids).
+template <int RT, int PF>
 NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double* dlx,
                               const double* sK, const double* sL, int pitch, int i0, int i1,
                               double* acc) {
@@ -828,20 +827,38 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
   const double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
-  double n2v[NB_PF], dv[NB_PF], dlv[NB_PF];
+  if (PF == 1) {
+    double n2 = xnw[i0 + 1], d = dsw[i0], dl = dlx[i0];
+    for (int i = i0; i < i1; ++i) {
+      const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
+      const double n2n = xnw[in + 1], dn = dsw[in], dln = dlx[in];
 #pragma unroll
-  for (int k = 0; k < NB_PF; ++k) {
+      for (int r = 0; r < RT; ++r) {
+        const double xy2 = n2 * sK[r * pitch + i + 1];
+        const double bp1 = d + sL[r * pitch + i];
+        acc[r] += interval_fast(prev[r], xy2, bp1, dl);
+        prev[r] = xy2;
+      }
+      n2 = n2n;
+      d = dn;
+      dl = dln;
+    }
+    return;
+  }
+  double n2v[PF], dv[PF], dlv[PF];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
     const int ik = (i0 + k < i1) ? i0 + k : i1 - 1;  // clamped: loads past the range repeat
     n2v[k] = xnw[ik + 1];
     dv[k] = dsw[ik];
     dlv[k] = dlx[ik];
   }
-  for (int i = i0; i < i1; i += NB_PF) {
+  for (int i = i0; i < i1; i += PF) {
 #pragma unroll
-    for (int k = 0; k < NB_PF; ++k) {
+    for (int k = 0; k < PF; ++k) {
       if (i + k < i1) {
         const double n2 = n2v[k], d = dv[k], dl = dlv[k];
-        const int ip = (i + k + NB_PF < i1) ? i + k + NB_PF : i1 - 1;
+        const int ip = (i + k + PF < i1) ? i + k + PF : i1 - 1;
         n2v[k] = xnw[ip + 1];
         dv[k] = dsw[ip];
         dlv[k] = dlx[ip];
@@ -860,7 +877,7 @@ NB_HD void contract_lane_fast(const double* xnw, const double* dsw, const double
 // lean contraction (cell_lean): same operands as contract_lane_fast; returns the running
 // maximum of the slope classification word (>= NB_REG_RANGE: some interval was irregular and
 // the caller must redo the range with contract_lane_fast)
-template <int RT>
+template <int RT, int PF>
 NB_HD unsigned contract_lane_lean(const double* xnw, const double* dsw, const double* sK,
                                   const double* sL, int pitch, int i0, int i1, double* acc) {
   double prev[RT];
@@ -868,19 +885,36 @@ NB_HD unsigned contract_lane_lean(const double* xnw, const double* dsw, const do
   const double n1 = xnw[i0];
 #pragma unroll
   for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
-  double n2v[NB_PF], dv[NB_PF];
+  if (PF == 1) {
+    double n2 = xnw[i0 + 1], d = dsw[i0];
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i) {
+      const int in = (i + 1 < i1) ? i + 1 : i;  // the last prefetch repeats (unused)
+      const double n2n = xnw[in + 1], dn = dsw[in];
 #pragma unroll
-  for (int k = 0; k < NB_PF; ++k) {
+      for (int r = 0; r < RT; ++r) {
+        const double xy2 = n2 * sK[r * pitch + i + 1];
+        cell_lean(prev[r], xy2, d + sL[r * pitch + i], acc[r], worst);
+        prev[r] = xy2;
+      }
+      n2 = n2n;
+      d = dn;
+    }
+    return worst;
+  }
+  double n2v[PF], dv[PF];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) {
     const int ik = (i0 + k < i1) ? i0 + k : i1 - 1;
     n2v[k] = xnw[ik + 1];
     dv[k] = dsw[ik];
   }
-  for (int i = i0; i < i1; i += NB_PF) {
+  for (int i = i0; i < i1; i += PF) {
 #pragma unroll
-    for (int k = 0; k < NB_PF; ++k) {
+    for (int k = 0; k < PF; ++k) {
       if (i + k < i1) {
         const double n2 = n2v[k], d = dv[k];
-        const int ip = (i + k + NB_PF < i1) ? i + k + NB_PF : i1 - 1;
+        const int ip = (i + k + PF < i1) ? i + k + PF : i1 - 1;
         n2v[k] = xnw[ip + 1];
         dv[k] = dsw[ip];
 #pragma unroll

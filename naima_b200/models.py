@@ -540,6 +540,12 @@ class InverseCompton(BaseElectron):
         return super()._symbolic() or any(sd.get("symbolic")
                                           for sd in self.seed_photon_fields.values())
 
+    def _is_batched(self):
+        # a per-walker seed density [W, N_s] batches the model like array-valued parameters do
+        return super()._is_batched() or any(
+            sd["type"] == "array" and not sd.get("symbolic") and sd["photon_density"].ndim == 2
+            for sd in self.seed_photon_fields.values())
+
     def _seed_tuple(self, seed):
         if seed["type"] == "thermal":
             t = ("thermal", float(seed["T"].to("K").value), float(seed["u"].to("erg/cm3").value))

@@ -160,9 +160,10 @@ void emu_contract(const double* K, const double* lrs, int R, int N, int pitch, c
           if (mode == 1)
             contract_lane_exact<1>(xn, xgrid, Kr, pitch, i0, i1, &acc);
           else if (mode == 2 && pass == 0)
-            worst[lane] = contract_lane_lean<1>(xn, ds1, Kr, Lr, pitch, i0, i1, &acc);
+            worst[lane] = (m >= 16 ? contract_lane_lean<1, 4>(xn, ds1, Kr, Lr, pitch, i0, i1, &acc)
+                                   : contract_lane_lean<1, 1>(xn, ds1, Kr, Lr, pitch, i0, i1, &acc));
           else
-            contract_lane_fast<1>(xn, ds1, dlx, Kr, Lr, pitch, i0, i1, &acc);
+            contract_lane_fast<1, 1>(xn, ds1, dlx, Kr, Lr, pitch, i0, i1, &acc);
         }
         part[lane] = acc;
         redo = redo || worst[lane] >= NB_REG_RANGE;

@@ -265,3 +265,26 @@ def test_host_draw_helper_is_bit_identical_to_numpy(W):
         got = c.rng_state_after(rng0, 3)
         assert got[0] == after3[0] and np.array_equal(got[1], after3[1]) and got[2] == after3[2]
         del s3
+
+
+def test_batched_simplex_is_the_serial_simplex():
+    """The batched Nelder-Mead (one launch per iteration: reflection, expansion and both
+    contractions evaluated together) makes the serial algorithm's decisions: same trajectory,
+    same evaluation count, same stopping status (core.py:181-187 stops at maxfev = 500)."""
+    from naima_b200.minimize import minimize
+
+    def f(x):
+        return 100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2 + (x[2] - 3) ** 2 + abs(x[3]) ** 1.5
+
+    def fb(X):
+        return np.array([f(x) for x in X])
+
+    for opts in ({"maxfev": 500, "xtol": 1e-1, "ftol": 1e-3},
+                 {"maxfev": 500, "xtol": 1e-6, "ftol": 1e-9},
+                 {"maxfev": 60, "xtol": 1e-8, "ftol": 1e-12}):
+        for x0 in ([1.3, 0.7, 2.0, 0.5], [-1.2, 1.0, 0.0, 4.0]):
+            a = minimize(f, x0, options=opts)
+            b = minimize(f, x0, options=opts, batch_func=fb)
+            assert np.array_equal(a["x"], b["x"]) and a["fun"] == b["fun"]
+            assert (a["nfev"], a["nit"], a["status"]) == (b["nfev"], b["nit"], b["status"])
+            assert b["launches"] <= b["nit"] + 1 + b["nfev"] // 4
