@@ -469,6 +469,7 @@ def run_native(args):
     clocks = ClockSampler(local if rank == 0 else None)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
+    eng.fallback_counts(reset=True)
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -480,6 +481,7 @@ def run_native(args):
     t_wall = time.perf_counter() - t_wall0
     if world > 1:
         dist.barrier()
+    fb_contract, fb_ssc = eng.fallback_counts()
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = _max_over_ranks(float(step_ms.sum()), world)
     value = W * args.steps / (total_ms * 1e-3)
@@ -553,6 +555,9 @@ def run_native(args):
         "gpu_launches": int(gpu_launches), "acceptance_fraction": acc_frac,
         "step_ms_min_median_max": [float(step_ms.min()), float(np.median(step_ms)),
                                    float(step_ms.max())],
+        # how often the lean integration cell met an irregular slope and the range was
+        # redone with the careful cell, in the timed region of this rank
+        "lean_cell_fallbacks": {"contract_walker_tiles": fb_contract, "ssc_rows": fb_ssc},
     }
     if world > 1:  # roofline and CPU baseline are N = 1 measurements
         base.update({"transport": getattr(ens, "transport", None),

@@ -175,7 +175,7 @@ class Workload:
     """One BASELINE configuration: model/prior callbacks, truth, photon-energy groups."""
 
     def __init__(self, name, title, model, prior, p_true, energies, walkers_per_gpu, steps,
-                 scaling="weak", sed_groups=(), describe="", spread=0.1):
+                 scaling="weak", sed_groups=(), describe="", spread=0.005):
         self.name, self.title, self.spread = name, title, spread
         self.model, self.prior = model, prior
         self.p_true = None if p_true is None else np.asarray(p_true, dtype=float)
@@ -239,8 +239,15 @@ class Workload:
         return walkers(self.p_true, W, seed=seed, spread=self.spread if spread is None else spread)
 
 
-def walkers(p_true, W, seed=SEED, spread=0.1):
-    """The reference's initial ball (core.py:477-481)."""
+def walkers(p_true, W, seed=SEED, spread=0.005):
+    """The reference's initial ball (core.py:474-481): p0 + spread * p0 * N(0, 1) with the
+    0.5 % spread naima uses when p0 is the maximum-likelihood point (P0_IS_ML) -- the
+    synthetic data are generated at p_true, so it is.  The 10 % ball of an unfitted p0 spans
+    +-3 decades on a log10(norm) of 33 (+-5 on 46): the ensemble then disperses along the
+    flat low-amplitude direction instead of converging, and within a few hundred steps
+    proposes amplitudes beyond 1e308 -- inf * 0 in the integrand, a NaN likelihood and
+    emcee's "Probability function returned NaN" (observed at 512 walkers; the reference
+    would stop the same way)."""
     rng = np.random.default_rng(seed + 1)
     return p_true * (1 + spread * rng.normal(size=(W, len(p_true))))
 
@@ -259,12 +266,7 @@ WORKLOADS = {
                    c4_model, c4_prior, C4_PTRUE, c4_energies, 256, 20, sed_groups=(0,)),
     "C5": Workload("C5", "PionDecay (Kafexhiu+14 Pythia8 LUT, nuclear enhancement) on PowerLaw "
                    "protons, N_E=64, proton grid 691 nodes, P=2; 512 walkers in total",
-                   # the 0.5 % ball naima starts from after a maximum-likelihood prefit
-                   # (core.py:474): a 10 % ball on log10(norm) = 46 spans nine decades, the
-                   # ensemble then drifts along the flat low-amplitude direction and proposes
-                   # amplitudes that overflow to inf (NaN likelihood, a ValueError in emcee too)
-                   c5_model, c5_prior, C5_PTRUE, c5_energies, 512, 500, scaling="strong",
-                   spread=0.005),
+                   c5_model, c5_prior, C5_PTRUE, c5_energies, 512, 500, scaling="strong"),
 }
 
 # C3 helpers under their round-1 names (tools/, tests/multi)

@@ -469,6 +469,12 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
                          const double* dlx, int W, const double* E_erg, int N_E, double* out,
                          int out_ld, void* stream);
 
+/* --- measurement aid: how often the lean cell fell back to the careful cell ----------
+ * out_host[0]: (walker, row tile) pairs of nb_contract_ex mode 2 that were re-integrated,
+ * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
+ * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
+int nb_fallback_counts(unsigned long long* out_host, int reset);
+
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;
  * the caller times it with CUDA events to obtain the fp64 roofline denominator. */

@@ -123,6 +123,7 @@ PROTOTYPES = {
                                       vp, vp, vp, vp, vp, c_int, vp, vp],
     "nb_peer_wait": [ctypes.POINTER(nb_stretch), vp],
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
+    "nb_fallback_counts": [ctypes.POINTER(ctypes.c_ulonglong), c_int],
 }
 
 _lib = None

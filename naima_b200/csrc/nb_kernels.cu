@@ -36,6 +36,10 @@ using namespace nb;
 
 static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
+// how often the lean cell had to be redone with the careful cell: [0] contraction (walker,
+// row tile) pairs, [1] self-Compton rows (x walkers per thread).  Read with nb_fallback_counts.
+__device__ unsigned long long g_fallbacks[2];
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -448,6 +452,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(Contra
         worst = deep ? contract_lane_lean<RT, 4>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc)
                      : contract_lane_lean<RT, 1>(xnw, dsw, sK, sL, a.pitch, i0, i1, acc);
       if (__any_sync(0xffffffffu, worst >= NB_REG_RANGE)) {  // irregular slope somewhere: redo
+        if (lane == 0) atomicAdd(&g_fallbacks[0], 1ull);
 #pragma unroll
         for (int r = 0; r < RT; ++r) acc[r] = 0.0;
         if (i0 < nint) contract_lane_fast<RT, 1>(xnw, dsw, a.dlx, sK, sL, a.pitch, i0, i1, acc);
@@ -1246,6 +1251,7 @@ __global__ void __launch_bounds__(128, WT >= 16 ? 4 : 6) ssc_inner_kernel(
   if (worst >= NB_REG_RANGE) {
     // an irregular slope somewhere on this row (sign change in the table, |b+1| <= 1e-10,
     // NaN operands): redo the row with the careful cell
+    atomicAdd(&g_fallbacks[1], 1ull);
 #pragma unroll 1
     for (int w = 0; w < WT; ++w) {
       double xy1 = s_x0[w] * k1, t = 0.0;
@@ -2032,12 +2038,14 @@ int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long lo
   SscInnerArgs a;
   a.KL = reinterpret_cast<const double2*>(KL); a.F0 = F0; a.coef = coef; a.Rp = Rp; a.Ns = Ns;
   a.sxn = sxn; a.sds = sds; a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
-  // walkers per thread: 16 (one table load per 16 cells, 4 CTAs per SM); NB_SSC_WT=8 in the
-  // environment selects 8 (6 CTAs per SM, twice the table traffic) for comparison
+  // walkers per thread: 8 (6 CTAs = 24 warps per SM; measured 1.4x faster than 16 walkers per
+  // thread at 4 CTAs per SM although it loads the table twice as often: the kernel is bound
+  // by fp64 dependency latency, and more resident warps hide it).  NB_SSC_WT=16 in the
+  // environment selects the other blocking for comparison.
   static int wt = 0;
   if (wt == 0) {
     const char* e = getenv("NB_SSC_WT");
-    wt = (e && atoi(e) == 8) ? 8 : 16;
+    wt = (e && atoi(e) == 16) ? 16 : 8;
   }
   return wt == 8 ? launch_ssc_inner<8>(a, as_stream(stream)) : launch_ssc_inner<16>(a, as_stream(stream));
 }
@@ -2077,6 +2085,18 @@ int nb_peer_wait(const nb_stretch* mv, void* stream) {
     return NB_EINVAL;
   peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(*mv);
   NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_fallback_counts(unsigned long long* out_host, int reset) {
+  if (!out_host) return NB_EINVAL;
+  cudaError_t e = cudaMemcpyFromSymbol(out_host, g_fallbacks, sizeof(g_fallbacks));
+  if (e != cudaSuccess) return (int)e;
+  if (reset) {
+    const unsigned long long z[2] = {0ull, 0ull};
+    e = cudaMemcpyToSymbol(g_fallbacks, z, sizeof(z));
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
 }
 

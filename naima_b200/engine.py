@@ -38,6 +38,9 @@ T_CMB = 2.72548
 
 DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
+# sentinel slope of intervals with a zero end point (NB_BIG_SLOPE in csrc/nb_math.cuh)
+BIG_SLOPE = 1.5 * 2.0 ** 1022
+
 # reference operation order (log10/pow per interval) instead of the hoisted
 # contraction; settable at run time (tests exercise both)
 EXACT = False
@@ -382,8 +385,9 @@ def pp_table(grid, E_eV, useLUT, hiEmodel, nuclear_enhancement):
 # ------------------------------------------------------------------------------
 # hot kernels
 # ------------------------------------------------------------------------------
-def contract(table, prep, out=None, exact=None):
-    """out[w][r] = coef[r] * trapz_loglog(n[w,:] K[r,:], x)."""
+def contract(table, prep, out=None, exact=None, coef=None):
+    """out[w][r] = coef[r] * trapz_loglog(n[w,:] K[r,:], x); coef: row coefficients in place
+    of the table's own (a plan's copy with per-energy factors folded in)."""
     exact = EXACT if exact is None else exact
     g = table.grid
     out = empty(prep.W, table.R) if out is None else out
@@ -393,7 +397,8 @@ def contract(table, prep, out=None, exact=None):
     check(lib().nb_contract_ex(ptr(table.K), ptr(table.lrs), table.R, g.N, g.pitch,
                                ptr(table.row_j0), ptr(prep.nraw if exact else prep.xn),
                                ptr(prep.ds1), g.pitch, prep.W, ptr(g.dlx_d), ptr(g.x_d),
-                               ptr(table.coef), ptr(out), mode, stream()), "nb_contract_ex")
+                               ptr(table.coef if coef is None else coef), ptr(out), mode,
+                               stream()), "nb_contract_ex")
     return out
 
 
@@ -548,6 +553,15 @@ class DeviceData:
         self.flux, self.err_lo, self.err_hi = to_dev(flux), to_dev(err_lo), to_dev(err_hi)
         self.ul = to_dev(np.asarray(ul).astype(np.int32), dtype=torch.int32)
         self.cl = to_dev(np.broadcast_to(np.asarray(cl, dtype=float), (self.N_E,)))
+
+
+def fallback_counts(reset=False):
+    """(contraction (walker, row tile) pairs, self-Compton rows) that the lean cell handed to
+    the careful cell since the last reset."""
+    torch.cuda.synchronize()
+    out = (ctypes.c_ulonglong * 2)()
+    check(lib().nb_fallback_counts(out, int(bool(reset))), "nb_fallback_counts")
+    return int(out[0]), int(out[1])
 
 
 def fp64_peak_tflops(iters=4096, reps=5):

@@ -171,7 +171,12 @@ class SymBlob:
 
 
 class SymFlux:
-    """Sum of groups ``(sum of component spectra) / (4 pi d^2)`` in a common unit."""
+    """Sum of groups ``(sum of component spectra) / (4 pi d^2)`` in a common unit.  A group
+    is ``(component, 4 pi d^2, scale[, efac])``: efac is an optional walker-independent
+    factor per photon energy (an absorption ``transmission(E)`` multiplied to the flux)."""
+
+    __array_ufunc__ = None  # ndarray * SymFlux -> SymFlux.__rmul__
+    __array_priority__ = 30000
 
     def __init__(self, groups, E, unit, sed, base_unit):
         self.groups, self.E, self.unit, self.sed = groups, E, Unit(unit), sed
@@ -202,7 +207,7 @@ class SymFlux:
             raise TraceError("cannot add fluxes on different energy grids / representations")
         o.unit._factor_to(self.unit)
         f = o.base_unit._factor_to(self.base_unit)  # groups are held in units of base_unit
-        og = o.groups if f == 1.0 else [(c, d, sc * f) for c, d, sc in o.groups]
+        og = o.groups if f == 1.0 else [(g[0], g[1], g[2] * f) + tuple(g[3:]) for g in o.groups]
         return SymFlux(self.groups + og, self.E, self.unit, self.sed, self.base_unit)
 
     __radd__ = __add__
@@ -223,11 +228,26 @@ class SymFlux:
             raise TraceError("flux times array")
         return kv, ku
 
+    def _times_energy_factor(self, f):
+        """Product with a dimensionless array f[N_E] (one factor per photon energy)."""
+        f = np.asarray(f.value if isinstance(f, Quantity) else f, dtype=float)
+        if isinstance(f, Quantity) and any(x != 0 for x in f.unit._dims()):
+            raise TraceError("flux times a dimensional array")
+        if f.shape != np.shape(self.E.value):
+            raise TraceError("flux times an array that is not one factor per photon energy")
+        groups = [(g[0], g[1], g[2], f if len(g) < 4 or g[3] is None else g[3] * f)
+                  for g in self.groups]
+        return SymFlux(groups, self.E, self.unit, self.sed, self.base_unit)
+
     def __mul__(self, o):
+        if not isinstance(o, (SymPar, SymFlux, Unit)) and np.ndim(
+                o.value if isinstance(o, Quantity) else o) == 1:
+            return self._times_energy_factor(o)
         kv, ku = self._scaled(o, None)
         unit = self.unit if ku is None else self.unit * ku
         base = self.base_unit if ku is None else self.base_unit * ku
-        return SymFlux([(c, d, s * kv) for c, d, s in self.groups], self.E, unit, self.sed, base)
+        return SymFlux([(g[0], g[1], g[2] * kv) + tuple(g[3:]) for g in self.groups], self.E,
+                       unit, self.sed, base)
 
     __rmul__ = __mul__
 
@@ -235,7 +255,8 @@ class SymFlux:
         kv, ku = self._scaled(o, None)
         unit = self.unit if ku is None else self.unit / ku
         base = self.base_unit if ku is None else self.base_unit / ku
-        return SymFlux([(c, d, s / kv) for c, d, s in self.groups], self.E, unit, self.sed, base)
+        return SymFlux([(g[0], g[1], g[2] / kv) + tuple(g[3:]) for g in self.groups], self.E,
+                       unit, self.sed, base)
 
     def check_seed_density(self, name, energy):
         """Usable as the photon density of a tabulated IC seed field on `energy`
@@ -252,7 +273,9 @@ class SymFlux:
     def seed_sources(self):
         """[(component, factor)]: density [1/(mec2 cm3)] = sum factor * spectrum[1/(s eV)]."""
         f = self.base_unit._factor_to("1/(eV cm3)") * eng.mec2_eV
-        return [(c, sc / d * f) for c, d, sc in self.groups]
+        if any(len(g) > 3 and g[3] is not None for g in self.groups):
+            raise TraceError("seed photon density with a per-energy factor is not traced")
+        return [(g[0], g[2] / g[1] * f) for g in self.groups]
 
 
 def comp_B(comp):
@@ -363,6 +386,8 @@ class LikelihoodPlan:
         self.scalars = []  # per-walker scalar columns: SymPar or float
 
         def pd_index(pd):
+            if isinstance(pd, M.TableModel):
+                raise TraceError("TableModel particle distributions are not traced")
             for i, (p, _) in enumerate(self.pds):
                 if p is pd:
                     return i
@@ -383,10 +408,16 @@ class LikelihoodPlan:
             return len(self.scalars) - 1
 
         exact = eng.EXACT
-        for gi, (comp, div, scale) in enumerate(self.flux.groups):
+        for gi, grp in enumerate(self.flux.groups):
+            comp, div, scale = grp[:3]
+            efac = grp[3] if len(grp) > 3 else None
+            if efac is not None and not isinstance(comp, (M.InverseCompton, M.Bremsstrahlung,
+                                                          M.PionDecay)):
+                raise TraceError("a per-energy factor on %s is not traced"
+                                 % type(comp).__name__)
             ipd = pd_index(comp.particle_distribution)
             grid = comp._grid()
-            c = {"group": gi, "div": div / scale, "obj": comp}
+            c = {"group": gi, "div": div / scale, "obj": comp, "efac": efac}
             if isinstance(comp, M.Synchrotron):
                 c["kind"] = "syn"
                 c["prep"] = prep_index(ipd, grid, False)
@@ -402,6 +433,8 @@ class LikelihoodPlan:
                         raise TraceError("per-walker seed photon fields given as arrays are "
                                          "not traced")
                     seeds.append(comp._seed_tuple(sd))
+                if sym and efac is not None:
+                    raise TraceError("a per-energy factor on self-Compton emission is not traced")
                 if sym and exact:
                     raise TraceError("seed fields computed from the fit parameters are traced "
                                      "in the hoisted mode only")
@@ -451,6 +484,12 @@ class LikelihoodPlan:
             else:
                 raise TraceError("unsupported radiative class %r" % type(comp).__name__)
             self.comps.append(c)
+        # per-energy factors (absorption) fold into a private copy of the table's row
+        # coefficients: coef_eff[c * N_E + e] = coef * efac[e]
+        for c in self.comps:
+            if c.get("efac") is not None and c["kind"] == "table":
+                tb = c["table"]
+                c["coef_eff"] = tb.coef * eng.to_dev(np.tile(c["efac"], tb.n_comp))
         # Synchrotron derives the walker's operands itself (no set-up launch in front of it:
         # its CTAs own one walker, so the operands cost one pass over the nodes); the
         # reference-order (exact) mode keeps the operand arrays
@@ -769,7 +808,7 @@ class LikelihoodPlan:
             else:
                 nodes.append(("table%d" % ic,
                               lambda c=c, out=out: eng.contract(c["table"], ex.preps[c["prep"]],
-                                                                out=out),
+                                                                out=out, coef=c.get("coef_eff")),
                               ["walker_prep"]))
         return nodes
 

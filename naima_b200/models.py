@@ -24,6 +24,7 @@ from .units import Quantity
 __all__ = [
     "Synchrotron", "InverseCompton", "PionDecay", "Bremsstrahlung", "BrokenPowerLaw",
     "ExponentialCutoffPowerLaw", "PowerLaw", "LogParabola", "ExponentialCutoffBrokenPowerLaw",
+    "TableModel", "EblAbsorptionModel",
 ]
 
 log = logging.getLogger("naima_b200.models")
@@ -267,6 +268,149 @@ class LogParabola(_ParticleDistribution):
         self.beta = beta
 
 
+class TableModel(_ParticleDistribution):
+    """A model generated from a table of energy and value arrays, interpolated in log-log
+    space with a cubic spline and 0 outside the table (models.py:425-469).
+
+    As the particle distribution of a radiative class the table is interpolated ONCE per
+    particle grid on the host (it does not depend on the walker); the walkers differ by
+    ``amplitude`` only, so the integration operands are x * amplitude_w * n0(x) and the
+    walker-independent log-slope of n0 -- the kernels downstream are the usual ones."""
+    param_names = ["amplitude"]
+    _kind = "TableModel"
+
+    def __init__(self, energy, values, amplitude=1):
+        from scipy.interpolate import interp1d
+
+        self._energy = validate_array("energy", energy, domain="positive",
+                                      physical_type="energy")
+        self._values = values
+        self.amplitude = amplitude
+        loge = np.log10(Quantity(self._energy).to("eV").value)
+        if u._is_quantity(values):
+            self.unit = Quantity(values).unit
+            vals = np.asarray(Quantity(values).value, dtype=float)
+        else:
+            self.unit = u.Unit()
+            vals = np.asarray(values, dtype=float)
+        with np.errstate(divide="ignore"):
+            logy = np.log10(vals)
+        self._interplogy = interp1d(loge, logy, fill_value=-np.inf, bounds_error=False,
+                                    kind="cubic")
+
+    def _symbolic(self):
+        if _is_sym(self.amplitude):
+            from .fused import TraceError
+            raise TraceError("TableModel particle distributions are not traced")
+        return False
+
+    def _amplitude_unit(self):
+        return self.unit
+
+    def _table(self, e_eV):
+        with np.errstate(all="ignore"):
+            return np.power(10, self._interplogy(np.log10(np.asarray(e_eV, dtype=float))))
+
+    @property
+    def batch(self):
+        return np.size(self.amplitude)
+
+    def _calc(self, e):
+        interpy = self._table(e.to("eV").value)
+        amp = np.asarray(self.amplitude, dtype=float)
+        if amp.ndim:
+            interpy = amp.reshape((-1,) + (1,) * np.ndim(interpy)) * interpy
+        else:
+            interpy = float(amp) * interpy
+        return Quantity(interpy, self.unit)
+
+    def _prepared(self, grid, W, need_raw, to_unit="1/eV"):
+        """Integration operands of W walkers on `grid` (what nb_pd_prep produces for the
+        parametrised distributions), from the host-side interpolation."""
+        import torch
+
+        x = grid.x
+        fac = self.unit._factor_to(to_unit) * grid.n_scale
+        n0 = self._table((x * grid.e_mul1) * grid.e_mul2) * fac
+        amp = np.broadcast_to(np.atleast_1d(np.asarray(self.amplitude, dtype=float)), (W,))
+        pitch = grid.pitch
+        xn0, ds = np.zeros(pitch), np.zeros(pitch)
+        xn0[: grid.N] = x * n0
+        live = (n0[:-1] != 0) & (n0[1:] != 0)
+        dl = np.log(x[1:] / x[:-1])
+        with np.errstate(all="ignore"):
+            ds[: grid.N - 1] = np.where(live, np.log(n0[1:] / n0[:-1]) / dl + 1.0,
+                                        eng.BIG_SLOPE)
+        pr = eng.Prepared()
+        amp_d = eng.to_dev(amp)
+        pr.xn = (amp_d[:, None] * eng.to_dev(xn0)[None, :]).contiguous()
+        pr.ds1 = eng.to_dev(ds)[None, :].expand(W, pitch).contiguous()
+        pr.nraw = None
+        if need_raw:
+            nr = np.zeros(pitch)
+            nr[: grid.N] = n0
+            pr.nraw = (amp_d[:, None] * eng.to_dev(nr)[None, :]).contiguous()
+        pr.W, pr.grid = W, grid
+        return pr
+
+    def _energy_on(self, grid, W):
+        """Total particle energy [erg] on `grid`: trapz_loglog(x n, x) in the reference's
+        operation order (the stand-alone device op)."""
+        x = grid.x
+        n0 = self._table((x * grid.e_mul1) * grid.e_mul2) * \
+            (self.unit._factor_to("1/eV") * grid.n_scale)
+        amp = np.broadcast_to(np.atleast_1d(np.asarray(self.amplitude, dtype=float)), (W,))
+        y = amp[:, None] * (x * n0)[None, :]
+        return eng.trapz_loglog(y, x * grid.x_to_erg)
+
+
+class EblAbsorptionModel(TableModel):
+    """Optical depth of the extragalactic background light (Dominguez et al. 2011) at the
+    tabulated redshift closest to ``redshift``; ``transmission(e)`` is the dimensionless
+    factor to multiply a model with (models.py:472-552).  Host-side: the factor does not
+    depend on the walkers unless the redshift is fitted."""
+
+    def __init__(self, redshift, ebl_absorption_model="Dominguez"):
+        if _is_sym(redshift):
+            from .fused import TraceError
+            raise TraceError("a fitted redshift is not traced")
+        if not u._is_quantity(redshift):
+            redshift = Quantity(redshift, u.dimensionless_unscaled)
+        validate_physical_type("redshift", redshift, "dimensionless")
+        z = np.asarray(Quantity(redshift).value, dtype=float)
+        if z.ndim != 0:
+            raise TypeError("redshift should be a scalar floating point value")
+        if z < 0:
+            raise ValueError("redshift should be positive")
+        self.redshift = Quantity(float(z), u.dimensionless_unscaled)
+        self.model = ebl_absorption_model
+        if self.model != "Dominguez":
+            raise ValueError('Model should be one of: ["Dominguez"]')
+        import os
+
+        f = np.load(os.path.join(eng.DATA_DIR, "ebl_dominguez11.npz"))
+        energy = Quantity(f["energy_TeV"], "TeV")
+        redshift_list = np.arange(0.01, 4, 0.01)
+        if z >= 0.01:
+            table_values = f["tau"][np.abs(redshift_list - float(z)).argmin()].copy()
+            table_values[table_values > 150.0] = 150.0  # models.py:530-532
+            taus = 10 ** table_values
+        else:
+            taus = 10 ** np.zeros(energy.size)
+        super().__init__(energy, taus)
+
+    def transmission(self, e):
+        e = _validate_ene(e)
+        E_eV = np.atleast_1d(e.to("eV").value).astype(float)
+        taus = np.zeros(E_eV.size)
+        mid = (E_eV >= 1e9) & (E_eV <= 100e12)
+        taus[E_eV > 100e12] = np.log10(6000.0)
+        if np.any(mid):
+            with np.errstate(all="ignore"):
+                taus[mid] = np.log10(self._table(E_eV[mid]))
+        return np.exp(-taus)
+
+
 # ------------------------------------------------------------------------------
 # radiative models
 # ------------------------------------------------------------------------------
@@ -280,13 +424,38 @@ class BaseRadiative:
                 "naima_b200 evaluates particle distributions on the device: use PowerLaw, "
                 "ExponentialCutoffPowerLaw, BrokenPowerLaw, ExponentialCutoffBrokenPowerLaw "
                 "or LogParabola (arbitrary callables are out of scope of the hot path)")
-        validate_physical_type("Particle distribution", particle_distribution.amplitude,
-                               physical_type="differential energy")
+        if isinstance(particle_distribution, TableModel):
+            if particle_distribution.unit.physical_type != "differential energy":
+                raise TypeError("Particle distribution should be given in units of "
+                                "differential energy")
+        else:
+            validate_physical_type("Particle distribution", particle_distribution.amplitude,
+                                   physical_type="differential energy")
 
     # -- device plumbing ---------------------------------------------------------
     def _pd_device(self):
         kind, par = self.particle_distribution._device_params("1/eV")
         return kind, eng.to_dev(par), par.shape[0]
+
+    def _prep(self, g, W=None, need_raw=None):
+        """Integration operands of this model's particle distribution on grid g for W walkers."""
+        pd = self.particle_distribution
+        if isinstance(pd, TableModel):
+            need_raw = eng.EXACT if need_raw is None else need_raw
+            return pd._prepared(g, pd.batch if W is None else W, need_raw)
+        kind, par_d, Wp = self._pd_device()
+        W = Wp if W is None else W
+        if Wp != W:
+            par_d = par_d.expand(W, par_d.shape[1]).contiguous()
+        return eng.pd_prep(g, kind, par_d, W, need_raw=need_raw)
+
+    def _particle_energy(self, grid):
+        """Total particle energy [erg] on `grid`, one value per walker (host array)."""
+        pd = self.particle_distribution
+        if isinstance(pd, TableModel):
+            return pd._energy_on(grid, pd.batch)
+        kind, par_d, W = self._pd_device()
+        return eng.particle_energy(grid, kind, par_d, W).cpu().numpy()
 
     def _batch(self):
         """Batch size W of this model (1 for the reference's scalar use)."""
@@ -376,9 +545,8 @@ class BaseElectron(BaseRadiative):
 
     @property
     def _nelec(self):
-        kind, par_d, W = self._pd_device()
         g = self._grid()
-        pr = eng.pd_prep(g, kind, par_d, W, need_raw=True)
+        pr = self._prep(g, need_raw=True)
         n = pr.nraw[:, : g.N].cpu().numpy()
         return n if self._is_batched() else n[0]
 
@@ -386,8 +554,7 @@ class BaseElectron(BaseRadiative):
         if self._symbolic():
             from .fused import SymBlob
             return SymBlob("W", comp=self, grid=grid)
-        kind, par_d, W = self._pd_device()
-        We = eng.particle_energy(grid, kind, par_d, W).cpu().numpy()
+        We = self._particle_energy(grid)
         return Quantity(We if self._is_batched() else float(We[0]), u.erg)
 
     @property
@@ -429,13 +596,10 @@ class Synchrotron(BaseElectron):
         self.__dict__.update(**kwargs)
 
     def _terms(self, E_eV):
-        kind, par_d, Wp = self._pd_device()
         W = self._batch()
         B = np.broadcast_to(np.atleast_1d(Quantity(self.B).to("G").value).astype(float), (W,))
-        if Wp != W:
-            par_d = par_d.expand(W, par_d.shape[1]).contiguous()
         g = self._grid()
-        pr = eng.pd_prep(g, kind, par_d, W, need_raw=False)
+        pr = self._prep(g, W, need_raw=False)
         out = eng.synchrotron(g, pr, eng.to_dev(B), eng.to_dev(E_eV * eng.eV_erg))
         return [(out, 0, True, 1.0, None)], W
 
@@ -563,7 +727,7 @@ class InverseCompton(BaseElectron):
         """One table for all walker-independent seeds + a fused launch for each
         per-walker tabulated seed (SSC); rows are kept in seed order so that
         ``self.specic`` and the seed sum follow radiative.py:706-710."""
-        kind, par_d, W = self._pd_device()
+        W = self.particle_distribution.batch
         g = self._grid()
         N_E = E_eV.size
         names = list(self.seed_photon_fields.keys())
@@ -577,9 +741,8 @@ class InverseCompton(BaseElectron):
         if batched:
             Wb = self.seed_photon_fields[names[batched[0]]]["photon_density"].shape[0]
             if W == 1 and Wb > 1:
-                par_d = par_d.expand(Wb, par_d.shape[1]).contiguous()
                 W = Wb
-        pr = eng.pd_prep(g, kind, par_d, W, need_raw=(bool(batched) and eng.EXACT) or None)
+        pr = self._prep(g, W, need_raw=(bool(batched) and eng.EXACT) or None)
         S = len(names)
         out = eng.empty(W, S * N_E)
         if shared:
@@ -674,13 +837,10 @@ class Bremsstrahlung(BaseElectron):
         self.__dict__.update(**kwargs)
 
     def _terms(self, E_eV):
-        kind, par_d, Wp = self._pd_device()
         W = self._batch()
-        if Wp != W:
-            par_d = par_d.expand(W, par_d.shape[1]).contiguous()
         g = self._grid()
         N_E = E_eV.size
-        pr = eng.pd_prep(g, kind, par_d, W)
+        pr = self._prep(g, W)
         tb = eng.brems_table(g, E_eV)
         out = eng.contract(tb, pr)
         n0 = np.broadcast_to(np.atleast_1d(Quantity(self.n0).to("1/cm3").value).astype(float),
@@ -717,9 +877,8 @@ class BaseProton(BaseRadiative):
 
     @property
     def _J(self):
-        kind, par_d, W = self._pd_device()
         g = self._grid()
-        pr = eng.pd_prep(g, kind, par_d, W, need_raw=True)
+        pr = self._prep(g, need_raw=True)
         n = pr.nraw[:, : g.N].cpu().numpy()
         return n if self._is_batched() else n[0]
 
@@ -727,8 +886,7 @@ class BaseProton(BaseRadiative):
         if self._symbolic():
             from .fused import SymBlob
             return SymBlob("W", comp=self, grid=grid)
-        kind, par_d, W = self._pd_device()
-        Wp = eng.particle_energy(grid, kind, par_d, W).cpu().numpy()
+        Wp = self._particle_energy(grid)
         return Quantity(Wp if self._is_batched() else float(Wp[0]), u.erg)
 
     @property
@@ -777,10 +935,7 @@ class PionDecay(BaseProton):
         self.__dict__.update(**kwargs)
 
     def _terms(self, E_eV):
-        kind, par_d, Wp = self._pd_device()
         W = self._batch()
-        if Wp != W:
-            par_d = par_d.expand(W, par_d.shape[1]).contiguous()
         useLUT = bool(self.useLUT)
         if useLUT and (self.hiEmodel, bool(self.nuclear_enhancement)) not in self._LUT_MODELS:
             # radiative.py:1484-1493: missing table -> analytic parametrisation
@@ -789,7 +944,7 @@ class PionDecay(BaseProton):
             useLUT = False
             self.useLUT = False
         g = self._grid()
-        pr = eng.pd_prep(g, kind, par_d, W)
+        pr = self._prep(g, W)
         tb = eng.pp_table(g, E_eV, useLUT, self.hiEmodel, self.nuclear_enhancement)
         out = eng.contract(tb, pr)
         nh = np.broadcast_to(np.atleast_1d(Quantity(self.nh).to("1/cm3").value).astype(float),

@@ -271,3 +271,80 @@ def test_nan_lnprob_is_reported_by_the_device_sampler(nb):
         de.run(40)
     with pytest.raises(ValueError, match="NaN"):
         nb.PlanSampler(W, 2, plan, seed=5).run_mcmc(P, 40)
+
+
+def test_tablemodel_as_particle_distribution(nb):
+    """tests/test_models.py:495-527: a TableModel as the particle distribution of the
+    radiative classes; against the analytic distribution it tabulates."""
+    from naima_b200 import units as u
+    from naima_b200.models import (ExponentialCutoffPowerLaw, InverseCompton, PionDecay,
+                                   Synchrotron, TableModel)
+
+    e = np.logspace(-4, 4, 400) * u.TeV
+    ecpl = ExponentialCutoffPowerLaw(1e36 / u.eV, 1 * u.TeV, 2.0, 10 * u.TeV)
+    tm = TableModel(e, ecpl(e), amplitude=1)
+    Eph = np.logspace(-3, 1.5, 19) * u.TeV
+    for cls, kw in ((InverseCompton, dict(Eemin=1 * u.GeV, Eemax=1 * u.PeV)),
+                    (Synchrotron, dict(Eemin=1 * u.GeV, Eemax=1 * u.PeV)),
+                    (PionDecay, dict(Epmax=1 * u.PeV))):
+        Ep = Eph if cls is not Synchrotron else np.logspace(-2, 4, 19) * u.eV
+        want = cls(ecpl, **kw).flux(Ep).value
+        got = cls(tm, **kw).flux(Ep).value
+        live = want > want.max() * 1e-30
+        assert_allclose(got[live], want[live], rtol=2e-3)  # cubic log-log interpolation
+    # amplitude batches like a fitted normalisation; We follows
+    tmb = TableModel(e, ecpl(e), amplitude=np.array([1.0, 3.0]))
+    ic = InverseCompton(tmb, Eemin=1 * u.GeV, Eemax=1 * u.PeV)
+    f = ic.flux(Eph).value
+    assert f.shape == (2, 19)
+    assert_allclose(f[1], 3 * f[0], rtol=1e-12)
+    assert_allclose(ic.We.value[1], 3 * ic.We.value[0], rtol=1e-12)
+    assert_allclose(ic.We.value[0], InverseCompton(ecpl, Eemin=1 * u.GeV,
+                                                   Eemax=1 * u.PeV).We.value, rtol=2e-3)
+
+
+def test_ebl_absorbed_model_traced(nb):
+    """examples/absorbed_SynIC.py with a fixed redshift: the transmission factor folds into
+    the IC table's row coefficients of the traced plan; against the class path and the
+    oracle times the same transmission."""
+    from naima_b200 import units as u
+    from naima_b200.models import (BrokenPowerLaw, EblAbsorptionModel, InverseCompton,
+                                   Synchrotron)
+
+    def model(pars, data):
+        BPL = BrokenPowerLaw(10 ** pars[0] / u.eV, 1.0 * u.TeV, (10 ** pars[1]) * u.TeV, pars[2],
+                             pars[3])
+        IC = InverseCompton(BPL, seed_photon_fields=["CMB"], Eemin=10 * u.GeV)
+        SYN = Synchrotron(BPL, B=pars[4] * u.uG)
+        EBL = EblAbsorptionModel(0.06, "Dominguez")
+        return (EBL.transmission(data) * IC.flux(data, distance=1.0 * u.kpc)
+                + SYN.flux(data, distance=1.0 * u.kpc))
+
+    p0 = np.array((31.0, 1.0, 1.5, 2.3, 0.35))
+    E = np.concatenate([np.logspace(2, 4, 8), np.logspace(10, 13.5, 16)])
+    trans = EblAbsorptionModel(0.06).transmission(E * u.eV)
+    assert trans[0] == 1.0 and trans[-1] < 0.9
+
+    def ofl(p, E):
+        pd = o.PDist("BrokenPowerLaw", 10 ** p[0], 1e12, 10 ** p[1] * 1e12, p[2], p[3])
+        ic = o.flux_from_spectrum(o.ic_spectrum(pd, E, ["CMB"], Eemin_eV=10e9), o.kpc_cm)
+        sy = o.flux_from_spectrum(o.synchrotron_spectrum(pd, E, p[4] * 1e-6), o.kpc_cm)
+        return trans * ic + sy
+
+    rng = np.random.default_rng(8)
+    t = nb.DataTable()
+    f = ofl(p0, E) * (1 + 0.1 * rng.normal(size=E.size))
+    t["energy"] = u.Quantity(E, "eV")
+    t["flux"] = u.Quantity(f, "1/(s cm2 eV)")
+    t["flux_error"] = u.Quantity(0.1 * f, "1/(s cm2 eV)")
+    data = nb.validate_data_table(t)
+    plan = nb.LikelihoodPlan(model, None, data, 5)
+    P = p0 * (1 + 0.01 * rng.normal(size=(9, 5)))
+    lnp, flux, _ = plan(P)
+    od = bm.oracle_data(data)
+    for w in range(9):
+        m = ofl(P[w], od["E_eV"]) * od["unit_fac"]
+        assert_allclose(flux[w], m, rtol=FLUX_RTOL)
+        assert_allclose(lnp[w], o.lnprobmodel(m, od), rtol=LNP_RTOL)
+    got = model(np.ascontiguousarray(P.T), data).to(data["flux"].unit).value
+    assert_allclose(got, flux, rtol=1e-12)

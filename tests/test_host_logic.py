@@ -288,3 +288,38 @@ def test_batched_simplex_is_the_serial_simplex():
             assert np.array_equal(a["x"], b["x"]) and a["fun"] == b["fun"]
             assert (a["nfev"], a["nit"], a["status"]) == (b["nfev"], b["nit"], b["status"])
             assert b["launches"] <= b["nit"] + 1 + b["nfev"] // 4
+
+
+def test_tablemodel_and_ebl_host_side():
+    """tests/test_models.py:495-547 (the parts that need no radiative class)."""
+    from naima_b200 import units as u
+    from naima_b200.models import EblAbsorptionModel, TableModel
+
+    lemin, lemax = -4, 2
+    e = np.logspace(lemin, lemax, 50) * u.TeV
+    n = (e.value) ** -2 * np.exp(-e.value / 10) / u.eV
+    tm = TableModel(e, n, amplitude=1)
+    np.testing.assert_allclose(n.to("1/eV").value, tm(e).to("1/eV").value)
+    e2 = np.logspace(lemin, lemax, 1000) * u.TeV
+    n2 = (e2.value) ** -2 * np.exp(-e2.value / 10) / u.eV
+    np.testing.assert_allclose(n2.to("1/eV").value, tm(e2).to("1/eV").value, rtol=1e-1)
+    tm2 = TableModel(e, n.value)
+    np.testing.assert_allclose(tm2(e2).value, n2.value, rtol=1e-1)
+    e3 = np.logspace(lemin - 4, lemin - 2, 100) * u.TeV
+    np.testing.assert_allclose(tm(e3).value, 0.0)
+    # a batch of amplitudes: one row per walker
+    tmb = TableModel(e, n, amplitude=np.array([1.0, 2.0, 0.5]))
+    out = tmb(e2).value
+    assert out.shape == (3, 1000)
+    np.testing.assert_allclose(out[1], 2 * out[0])
+
+    EBL_zero = EblAbsorptionModel(0.0, "Dominguez")
+    EBL_moderate = EblAbsorptionModel(0.5, "Dominguez")
+    np.testing.assert_allclose(np.ones(50), EBL_zero.transmission(e), rtol=1e-1)
+    assert np.all(EBL_zero.transmission(e) - EBL_moderate.transmission(e) > -1e-10)
+    t = EBL_moderate.transmission(np.array([0.5, 1e3, 2e5]) * u.GeV)
+    assert t[0] == 1.0 and 0 < t[1] < 1 and t[2] == np.exp(-np.log10(6000.0))
+    with pytest.raises(ValueError):
+        EblAbsorptionModel(0.3, "Franceschini")
+    with pytest.raises(ValueError):
+        EblAbsorptionModel(-0.1)

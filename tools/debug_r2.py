@@ -35,16 +35,17 @@ if what == "c5nan":
         lp = ens.chain_lp[:30].cpu().numpy()
         t, w = np.argwhere(np.isnan(lp))[0]
         print("first NaN at step", t, "walker", w, "state", ens.chain[t, w].cpu().numpy())
-elif what == "c5step":
-    wk = wl.WORKLOADS["C5"]
+elif what == "nanstep":
+    name, W, nst = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    wk = wl.WORKLOADS[name]
     data = nb.validate_data_table(wk.tables())
     plan = nb.LikelihoodPlan(wk.model, wk.prior, data, wk.P)
-    ens = nb.DeviceEnsemble(plan, 512, seed=wl.SEED, use_graph=False)
-    ens.set_state(wk.walkers(512))
-    ens.load_draws(30)
+    ens = nb.DeviceEnsemble(plan, W, seed=wl.SEED, use_graph=False)
+    ens.set_state(wk.walkers(W))
+    ens.load_draws(nst)
     ex = ens.ex
     found = False
-    for t in range(30):
+    for t in range(nst):
         for split in range(2):
             plan._enqueue(ex, mv=ens._stretch(split))
             torch.cuda.synchronize()
@@ -65,6 +66,12 @@ elif what == "c5step":
                 print("xn nan/inf", np.isnan(xn).sum(), np.isinf(xn).sum(), xn[:4], xn[-4:])
                 print("ds1 nan/inf", np.isnan(ds).sum(), np.isinf(ds).sum(), ds[:4], ds[-4:])
                 print("pm", ex.pm.cpu().numpy().reshape(-1)[w * 8:(w + 1) * 8])
+                for k, o_ in enumerate(ex.outs):
+                    ov = o_[w].cpu().numpy()
+                    print("comp", k, plan.comps[k]["kind"], "nan", np.isnan(ov).sum(), "inf",
+                          np.isinf(ov).sum(), "first nan idx", np.flatnonzero(np.isnan(ov))[:5])
+                coords = ens.coords.cpu().numpy()
+                print("ensemble range:", coords.min(axis=0), coords.max(axis=0))
                 l2, f2, _ = plan(q[None, :])
                 print("same proposal through plan():", l2, "flux nan", np.isnan(f2).sum())
                 found = True
