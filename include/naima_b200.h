@@ -469,6 +469,22 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
                          const double* dlx, int W, const double* E_erg, int N_E, double* out,
                          int out_ld, void* stream);
 
+/* --- pion decay, Kelner+06 (PionDecayKelner06 radiative.py:1543-1767) ----------------
+ * The reference integrates KAB06 Eq. 71 (photon energies >= Etrans) and the delta-functional
+ * approximation Eq. 78 (below) with adaptive QUADPACK at epsrel = 1e-3, one Python callback
+ * per sample point.  Here both are log-log trapezoids over a per-row proton-energy grid
+ * (100 nodes per decade from the row's own lower limit):
+ *   nb_kelner_table  for row r (photon energy Eg_TeV[r]; hi[r] != 0: full calculation, else
+ *                    delta-functional): Ep[r][j] = E0_r 10^(decades j/(N-1)) and the
+ *                    walker-independent integrand kernel Kk[r][j]
+ *                    (c sigma_inel F_gamma(Eg/Ep, Ep)/Ep, or 2 c sigma_inel/sqrt(Epi^2-m_pi^2)).
+ *   nb_kelner_rows   out[w][r] = trapz_loglog(J_w(Ep[r,:]) Kk[r,:], Ep[r,:]) in 1/(s TeV)
+ *                    for n_H = 1 and nhat = 1, J = PD.eval per TeV. */
+int nb_kelner_table(const double* Eg_TeV, const int* hi, int R, int N, double decades,
+                    double* Ep, double* Kk, void* stream);
+int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, const double* Kk,
+                   int R, int N, double* out, void* stream);
+
 /* --- measurement aid: how often the lean cell fell back to the careful cell ----------
  * out_host[0]: (walker, row tile) pairs of nb_contract_ex mode 2 that were re-integrated,
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since

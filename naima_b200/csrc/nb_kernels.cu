@@ -1305,6 +1305,58 @@ __global__ void __launch_bounds__(256) ssc_outer_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------
+// pion decay, Kelner+06: every photon energy integrates over its OWN proton-energy grid
+// (the lower limit depends on the photon energy), so the particle distribution is evaluated
+// per (walker, row, node).  CTA = (row, walker); rows carry their grid Ep[r][N] (TeV) and the
+// walker-independent integrand kernel Kk[r][N]; reference-order trapezoid, fixed-order sum.
+// ---------------------------------------------------------------------------
+__global__ void kelner_table_kernel(const double* __restrict__ Eg, const int* __restrict__ hi,
+                                    int R, int N, double decades, double* __restrict__ Ep,
+                                    double* __restrict__ Kk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (j >= N || r >= R) return;
+  const double eg = Eg[r];
+  double e0;
+  if (hi[r]) {
+    e0 = eg;
+  } else {
+    const double Epimin = eg + KEL_MPI_TEV * KEL_MPI_TEV / (4 * eg);
+    e0 = KEL_MP_TEV + Epimin / KEL_KPI;
+  }
+  const double ep = e0 * exp10(decades * j / (N - 1));
+  Ep[(size_t)r * N + j] = ep;
+  Kk[(size_t)r * N + j] = hi[r] ? kel_kernel_hi(ep, eg) : kel_kernel_lo(ep);
+}
+
+__global__ void __launch_bounds__(256) kelner_rows_kernel(
+    int kind, const double* __restrict__ params, const double* __restrict__ Ep,
+    const double* __restrict__ Kk, int R, int N, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_y = reinterpret_cast<double*>(smem_raw);  // [N]
+  __shared__ double s_red[256];
+  const int r = blockIdx.x, w = blockIdx.y;
+  double p[PD_MAXPAR];
+#pragma unroll
+  for (int k = 0; k < PD_MAXPAR; ++k) p[k] = params[w * PD_MAXPAR + k];
+  const double* ep = Ep + (size_t)r * N;
+  const double* kk = Kk + (size_t)r * N;
+  // J per TeV: PD.eval(E [eV]) [1/eV] * 1e12  (radiative.py:1589-1590)
+  for (int j = threadIdx.x; j < N; j += blockDim.x)
+    s_y[j] = pd_eval(kind, p, ep[j] * 1e12) * 1e12 * kk[j];
+  __syncthreads();
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < N - 1; j += blockDim.x)
+    acc += interval_exact(ep[j], ep[j + 1], s_y[j], s_y[j + 1]);
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) s_red[threadIdx.x] += s_red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[(size_t)w * R + r] = s_red[0];
+}
+
+// ---------------------------------------------------------------------------
 // accept step + chain append from all-gathered packed records (walker sharding): one
 // warp per proposal of the active half, identical on every rank
 // ---------------------------------------------------------------------------
@@ -2084,6 +2136,30 @@ int nb_peer_wait(const nb_stretch* mv, void* stream) {
       mv->wait_world > NB_MAX_PEERS)
     return NB_EINVAL;
   peer_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(*mv);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_kelner_table(const double* Eg_TeV, const int* hi, int R, int N, double decades,
+                    double* Ep, double* Kk, void* stream) {
+  if (!Eg_TeV || !hi || !Ep || !Kk || R < 1 || N < 2 || !(decades > 0.0)) return NB_EINVAL;
+  dim3 grid((N + 127) / 128, R);
+  kelner_table_kernel<<<grid, 128, 0, as_stream(stream)>>>(Eg_TeV, hi, R, N, decades, Ep, Kk);
+  NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, const double* Kk,
+                   int R, int N, double* out, void* stream) {
+  if (!pd_params || !Ep || !Kk || !out || W < 0 || R < 1 || N < 2 || kind < 0 ||
+      kind > NB_PD_LOGPAR)
+    return NB_EINVAL;
+  if (W == 0) return 0;
+  if (W > 65535) return NB_ETOOLARGE;
+  size_t smem = (size_t)N * sizeof(double);
+  if (smem > 48 * 1024) return NB_ETOOLARGE;
+  dim3 grid(R, W);
+  kelner_rows_kernel<<<grid, 256, smem, as_stream(stream)>>>(kind, pd_params, Ep, Kk, R, N, out);
   NB_CHECK_LAUNCH();
   return 0;
 }

@@ -751,6 +751,59 @@ NB_HD double pp_diffsigma(double Ep, double Egamma, int model, int nuclear_enhan
 }
 
 // ---------------------------------------------------------------------------
+// pion decay, Kelner+06 (radiative.py:1592-1646); energies in TeV
+// ---------------------------------------------------------------------------
+NB_HD double kel_sigma_inel(double Ep) {  // KAB06 Eq. 73, 79 [cm2]
+  double L = log(Ep);
+  double sigma = 34.3 + 1.88 * L + 0.25 * (L * L);
+  if (Ep <= 0.1) {
+    const double Eth = 1.22e-3;
+    double r = Eth / Ep;
+    double r2 = r * r;
+    double t = 1 - r2 * r2;
+    sigma *= (t * t) * heaviside(Ep - Eth);
+  }
+  return sigma * 1e-27;
+}
+
+NB_HD double kel_Fgamma(double x, double Ep) {  // KAB06 Eq. 58-61
+  double L = log(Ep);
+  double B = 1.30 + 0.14 * L + 0.011 * (L * L);
+  double beta = 1.0 / (1.79 + 0.11 * L + 0.008 * (L * L));
+  double k = 1.0 / (0.801 + 0.049 * L + 0.014 * (L * L));
+  double xb = pow(x, beta);
+  double lx = log(x);
+  double q = (1 - xb) / (1 + k * xb * (1 - xb));
+  double q2 = q * q;
+  double F1 = B * (lx / x) * (q2 * q2);
+  double F2 = 1.0 / lx - (4 * beta * xb) / (1 - xb) -
+              (4 * k * beta * xb * (1 - 2 * xb)) / (1 + k * xb * (1 - xb));
+  return F1 * F2;
+}
+
+constexpr double KEL_KPI = 0.17;
+constexpr double KEL_MPI_TEV = 1.349766e-4;
+constexpr double KEL_MP_TEV = MPC2_GEV * 1e-3;
+
+// integrand kernels per unit proton energy, to be multiplied with J(Ep) [1/TeV]:
+//   full calculation (Eq. 71 with x = Eg/Ep, dx/x = -dEp/Ep):  c sigma F(Eg/Ep, Ep) / Ep
+//   delta-functional approximation (Eq. 78 with Epi = Kpi (Ep - mp)):
+//                                                 2 c sigma / sqrt(Epi^2 - m_pi^2)
+NB_HD double kel_kernel_hi(double Ep, double Eg) {
+  double x = Eg / Ep;
+  if (!(x < 1.0)) return 0.0;  // F -> 0 as x -> 1 (the limit of 0 * inf)
+  double v = C_CGS * kel_sigma_inel(Ep) * kel_Fgamma(x, Ep) / Ep;
+  return (v == v) ? v : 0.0;
+}
+
+NB_HD double kel_kernel_lo(double Ep) {
+  double Epi = KEL_KPI * (Ep - KEL_MP_TEV);
+  double d = Epi * Epi - KEL_MPI_TEV * KEL_MPI_TEV;
+  if (!(d > 0.0)) return 0.0;
+  return 2.0 * C_CGS * kel_sigma_inel(Ep) / sqrt(d);
+}
+
+// ---------------------------------------------------------------------------
 // FITPACK cubic B-spline pieces (fpbspl / fpbisp), 0-based
 // ---------------------------------------------------------------------------
 // interval search of fpbisp: returns l with t[l] <= x < t[l+1], l in [3, n-5]

@@ -493,6 +493,38 @@ def ic_seed_spectrum(grid, prep, E_eV, seed_E_eV, phn_d, per_walker, out, out_of
     return out
 
 
+# ------------------------------------------------------------------------------
+# pion decay, Kelner+06
+# ------------------------------------------------------------------------------
+KELNER_NODES_PER_DECADE = 100
+KELNER_DECADES = 7.0
+
+
+def kelner_table(Eg_TeV, hi):
+    """Per-row proton grids and integrand kernels (nb_kelner_table): (Ep[R][N], Kk[R][N])."""
+    def make():
+        R = Eg_TeV.size
+        N = int(KELNER_NODES_PER_DECADE * KELNER_DECADES) + 1
+        Eg_d = to_dev(Eg_TeV)
+        hi_d = to_dev(hi.astype(np.int32), dtype=torch.int32)
+        Ep, Kk = empty(R, N), empty(R, N)
+        check(lib().nb_kelner_table(ptr(Eg_d), ptr(hi_d), R, N, KELNER_DECADES, ptr(Ep), ptr(Kk),
+                                    stream()), "nb_kelner_table")
+        return Ep, Kk, (Eg_d, hi_d)
+
+    key = ("kelner", _ekey(Eg_TeV), hash(hi.tobytes()))
+    return _cache_get(_TABLES, key, make, _TABLES_MAX)
+
+
+def kelner_rows(kind, params_d, W, Ep, Kk):
+    """out[w][r] = trapz_loglog(J_w(Ep[r]) Kk[r], Ep[r]) in 1/(s TeV) (nb_kelner_rows)."""
+    R, N = Ep.shape
+    out = empty(W, R)
+    check(lib().nb_kelner_rows(PD_KIND[kind], ptr(params_d), W, ptr(Ep), ptr(Kk), R, N, ptr(out),
+                               stream()), "nb_kelner_rows")
+    return out
+
+
 def make_terms(terms):
     """terms: list of (src tensor [W][ld], off, group_end, div, wscale tensor|None)."""
     arr = (nb_term * len(terms))()

@@ -24,7 +24,7 @@ from .units import Quantity
 __all__ = [
     "Synchrotron", "InverseCompton", "PionDecay", "Bremsstrahlung", "BrokenPowerLaw",
     "ExponentialCutoffPowerLaw", "PowerLaw", "LogParabola", "ExponentialCutoffBrokenPowerLaw",
-    "TableModel", "EblAbsorptionModel",
+    "TableModel", "EblAbsorptionModel", "PionDecayKelner06",
 ]
 
 log = logging.getLogger("naima_b200.models")
@@ -950,3 +950,65 @@ class PionDecay(BaseProton):
         nh = np.broadcast_to(np.atleast_1d(Quantity(self.nh).to("1/cm3").value).astype(float),
                              (W,))
         return [(out, 0, True, 1.0, eng.to_dev(nh))], W
+
+
+class PionDecayKelner06(BaseRadiative):
+    """Pion-decay gamma rays after Kelner, Aharonian & Bugayov 2006 (radiative.py:1543-1767):
+    the full calculation (Eq. 71) at photon energies >= ``Etrans``, the delta-functional
+    approximation (Eq. 78) below, matched at ``Etrans`` through ``nhat``.
+
+    The reference integrates with adaptive QUADPACK at epsrel = 1e-3; here both integrals are
+    log-log trapezoids over per-row proton-energy grids of 100 nodes per decade evaluated by
+    nb_kelner_rows -- they agree with the reference to its own quadrature accuracy (a few
+    1e-4), which is also all the reference's answers are good for."""
+    _walker_scalars = ("nh",)
+    param_names = ["nh", "Etrans"]
+
+    def __init__(self, particle_distribution, nh=1.0 / u.cm**3, Etrans=0.1 * u.TeV, **kwargs):
+        super().__init__(particle_distribution)
+        if isinstance(particle_distribution, TableModel):
+            raise TypeError("PionDecayKelner06 needs a parametrised particle distribution")
+        self.nh = validate_scalar("nh", nh, physical_type="number density")
+        self.Etrans = validate_scalar("Etrans", Etrans, domain="positive",
+                                      physical_type="energy")
+        self.__dict__.update(**kwargs)
+
+    def _symbolic(self):
+        if super()._symbolic():
+            from .fused import TraceError
+            raise TraceError("PionDecayKelner06 is not traced")
+        return False
+
+    def _terms(self, E_eV):
+        kind, par_d, Wp = self._pd_device()
+        W = self._batch()
+        if Wp != W:
+            par_d = par_d.expand(W, par_d.shape[1]).contiguous()
+        Etr = Quantity(self.Etrans).to("TeV").value
+        Eg = E_eV * 1e-12
+        hi = Eg >= Etr
+        mixed = bool(np.any(hi) and np.any(~hi))
+        # two more rows at Etrans: the full and the delta-functional value that fix nhat
+        Eg_all = np.concatenate([Eg, [Etr, Etr]])
+        hi_all = np.concatenate([hi, [True, False]])
+        Ep, Kk, _ = eng.kelner_table(Eg_all, hi_all)
+        rows = eng.kelner_rows(kind, par_d, W, Ep, Kk)  # [W][N_E + 2], 1/(s TeV), nhat = 1
+        N_E = E_eV.size
+        spec = rows[:, :N_E].clone()
+        if mixed:  # radiative.py:1748-1753
+            nhat = rows[:, N_E] / rows[:, N_E + 1]
+            lo = eng.to_dev((~hi).astype(float))
+            spec = spec * (1.0 + lo[None, :] * (nhat[:, None] - 1.0))
+        spec = spec * 1e-12  # 1/(s TeV) -> 1/(s eV)
+        nh = np.broadcast_to(np.atleast_1d(Quantity(self.nh).to("1/cm3").value).astype(float),
+                             (W,))
+        return [(spec.contiguous(), 0, True, 1.0, eng.to_dev(nh))], W
+
+    @property
+    def Wp(self):
+        """Total energy in protons above the 1.22 GeV threshold (radiative.py:1719-1729)."""
+        kind, par_d, W = self._pd_device()
+        x = np.logspace(np.log10(1.22e-3), 7, 1001)  # TeV
+        n = eng.pdist_eval(kind, par_d, W, x * 1e12).cpu().numpy() * 1e12  # 1/TeV
+        Wp = eng.trapz_loglog(x[None, :] * n, x) * (1e12 * eng.eV_erg)
+        return Quantity(Wp if self._is_batched() else float(Wp[0]), u.erg)

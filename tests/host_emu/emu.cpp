@@ -291,6 +291,31 @@ void emu_ssc(const double* gam, int N, const double* Eph, const double* E_eV, in
   free(dls); free(inv); free(sds); free(F); free(L); free(inner);
 }
 
+// kelner_table_kernel + kelner_rows_kernel for one walker (serial sum instead of the CTA's
+// tree: the comparison is against adaptive quadrature at 1e-3)
+void emu_kelner(int kind, const double* p, const double* Eg, const int* hi, int R, int N,
+                double decades, double* out) {
+  double* ep = (double*)malloc(sizeof(double) * N);
+  double* y = (double*)malloc(sizeof(double) * N);
+  for (int r = 0; r < R; ++r) {
+    double e0 = Eg[r];
+    if (!hi[r]) {
+      double Epimin = Eg[r] + KEL_MPI_TEV * KEL_MPI_TEV / (4 * Eg[r]);
+      e0 = KEL_MP_TEV + Epimin / KEL_KPI;
+    }
+    for (int j = 0; j < N; ++j) {
+      ep[j] = e0 * pow(10.0, decades * j / (N - 1));
+      double kk = hi[r] ? kel_kernel_hi(ep[j], Eg[r]) : kel_kernel_lo(ep[j]);
+      y[j] = pd_eval(kind, p, ep[j] * 1e12) * 1e12 * kk;
+    }
+    double acc = 0.0;
+    for (int j = 0; j < N - 1; ++j) acc += interval_exact(ep[j], ep[j + 1], y[j], y[j + 1]);
+    out[r] = acc;
+  }
+  free(ep);
+  free(y);
+}
+
 // combine_lnprob_kernel
 void emu_combine_lnprob(const nb_term* terms, int n_terms, int W, int N_E,
                         const double* unit_fac, const double* data_flux, const double* err_lo,

@@ -348,3 +348,33 @@ def test_ebl_absorbed_model_traced(nb):
         assert_allclose(lnp[w], o.lnprobmodel(m, od), rtol=LNP_RTOL)
     got = model(np.ascontiguousarray(P.T), data).to(data["flux"].unit).value
     assert_allclose(got, flux, rtol=1e-12)
+
+
+def test_pion_decay_kelner06(nb, goldens):
+    """PionDecayKelner06 (radiative.py:1543-1767) against the reference's golden
+    (tests/test_models.py:454-471) and the oracle's QUADPACK restatement, at the accuracy the
+    reference's own epsrel = 1e-3 quadrature defines."""
+    from naima_b200 import units as u
+    from naima_b200.models import ExponentialCutoffPowerLaw, PionDecayKelner06, PowerLaw
+
+    ecpl = ExponentialCutoffPowerLaw(1 / u.TeV, 20 * u.TeV, 2.0, 10 * u.TeV)
+    energy = np.logspace(9, 13, 20) * u.eV
+    pp = PionDecayKelner06(ecpl)
+    flux = pp.flux(energy, 0)
+    lum = nb.trapz_loglog(flux * energy, energy).to("erg/s").value
+    assert_allclose(lum, 5.54580582494601e-13, rtol=2e-3)
+    want = o.PionDecayKelner06(o.PDist("ExponentialCutoffPowerLaw", 1e-12, 20e12, 2.0, 10e12,
+                                       1.0)).spectrum(energy.value)
+    assert_allclose(flux.value, want, rtol=3e-3)
+    # only-high and only-low photon energies (nhat stays 1), a batch of walkers, nh scaling
+    hiE = np.logspace(11.2, 13, 5) * u.eV
+    assert_allclose(pp.flux(hiE, 0).value, o.PionDecayKelner06(
+        o.PDist("ExponentialCutoffPowerLaw", 1e-12, 20e12, 2.0, 10e12, 1.0)).spectrum(hiE.value),
+        rtol=3e-3)
+    plb = PowerLaw(np.array([1.0, 2.0]) / u.TeV, 20 * u.TeV, np.array([2.2, 2.4]))
+    fb = PionDecayKelner06(plb, nh=np.array([1.0, 3.0]) / u.cm**3).flux(energy, 0).value
+    assert fb.shape == (2, 20)
+    for w, (a, al, nh) in enumerate(((1.0, 2.2, 1.0), (2.0, 2.4, 3.0))):
+        ref = o.PionDecayKelner06(o.PDist("PowerLaw", a * 1e-12, 20e12, al), nh=nh)
+        assert_allclose(fb[w], ref.spectrum(energy.value), rtol=3e-3)
+    assert pp.Wp.unit.to_string() == "erg"

@@ -404,3 +404,27 @@ def test_ssc_hoisted(emu):
     assert_allclose(out[nz], ref[nz], rtol=1e-9)
     assert np.all(out[ref == 0] == 0)
     assert nfb.value < 0.05 * N * E_eV.size  # the lean cell carries (almost) all rows
+
+
+def test_kelner06_fixed_grid_vs_adaptive_quadrature(emu):
+    """PionDecayKelner06 (radiative.py:1543-1767): the device formulation (log-log trapezoid
+    over a per-row proton grid, 100 nodes per decade) against the oracle's restatement with
+    the reference's adaptive QUADPACK calls; both sides are only 1e-3 accurate by the
+    reference's own epsrel."""
+    pd = o.PDist("ExponentialCutoffPowerLaw", 1e-12, 20e12, 2.0, 10e12, 1.0)
+    E_eV = np.logspace(9, 13, 20)
+    Eg = np.concatenate([E_eV * 1e-12, [0.1, 0.1]])
+    hi = np.concatenate([E_eV * 1e-12 >= 0.1, [True, False]]).astype(np.int32)
+    R, N = Eg.size, 701
+    out = np.empty(R)
+    with np.errstate(all="ignore"):
+        emu.emu_kelner(KINDS[pd.kind], P(pdpar(pd)), P(Eg), hi.ctypes.data_as(ctypes.c_void_p), R,
+                       N, ctypes.c_double(7.0), P(out))
+    nhat = out[-2] / out[-1]
+    spec = np.where(hi[:-2] == 1, out[:-2], nhat * out[:-2]) * 1e-12
+    pk = o.PionDecayKelner06(pd)
+    want = pk.spectrum(E_eV)
+    assert_allclose(nhat, pk.nhat, rtol=2e-3)
+    assert_allclose(spec, want, rtol=3e-3)
+    lum = o.trapz_loglog(spec * E_eV, E_eV) * o.eV_erg
+    assert_allclose(lum, 5.54580582494601e-13, rtol=2e-3)  # tests/test_models.py:464

@@ -288,3 +288,13 @@ def test_ref_exec_bremsstrahlung(ref_units):
         _close(o._sigma_ee(g2, eps) / o.mec2_eV, r["br_sigma_ee"], 1e-15)
         _close(o.bremsstrahlung_spectrum(o.PDist(*PD_ECPL), r["br_E_eV"], n0=3.0, Eemin_eV=1e8,
                                          nEed=40), r["br_spec"])
+
+
+def test_kelner06_golden():
+    """PionDecayKelner06 (radiative.py:1543-1767) restated with the reference's own QUADPACK
+    calls reproduces the reference's golden (tests/test_models.py:454-471)."""
+    pd = o.PDist("ExponentialCutoffPowerLaw", 1e-12, 20e12, 2.0, 10e12, 1.0)
+    E = np.logspace(9, 13, 20)
+    spec = o.PionDecayKelner06(pd).spectrum(E)
+    lum = o.trapz_loglog(spec * E, E) * o.eV_erg
+    assert_allclose(lum, 5.54580582494601e-13, rtol=1e-7)
