@@ -357,7 +357,7 @@ def run_c1(args):
     # device-resident: the launches of one call on resident inputs
     kind, par_d, W = SYN._pd_device()
     g = SYN._grid()
-    B_d, E_d = eng.to_dev([wl.C1_PARS[4] * 1e-6]), eng.to_dev(E * eng.eV_erg)
+    B_d, E_d = eng.to_dev([wl.C1_PARS[4] * 1e-6]), eng.photon_energies(E)
     out, fl = eng.empty(1, E.size), eng.empty(1, E.size)
     ones = eng.to_dev(np.ones(E.size))
     pr = eng.pd_prep(g, kind, par_d, 1, need_raw=False)

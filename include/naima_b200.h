@@ -178,12 +178,12 @@ int nb_contract_ex(const double* K, const double* lrs, int R, int N, int pitch,
  * out[w][e] = spectrum in 1/(s eV) for B[w] (Gauss) on grid gam[N] with
  * operands xn/ds1 from nb_pd_prep; E_erg[N_E] photon energies in erg.
  * gm2[j] = gam[j]^-2 and g23[j] = cbrt(gam[j]^-2) are the grid's walker-independent
- * node tables (both NULL: computed per node in the kernel); out_ld >= N_E is the row
- * pitch of out (0 = N_E). */
+ * node tables (both NULL: computed per node in the kernel); cbrtE[e] = cbrt(E_erg[e]) (NULL:
+ * computed per lane); out_ld >= N_E is the row pitch of out (0 = N_E). */
 int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g23,
                    const double* xn, const double* ds1, int wpitch, const double* invdlx,
-                   const double* dlx, const double* B, int W, const double* E_erg, int N_E,
-                   double* out, int out_ld, void* stream);
+                   const double* dlx, const double* B, int W, const double* E_erg,
+                   const double* cbrtE, int N_E, double* out, int out_ld, void* stream);
 
 /* --- combine + likelihood (BaseRadiative.flux radiative.py:102-111,
  * lnprobmodel/lnprob core.py:64-121) ------------------------------------------
@@ -470,11 +470,11 @@ int nb_contract_self(const nb_walker_src* src, const nb_pd_desc* pd, const doubl
                      const double* lrs, int R, int N, int pitch, const int* row_j0, int W,
                      const double* dlx, const double* xgrid, const double* coef, double* out,
                      void* stream);
-/* b_entry: index of the map entry holding B [G]; gm2 / g23 / out_ld as nb_synchrotron */
+/* b_entry: index of the map entry holding B [G]; gm2 / g23 / cbrtE / out_ld as nb_synchrotron */
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
                          const double* gam, int N, const double* gm2, const double* g23,
-                         const double* dlx, int W, const double* E_erg, int N_E, double* out,
-                         int out_ld, void* stream);
+                         const double* dlx, int W, const double* E_erg, const double* cbrtE,
+                         int N_E, double* out, int out_ld, void* stream);
 
 /* --- pion decay, Kelner+06 (PionDecayKelner06 radiative.py:1543-1767) ----------------
  * The reference integrates KAB06 Eq. 71 (photon energies >= Etrans) and the delta-functional

@@ -94,7 +94,7 @@ PROTOTYPES = {
     "nb_table_finalize": [vp, c_int, c_int, c_int, vp, vp, vp],
     "nb_contract": [vp, vp, c_int, c_int, c_int, c_ll, vp, vp, c_int, c_int, vp, vp, vp, vp,
                     c_int, vp],
-    "nb_synchrotron": [vp, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp, c_int, vp,
+    "nb_synchrotron": [vp, c_int, vp, vp, vp, vp, c_int, vp, vp, vp, c_int, vp, vp, c_int, vp,
                        c_int, vp],
     "nb_table_scan": [vp, c_int, c_int, c_int, vp, vp, vp],
     "nb_contract_ex": [vp, vp, c_int, c_int, c_int, vp, vp, vp, c_int, c_int, vp, vp, vp, vp,
@@ -119,7 +119,7 @@ PROTOTYPES = {
     "nb_contract_self": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), vp, vp, c_int,
                          c_int, c_int, vp, c_int, vp, vp, vp, vp, vp],
     "nb_synchrotron_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), c_int, vp,
-                             c_int, vp, vp, vp, c_int, vp, c_int, vp, c_int, vp],
+                             c_int, vp, vp, vp, c_int, vp, vp, c_int, vp, c_int, vp],
     "nb_combine_lnprob_update_push": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp,
                                       ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp,
                                       vp, vp, vp, vp, vp, c_int, vp, vp],

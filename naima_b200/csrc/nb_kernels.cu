@@ -1051,6 +1051,7 @@ struct SynArgs {
   const double* B;    // [W] (plain kernel)
   int W;
   const double* E_erg;
+  const double* cbrtE;  // cbrt(E_erg) per photon energy, or NULL (computed per lane)
   int N_E;
   double* out;
   int out_ld;         // row pitch of out (>= N_E)
@@ -1160,10 +1161,11 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
     const int len = nint - js;
     double acc = 0.0;
     if (len > 0) {
+      const double cbE = a.cbrtE ? a.cbrtE[blockIdx.y + k * nsl] : cbrt(E);
       const int m = odd_chunk2(len);
       const int i0 = js + (half * 32 + lane) * m;
       const int i1 = min(i0 + m, nint);
-      if (i0 < nint) acc = syn_lane(E, cbrt(E), s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
+      if (i0 < nint) acc = syn_lane(E, cbE, s_iec, s_cb, s_xn, s_ds, s_idl, s_dl, i0, i1);
       acc = warp_sum(acc);
     }
     if (lane == 0) s_part[2 * k + half] = acc;
@@ -1814,8 +1816,8 @@ static int syn_geometry(SynArgs& a, int N, int W, int N_E, long long* smem) {
 
 int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g23,
                    const double* xn, const double* ds1, int wpitch, const double* invdlx,
-                   const double* dlx, const double* B, int W, const double* E_erg, int N_E,
-                   double* out, int out_ld, void* stream) {
+                   const double* dlx, const double* B, int W, const double* E_erg,
+                   const double* cbrtE, int N_E, double* out, int out_ld, void* stream) {
   if (!gam || !xn || !ds1 || !invdlx || !dlx || !B || !E_erg || !out || N < 2 || wpitch < N ||
       W < 0 || N_E < 1 || (gm2 == nullptr) != (g23 == nullptr))
     return NB_EINVAL;
@@ -1824,8 +1826,8 @@ int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g2
   if (W == 0) return 0;
   SynArgs a;
   a.gam = gam; a.N = N; a.gm2 = gm2; a.g23 = g23; a.xn = xn; a.ds1 = ds1; a.wpitch = wpitch;
-  a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.N_E = N_E; a.out = out;
-  a.out_ld = out_ld;
+  a.invdlx = invdlx; a.dlx = dlx; a.B = B; a.W = W; a.E_erg = E_erg; a.cbrtE = cbrtE;
+  a.N_E = N_E; a.out = out; a.out_ld = out_ld;
   long long smem;
   int rc = syn_geometry(a, N, W, N_E, &smem);
   if (rc) return rc;
@@ -1939,8 +1941,8 @@ int nb_contract_self(const nb_walker_src* src, const nb_pd_desc* pd, const doubl
 
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
                          const double* gam, int N, const double* gm2, const double* g23,
-                         const double* dlx, int W, const double* E_erg, int N_E, double* out,
-                         int out_ld, void* stream) {
+                         const double* dlx, int W, const double* E_erg, const double* cbrtE,
+                         int N_E, double* out, int out_ld, void* stream) {
   if (!gam || !dlx || !E_erg || !out || N < 2 || W < 0 || N_E < 1 || b_entry < 0 ||
       (gm2 == nullptr) != (g23 == nullptr))
     return NB_EINVAL;
@@ -1956,8 +1958,8 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
   fa.b_entry = b_entry;
   SynArgs& a = fa.a;
   a.gam = gam; a.N = N; a.gm2 = gm2; a.g23 = g23; a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0;
-  a.invdlx = pd->invdlx; a.dlx = dlx; a.B = nullptr; a.W = W; a.E_erg = E_erg; a.N_E = N_E;
-  a.out = out; a.out_ld = out_ld;
+  a.invdlx = pd->invdlx; a.dlx = dlx; a.B = nullptr; a.W = W; a.E_erg = E_erg;
+  a.cbrtE = cbrtE; a.N_E = N_E; a.out = out; a.out_ld = out_ld;
   long long smem;
   rc = syn_geometry(a, N, W, N_E, &smem);
   if (rc) return rc;

@@ -402,14 +402,21 @@ def contract(table, prep, out=None, exact=None, coef=None):
     return out
 
 
-def synchrotron(grid, prep, B_d, E_erg_d, out=None):
-    """Synchrotron._spectrum (radiative.py:282-342): out[w][e] in 1/(s eV)."""
-    N_E = E_erg_d.numel()
+def photon_energies(E_eV):
+    """Device pair (E [erg], cbrt(E)) of photon energies for the synchrotron kernels."""
+    E_erg = np.ascontiguousarray(E_eV, dtype=float) * eV_erg
+    return to_dev(np.stack([E_erg, np.cbrt(E_erg)]))
+
+
+def synchrotron(grid, prep, B_d, E2_d, out=None):
+    """Synchrotron._spectrum (radiative.py:282-342): out[w][e] in 1/(s eV); E2_d from
+    photon_energies()."""
+    N_E = E2_d.shape[1]
     out = empty(prep.W, N_E) if out is None else out
     check(lib().nb_synchrotron(ptr(grid.x_d), grid.N, ptr(grid.gm2_d), ptr(grid.g23_d),
                                ptr(prep.xn), ptr(prep.ds1), grid.pitch, ptr(grid.invdlx_d),
-                               ptr(grid.dlx_d), ptr(B_d), prep.W, ptr(E_erg_d), N_E, ptr(out),
-                               out.stride(0), stream()), "nb_synchrotron")
+                               ptr(grid.dlx_d), ptr(B_d), prep.W, ptr(E2_d[0]), ptr(E2_d[1]),
+                               N_E, ptr(out), out.stride(0), stream()), "nb_synchrotron")
     return out
 
 

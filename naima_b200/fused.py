@@ -621,7 +621,7 @@ class LikelihoodPlan:
             ex.outs.append(out)
         # auxiliary synchrotron spectra (seed luminosities) and the self-Compton work buffers
         ex.aux_outs = [eng.zeros(W, a["E_eV"].size) for a in self.aux]
-        ex.aux_E = [eng.to_dev(a["E_eV"] * eng.eV_erg) for a in self.aux]
+        ex.aux_E = [eng.photon_energies(a["E_eV"]) for a in self.aux]
         ex.ssc = {}
         for ic, c in enumerate(self.comps):
             if c["kind"] != "ssc":
@@ -639,7 +639,7 @@ class LikelihoodPlan:
         ex.row_ld = ex.row.stride(0)
         ex.flux = ex.row[:, :self.N_E]
         ex.lnp = eng.zeros(W) if pack is None else pack[:, self.row_width]
-        ex.E_erg = eng.to_dev(self.E_eV * eng.eV_erg)
+        ex.E_erg = eng.photon_energies(self.E_eV)  # [2][N_E]: E in erg, cbrt(E)
         ex.blob_bufs = []
         for spec, (off, width) in zip(self._flat_blob_specs(), self.blob_cols):
             ex.blob_bufs.append(ex.row[:, off] if spec["kind"] == "W"
@@ -772,8 +772,9 @@ class LikelihoodPlan:
             d = ex.pd_desc[c["prep"]]
             check(L.nb_synchrotron_fused(
                 ctypes.byref(src), ctypes.byref(d), ex.scalar_entry[c["B"]], eng.ptr(g.x_d), g.N,
-                eng.ptr(g.gm2_d), eng.ptr(g.g23_d), eng.ptr(g.dlx_d), W, eng.ptr(E_erg),
-                E_erg.numel(), eng.ptr(out), out.stride(0), eng.stream()), "nb_synchrotron_fused")
+                eng.ptr(g.gm2_d), eng.ptr(g.g23_d), eng.ptr(g.dlx_d), W, eng.ptr(E_erg[0]),
+                eng.ptr(E_erg[1]), E_erg.shape[1], eng.ptr(out), out.stride(0), eng.stream()),
+                "nb_synchrotron_fused")
         else:
             eng.synchrotron(g, p, ex.scalar_col(c["B"]), E_erg, out=out)
 

@@ -600,7 +600,7 @@ class Synchrotron(BaseElectron):
         B = np.broadcast_to(np.atleast_1d(Quantity(self.B).to("G").value).astype(float), (W,))
         g = self._grid()
         pr = self._prep(g, W, need_raw=False)
-        out = eng.synchrotron(g, pr, eng.to_dev(B), eng.to_dev(E_eV * eng.eV_erg))
+        out = eng.synchrotron(g, pr, eng.to_dev(B), eng.photon_energies(E_eV))
         return [(out, 0, True, 1.0, None)], W
 
 
