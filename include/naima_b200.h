@@ -437,7 +437,7 @@ int nb_combine_lnprob_update_push(const nb_stretch* mv_host, const nb_peers* pee
                                   double* lnp, void* stream);
 
 /* --- self-contained component kernels -------------------------------------------
- * nb_contract_ex / nb_synchrotron with the walker's operands derived INSIDE the kernel from
+ * nb_synchrotron with the walker's operands derived INSIDE the kernel from
  * the raw parameters (each warp / CTA repeats the few-hundred-instruction parameter map
  * and evaluates the particle distribution at the nodes it integrates), so that a
  * likelihood evaluation needs no set-up launch in front of its components.
@@ -463,13 +463,6 @@ typedef struct nb_pd_desc {
   const double* lnx;    /* [N] */
   const double* invdlx; /* [N-1] */
 } nb_pd_desc;
-/* nb_contract_ex mode 2 (lean cell, row_j0, careful fall-back) with the operands derived in
- * the kernel; xgrid[N] is the grid itself.  The table must come from nb_table_finalize and
- * hold no negative entries. */
-int nb_contract_self(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
-                     const double* lrs, int R, int N, int pitch, const int* row_j0, int W,
-                     const double* dlx, const double* xgrid, const double* coef, double* out,
-                     void* stream);
 /* b_entry: index of the map entry holding B [G]; gm2 / g23 / cbrtE / out_ld as nb_synchrotron */
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,
                          const double* gam, int N, const double* gm2, const double* g23,

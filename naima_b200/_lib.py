@@ -116,8 +116,6 @@ PROTOTYPES = {
     "nb_combine_lnprob_ld": [ctypes.POINTER(nb_term), c_int, c_int, c_int, vp, vp, vp, vp, vp,
                              vp, vp, vp, c_int, vp, c_int, vp],
     "nb_stretch_update_packed": [ctypes.POINTER(nb_stretch), vp, c_int, vp],
-    "nb_contract_self": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), vp, vp, c_int,
-                         c_int, c_int, vp, c_int, vp, vp, vp, vp, vp],
     "nb_synchrotron_fused": [ctypes.POINTER(nb_walker_src), ctypes.POINTER(nb_pd_desc), c_int, vp,
                              c_int, vp, vp, vp, c_int, vp, vp, c_int, vp, c_int, vp],
     "nb_combine_lnprob_update_push": [ctypes.POINTER(nb_stretch), ctypes.POINTER(nb_peers), vp,

@@ -910,132 +910,6 @@ __device__ __forceinline__ void warp_walker_params(const WalkerSrc& s, int w, lo
 }
 
 // ---------------------------------------------------------------------------
-// self-contained contraction: contract_kernel<RT, 2> whose warps derive their walker's
-// operands themselves (parameter map -> log-space constants -> the particle distribution at
-// the nodes of each lane's range, evaluated on the fly next to the cells).  No set-up kernel
-// in front of it: the likelihood's critical path is one launch shorter.  The grid's
-// walker-independent tables (x, ln x, dlx, 1/dlx) are staged in shared memory beside the
-// table tile.
-// ---------------------------------------------------------------------------
-struct ContractSelfArgs {
-  ContractArgs a;  // xn / ds1 / wpitch unused
-  WalkerSrc src;
-  PdDesc pd;
-};
-
-template <int RT>
-__global__ void __launch_bounds__(256, 3) contract_self_kernel(
-    const __grid_constant__ ContractSelfArgs fa) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ PdLog s_S[8];  // per warp: the distribution's constants stay out of registers
-  const ContractArgs& a = fa.a;
-  double* sK = reinterpret_cast<double*>(smem_raw);
-  double* sL = sK + (size_t)RT * a.pitch;
-  double* sX = sL + (size_t)RT * a.pitch;  // grid tables: x, ln x, dlx, 1/dlx
-  double* sLX = sX + a.pitch;
-  double* sDL = sLX + a.pitch;
-  double* sIDL = sDL + a.pitch;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sIDL + a.pitch);
-
-  const int row0 = blockIdx.x * RT;
-  const int nrows = min(RT, a.R - row0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nint = a.N - 1;
-  int jt = 0;
-  if (a.row_j0) {
-    jt = a.N;
-    for (int r = 0; r < nrows; ++r) jt = min(jt, a.row_j0[row0 + r]);
-    jt = max(jt - 1, 0) & ~1;
-  }
-  const int wbeg = blockIdx.y * a.w_per_cta;
-  const int wend = min(wbeg + a.w_per_cta, a.W);
-  if (jt >= nint) {  // all-zero tile
-    for (int k = threadIdx.x; k < (wend - wbeg) * nrows; k += blockDim.x)
-      a.out[(size_t)(wbeg + k / nrows) * a.R + row0 + k % nrows] = 0.0;
-    return;
-  }
-  if (threadIdx.x == 0) {
-    ptx::mbarrier_init(bar, 1);
-    ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t bytes = (uint32_t)(a.pitch - jt) * 8u;
-    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, bar,
-                                   2u * bytes * (uint32_t)nrows);
-    for (int r = 0; r < nrows; ++r) {
-      const size_t off = (size_t)r * a.pitch + jt;
-      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sK + off,
-                         a.K + (size_t)row0 * a.pitch + off, bytes, bar);
-      ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, sL + off,
-                         a.lrs + (size_t)row0 * a.pitch + off, bytes, bar);
-    }
-  }
-  for (int j = jt + threadIdx.x; j < a.N; j += blockDim.x) {
-    sX[j] = a.xgrid[j];
-    sLX[j] = fa.pd.lnx[j];
-    if (j < nint) {
-      sDL[j] = a.dlx[j];
-      sIDL[j] = fa.pd.invdlx[j];
-    }
-  }
-  if (nrows < RT)
-    for (int k = threadIdx.x; k < (RT - nrows) * a.pitch; k += blockDim.x) {
-      sK[(size_t)nrows * a.pitch + k] = 0.0;
-      sL[(size_t)nrows * a.pitch + k] = NB_BIG_SLOPE;
-    }
-  if (fa.src.has_mv) wait_for_peers(fa.src.mv);  // (ends with a __syncthreads)
-  __syncthreads();
-  {
-    unsigned long long t0 = 0;
-    for (unsigned spins = 0; !ptx::mbarrier_try_wait_parity(bar, 0);) {
-      if ((++spins & 1023u) == 0u) {
-        const unsigned long long now = global_timer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > NB_WATCHDOG_NS) __trap();
-      }
-    }
-  }
-  const int m = odd_chunk(nint - jt);
-  const int i0 = jt + lane * m;
-  const int i1 = min(i0 + m, nint);
-  for (int w = wbeg + warp; w < wend; w += 8) {
-    double pp[PD_MAXPAR], unused;
-    warp_walker_params(fa.src, w, fa.pd.pd_off, -1, pp, &unused);
-    if (lane == 0) {
-      PdLog S = pd_log_setup(fa.pd.kind, pp, fa.pd.n_scale);
-      pd_log_setup_grid(S, fa.pd.e_mul1, fa.pd.e_mul2);
-      s_S[warp] = S;
-    }
-    __syncwarp();
-    double acc[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-    unsigned worst = 0u;
-    if (i0 < nint)
-      worst = contract_lane_self<RT, true>(s_S[warp], sX, sLX, sDL, sIDL, sK, sL, a.pitch, i0, i1,
-                                           acc);
-    if (__any_sync(0xffffffffu, worst >= NB_REG_RANGE)) {  // irregular slope somewhere: redo
-      if (lane == 0) atomicAdd(&g_fallbacks[0], 1ull);
-#pragma unroll
-      for (int r = 0; r < RT; ++r) acc[r] = 0.0;
-      if (i0 < nint)
-        contract_lane_self<RT, false>(s_S[warp], sX, sLX, sDL, sIDL, sK, sL, a.pitch, i0, i1, acc);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      double v = warp_sum(acc[r]);
-      if (lane == 0 && r < nrows) {
-        int row = row0 + r;
-        if (a.coef) v *= a.coef[row];
-        a.out[(size_t)w * a.R + row] = v;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // synchrotron: CTA = (walker, strided slice of photon energies)
 // ---------------------------------------------------------------------------
 struct SynArgs {
@@ -1882,61 +1756,6 @@ static int fill_pd_desc(PdDesc& d, const nb_pd_desc* pd) {
   d.lnx = pd->lnx;
   d.invdlx = pd->invdlx;
   return 0;
-}
-
-}  // extern "C"
-
-template <int RT>
-static int launch_contract_self(const ContractSelfArgs& fa, int smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(contract_self_kernel<RT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const ContractArgs& a = fa.a;
-  dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
-  contract_self_kernel<RT><<<grid, 256, smem, st>>>(fa);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" {
-
-int nb_contract_self(const nb_walker_src* src, const nb_pd_desc* pd, const double* K,
-                     const double* lrs, int R, int N, int pitch, const int* row_j0, int W,
-                     const double* dlx, const double* xgrid, const double* coef, double* out,
-                     void* stream) {
-  if (!K || !lrs || !dlx || !xgrid || !out || R < 1 || N < 2 || pitch < N || W < 0)
-    return NB_EINVAL;
-  if ((pitch & 1) || ((uintptr_t)K & 15) || ((uintptr_t)lrs & 15)) return NB_EALIGN;
-  ContractSelfArgs fa;
-  int rc = fill_walker_src(fa.src, src, W);
-  if (rc) return rc;
-  rc = fill_pd_desc(fa.pd, pd);
-  if (rc) return rc;
-  if (W == 0) return 0;
-  ContractArgs& a = fa.a;
-  a.K = K; a.lrs = lrs; a.R = R; a.N = N; a.pitch = pitch;
-  a.xn = nullptr; a.ds1 = nullptr; a.wpitch = 0; a.W = W;
-  a.dlx = dlx; a.xgrid = xgrid; a.coef = coef; a.out = out; a.row_j0 = row_j0;
-  long long row_bytes = 2LL * pitch * 8, grid_bytes = 4LL * pitch * 8;
-  int RT = 8;
-  while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
-  if (RT * row_bytes + grid_bytes + 16 > 224 * 1024) return NB_ETOOLARGE;
-  int smem = (int)(RT * row_bytes + grid_bytes + 16);
-  int resident = (int)((227LL * 1024) / (smem + 1024));
-  if (resident > 3) resident = 3;
-  if (resident < 1) resident = 1;
-  int row_tiles = (R + RT - 1) / RT;
-  int wpc = 8;
-  while (wpc < 64 && (long long)row_tiles * ((W + wpc - 1) / wpc) > 148LL * resident) wpc <<= 1;
-  a.w_per_cta = wpc;
-  cudaStream_t st = as_stream(stream);
-  if (RT == 8) return launch_contract_self<8>(fa, smem, st);
-  if (RT == 4) return launch_contract_self<4>(fa, smem, st);
-  return launch_contract_self<2>(fa, smem, st);
 }
 
 int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_entry,

@@ -982,43 +982,6 @@ NB_HD unsigned contract_lane_lean(const double* xnw, const double* dsw, const do
   return worst;
 }
 
-// Contraction with the walker's operands evaluated on the fly from the log-space distribution
-// (no set-up kernel in front, no operand arrays): xg / lnx / dlx / invdlx are the grid's
-// walker-independent tables.  The node of interval i + 1 is evaluated before the RT cells of
-// interval i, so that its exponential's dependent chain overlaps them.  LEAN: cell_lean and
-// the running classification maximum as contract_lane_lean; else the careful cell.
-template <int RT, bool LEAN>
-NB_HD unsigned contract_lane_self(const PdLog& S, const double* xg, const double* lnx,
-                                  const double* dlx, const double* invdlx, const double* sK,
-                                  const double* sL, int pitch, int i0, int i1, double* acc) {
-  double prev[RT];
-  unsigned worst = 0u;
-  PdNode nd1 = pd_log_node_tab(S, xg[i0], lnx[i0]);
-  const double n1 = xg[i0] * pd_log_value_fast(S, nd1);
-#pragma unroll
-  for (int r = 0; r < RT; ++r) prev[r] = n1 * sK[r * pitch + i0];
-  PdNode nd2 = pd_log_node_tab(S, xg[i0 + 1], lnx[i0 + 1]);
-  double n2 = xg[i0 + 1] * pd_log_value_fast(S, nd2);
-  for (int i = i0; i < i1; ++i) {
-    const double d = pd_log_ds1(S, nd1, nd2, invdlx[i]);
-    const int in = (i + 2 <= i1) ? i + 2 : i + 1;  // the last look-ahead repeats (unused)
-    const PdNode nd3 = pd_log_node_tab(S, xg[in], lnx[in]);
-    const double n3 = xg[in] * pd_log_value_fast(S, nd3);
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const double xy2 = n2 * sK[r * pitch + i + 1];
-      const double bp1 = d + sL[r * pitch + i];
-      if (LEAN) cell_lean(prev[r], xy2, bp1, acc[r], worst);
-      else acc[r] += interval_fast(prev[r], xy2, bp1, dlx[i]);
-      prev[r] = xy2;
-    }
-    nd1 = nd2;
-    nd2 = nd3;
-    n2 = n3;
-  }
-  return worst;
-}
-
 // exact contraction: reference operation order per interval (nw = n itself)
 template <int RT>
 NB_HD void contract_lane_exact(const double* nw, const double* xg, const double* sK, int pitch,

@@ -17,7 +17,6 @@ back to calling the callback with batched numpy parameters.
 """
 import ctypes
 import math
-import os
 
 import numpy as np
 import torch
@@ -494,14 +493,8 @@ class LikelihoodPlan:
         # Synchrotron derives the walker's operands itself (no set-up launch in front of it:
         # its CTAs own one walker, so the operands cost one pass over the nodes); the
         # reference-order (exact) mode keeps the operand arrays
-        # and so does the contraction where the lean cell applies (table without negative
-        # entries): its warps evaluate the distribution at the nodes of their lanes' ranges
-        # next to the cells, which takes the set-up kernel off the critical path
-        self_table = os.environ.get("NB_SELF_TABLE", "1") != "0"
         for c in self.comps:
-            c["selfprep"] = self.selfprep and not exact and self.P <= 32 and (
-                c["kind"] == "syn" or (c["kind"] == "table" and self_table and eng.LEAN
-                                       and c["table"].clean))
+            c["selfprep"] = (self.selfprep and not exact and self.P <= 32 and c["kind"] == "syn")
         for a in self.aux:
             a["selfprep"] = a["selfprep"] and self.selfprep and not exact
         # blobs
@@ -778,16 +771,6 @@ class LikelihoodPlan:
         else:
             eng.synchrotron(g, p, ex.scalar_col(c["B"]), E_erg, out=out)
 
-    def _launch_contract_self(self, ex, c, out, src):
-        tb = c["table"]
-        g = tb.grid
-        coef = c.get("coef_eff")
-        check(lib().nb_contract_self(
-            ctypes.byref(src), ctypes.byref(ex.pd_desc[c["prep"]]), eng.ptr(tb.K),
-            eng.ptr(tb.lrs), tb.R, g.N, g.pitch, eng.ptr(tb.row_j0), ex.W, eng.ptr(g.dlx_d),
-            eng.ptr(g.x_d), eng.ptr(tb.coef if coef is None else coef), eng.ptr(out),
-            eng.stream()), "nb_contract_self")
-
     def _nodes(self, ex, mv):
         """The launches of one likelihood evaluation before the combine kernel, as a DAG:
         [(name, launch function, [names it depends on])], in a valid launch order with the
@@ -823,10 +806,6 @@ class LikelihoodPlan:
                 nodes.append(("syn%d" % ic,
                               lambda c=c, out=out: self._launch_syn(ex, c, ex.E_erg, out, src),
                               [] if c["selfprep"] else ["walker_prep"]))
-            elif c["selfprep"]:
-                nodes.append(("table%d" % ic,
-                              lambda c=c, out=out: self._launch_contract_self(ex, c, out, src),
-                              []))
             else:
                 nodes.append(("table%d" % ic,
                               lambda c=c, out=out: eng.contract(c["table"], ex.preps[c["prep"]],
@@ -947,9 +926,7 @@ class LikelihoodPlan:
                 tb = c["table"]
                 kind = type(c["obj"]).__name__
                 out["table%d" % i] = {
-                    "kernel": "%s (%s, %d x %d rows)" % (
-                        "contract_self_kernel" if c["selfprep"] else "contract_kernel", kind,
-                        tb.n_comp, N_E),
+                    "kernel": "contract_kernel (%s, %d x %d rows)" % (kind, tb.n_comp, N_E),
                     "cells_per_launch": Wh * tb.R * (g.N - 1),
                     "algorithmic_bytes_per_launch":
                         8 * (2 * tb.R * g.N + 2 * Wh * g.N + g.N + tb.R + Wh * tb.R),

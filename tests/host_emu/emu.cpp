@@ -214,48 +214,6 @@ void emu_synchrotron(const double* gam, int N, const double* xn, const double* d
   free(cb);
 }
 
-// contract_self_kernel<RT=1>, one walker: operands derived on the fly from the grid's ln x
-// table (contract_lane_self), lean cell with the careful fall-back, leading zeros skipped
-void emu_contract_self(int kind, const double* p, double m1, double m2, double ns,
-                       const double* K, const double* lrs, int R, int N, int pitch,
-                       const double* x, const double* lnx, const double* dlx,
-                       const double* invdlx, double* out, int* n_fallback) {
-  PdLog S = pd_log_setup(kind, p, ns);
-  pd_log_setup_grid(S, m1, m2);
-  int nint = N - 1;
-  if (n_fallback) *n_fallback = 0;
-  for (int r = 0; r < R; ++r) {
-    const double* Kr = K + (size_t)r * pitch;
-    const double* Lr = lrs + (size_t)r * pitch;
-    int j0 = N;
-    for (int j = 0; j < N; ++j)
-      if (Kr[j] != 0.0) { j0 = j; break; }
-    int jt = (j0 - 1 > 0 ? j0 - 1 : 0) & ~1;
-    if (jt >= nint) { out[r] = 0.0; continue; }
-    int m = odd_chunk(nint - jt);
-    double part[32];
-    for (int pass = 0; pass < 2; ++pass) {
-      bool redo = false;
-      for (int lane = 0; lane < 32; ++lane) {
-        int i0 = jt + lane * m, i1 = i0 + m < nint ? i0 + m : nint;
-        double acc = 0.0;
-        unsigned worst = 0u;
-        if (i0 < nint) {
-          if (pass == 0)
-            worst = contract_lane_self<1, true>(S, x, lnx, dlx, invdlx, Kr, Lr, pitch, i0, i1, &acc);
-          else
-            contract_lane_self<1, false>(S, x, lnx, dlx, invdlx, Kr, Lr, pitch, i0, i1, &acc);
-        }
-        part[lane] = acc;
-        redo = redo || worst >= NB_REG_RANGE;
-      }
-      if (!redo) break;
-      if (n_fallback && pass == 0) ++*n_fallback;
-    }
-    out[r] = tree32(part);
-  }
-}
-
 // synchrotron_fused_kernel for one walker: node set-up from the ln x table, then the
 // same pair-of-warps integration as emu_synchrotron
 void emu_synchrotron_fused(int kind, const double* p, double m1, double m2, double ns,

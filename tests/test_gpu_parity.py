@@ -625,11 +625,10 @@ def test_priors(nb):
     assert_allclose(lnp[fin], want[fin], rtol=LNP_RTOL)
 
 
-@pytest.mark.parametrize("kinds", [(), ("syn",), ("syn", "table")],
-                         ids=["operand-arrays", "syn-selfprep", "all-selfprep"])
+@pytest.mark.parametrize("kinds", [(), ("syn",)], ids=["operand-arrays", "syn-selfprep"])
 def test_selfprep_kernels_vs_oracle(nb, kinds):
-    """nb_contract_self / nb_synchrotron_fused (operands derived inside the component
-    kernels) and their operand-array counterparts against the oracle, through the plan."""
+    """nb_synchrotron_fused (operands derived inside the kernel) and nb_synchrotron (operand
+    arrays of the set-up kernel) against the oracle, through the plan."""
     suz, hess = rxj_tables()
     data = nb.validate_data_table([suz, hess])
     rng = np.random.default_rng(11)
