@@ -280,7 +280,7 @@ def test_tablemodel_as_particle_distribution(nb):
     from naima_b200.models import (ExponentialCutoffPowerLaw, InverseCompton, PionDecay,
                                    Synchrotron, TableModel)
 
-    e = np.logspace(-4, 4, 400) * u.TeV
+    e = np.logspace(-4, 3, 400) * u.TeV  # the table ends where the cut-off has reached 1e-44
     ecpl = ExponentialCutoffPowerLaw(1e36 / u.eV, 1 * u.TeV, 2.0, 10 * u.TeV)
     tm = TableModel(e, ecpl(e), amplitude=1)
     Eph = np.logspace(-3, 1.5, 19) * u.TeV
@@ -347,7 +347,7 @@ def test_ebl_absorbed_model_traced(nb):
         assert_allclose(flux[w], m, rtol=FLUX_RTOL)
         assert_allclose(lnp[w], o.lnprobmodel(m, od), rtol=LNP_RTOL)
     got = model(np.ascontiguousarray(P.T), data).to(data["flux"].unit).value
-    assert_allclose(got, flux, rtol=1e-12)
+    assert_allclose(got, flux, rtol=1e-9)  # set-up kernel vs in-kernel operand evaluation
 
 
 def test_pion_decay_kelner06(nb, goldens):
