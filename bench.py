@@ -58,6 +58,11 @@ def parse():
     ap.add_argument("--no-check", action="store_true", help="skip the N > 1 bitwise chain check")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostic)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the public-API loop (diagnostic)")
+    ap.add_argument("--timeline", default=None, metavar="PREFIX",
+                    help="diagnostic (N > 1, implies --no-check): every rank saves its "
+                         "per-half-step device time stamps to PREFIX<rank>.npy")
+    ap.add_argument("--no-blobs", action="store_true",
+                    help="device loop without blob records (diagnostic: cost of moving them)")
     return ap.parse_args()
 
 
@@ -450,11 +455,13 @@ def run_native(args):
     # ---- N > 1: the sharded chain must equal the single-GPU chain bit for bit ---------
     check = None
     if world == 1:
-        ens = nb.DeviceEnsemble(plan, W, seed=wl.SEED)
+        ens = nb.DeviceEnsemble(plan, W, seed=wl.SEED, store_blobs=not args.no_blobs)
     else:
-        if args.no_check:
+        if args.no_check or args.timeline:
             ens = parallel.ShardedDeviceEnsemble(plan, W, seed=wl.SEED, transport=args.transport,
-                                                 multicast=multicast)
+                                                 multicast=multicast,
+                                                 store_blobs=not args.no_blobs,
+                                                 timeline=bool(args.timeline))
         else:
             check, ens = sharded_chain_check(nb, plan, wk, W, world, args.transport, multicast)
             ens._random = np.random.mtrand.RandomState(wl.SEED)
@@ -481,6 +488,10 @@ def run_native(args):
     t_wall = time.perf_counter() - t_wall0
     if world > 1:
         dist.barrier()
+    if args.timeline and world > 1:
+        tl, gen_now = ens.timeline()
+        np.save("%s%d.npy" % (args.timeline, rank), np.concatenate(
+            [tl, np.full((tl.shape[0], 1), gen_now, dtype=tl.dtype)], axis=1))
     fb_contract, fb_ssc = eng.fallback_counts()
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = _max_over_ranks(float(step_ms.sum()), world)

@@ -360,6 +360,9 @@ typedef struct nb_stretch {
   const unsigned long long* wait_gen;
   int wait_world;
   int pad2_;
+  /* optional diagnostic: [NB_TIMELINE_CAP][2] %globaltimer stamps (ns) of CTA 0 entering and
+   * leaving the wait of half-step *wait_gen; NULL in production */
+  unsigned long long* wait_timeline;
 } nb_stretch;
 int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
                         const nb_parmap* map_host, int n_map, double* pm,
@@ -397,6 +400,7 @@ int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int 
  * The ensemble state and the chain live in buffers that every rank has mapped from every
  * peer (symmetric memory).  See nb_combine_lnprob_update_push below. */
 #define NB_MAX_PEERS 16
+#define NB_TIMELINE_CAP 8192 /* half-steps kept by the diagnostic timelines (a ring) */
 typedef struct nb_peers {
   int world, rank;
   int i0;                               /* unused (reserved) */
@@ -405,7 +409,10 @@ typedef struct nb_peers {
   unsigned long long* flags[NB_MAX_PEERS]; /* peer r's flag array [world] */
   unsigned long long* gen;              /* this rank's half-step generation counter */
   int* ticket;                          /* int32 scratch, zero before the first launch */
-  double* mc_pack;                      /* unused (reserved) */
+  unsigned long long* timeline;         /* optional diagnostic: [NB_TIMELINE_CAP][4] %globaltimer
+                                           stamps (ns) of the accept kernel of half-step *gen:
+                                           entry of CTA 0, last CTA before its release, after
+                                           the flag store; NULL in production */
   /* replicated-state mode (nb_combine_lnprob_update_push): up to two symmetric arenas that
    * hold the ensemble state and the chain on every rank; a local pointer inside arena k
    * maps to arena_peer[k][r] + offset on rank r and to arena_mc[k] + offset for a

@@ -48,16 +48,18 @@ class nb_stretch(ctypes.Structure):
                 ("pars_ld", c_int), ("pad_", c_int), ("step", vp), ("sync", vp),
                 ("s_idx", vp), ("c_idx", vp), ("zz", vp), ("lnu", vp), ("n_accepted", vp),
                 ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp), ("wait_flags", vp),
-                ("wait_gen", vp), ("wait_world", c_int), ("pad2_", c_int)]
+                ("wait_gen", vp), ("wait_world", c_int), ("pad2_", c_int),
+                ("wait_timeline", vp)]
 
 
 NB_MAX_PEERS = 16
+NB_TIMELINE_CAP = 8192
 
 
 class nb_peers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("i0", c_int), ("ld", c_int),
                 ("pack", vp * NB_MAX_PEERS), ("flags", vp * NB_MAX_PEERS), ("gen", vp),
-                ("ticket", vp), ("mc_pack", vp), ("arena_local", vp * 2), ("arena_mc", vp * 2),
+                ("ticket", vp), ("timeline", vp), ("arena_local", vp * 2), ("arena_mc", vp * 2),
                 ("arena_peer", (vp * NB_MAX_PEERS) * 2), ("arena_bytes", ctypes.c_ulonglong * 2),
                 ("mc_flags", vp)]
 

@@ -56,8 +56,19 @@ def _blob_columns(sampler):
 
 
 def save_run(filename, sampler, compression=True, clobber=False):
-    """analysis.py:366-471.  ``filename`` must end in .h5/.hdf5 (real HDF5, needs h5py) or
-    .npz (same layout as flat keys)."""
+    """Save chain, log-probabilities, blobs, data table, labels and run information
+    (analysis.py:366-471).
+
+    ``.h5`` / ``.hdf5`` (needs h5py, absent from this image) or ``.npz``: the same names
+    either way -- group ``mcmc`` with datasets ``chain``, ``log_prob``, ``blob<i>`` (flattened
+    over steps x walkers, attributes ``unit`` / ``unit<j>``) and the attributes
+    ``acceptance_fraction``, ``label<i>`` and the run_info keys, as the reference writes them
+    (checked against tests/golden/save_run_layout.json, read off the reference source).
+    ONE DIFFERENCE: the reference stores the data table with astropy's ``write_table_hdf5``
+    as one compound dataset ``mcmc/data`` plus serialised meta; here it is one dataset per
+    column ``mcmc/data/<column>`` with a ``unit`` attribute.  Files are therefore read back by
+    this module's read_run only; a file whose ``mcmc/data`` is a compound dataset (written
+    by the reference) is refused with a clear error rather than misread."""
     filename = str(filename)
     ext = os.path.splitext(filename)[1]
     if ext not in (".hdf5", ".h5", ".npz"):
@@ -146,6 +157,12 @@ def read_run(filename, modelfn=None):
             f.visititems(visit)
             for k, v in f["mcmc"].attrs.items():
                 attrs["mcmc@" + k] = v
+    if "mcmc/data" in arrays:
+        raise ValueError(
+            "%s stores its data table as one compound dataset 'mcmc/data' (a file written by "
+            "the reference's save_run with astropy's write_table_hdf5); naima_b200 reads the "
+            "files of its own save_run, which keep one dataset per column under 'mcmc/data/'"
+            % filename)
     result = _result()
     result.modelfn = modelfn
     result.chain = arrays["mcmc/chain"]

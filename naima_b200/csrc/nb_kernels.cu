@@ -64,6 +64,9 @@ __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv) {
   if (mv.wait_flags == nullptr) return;
   if ((int)threadIdx.x < mv.wait_world) {
     const unsigned long long need = *mv.wait_gen;
+    const bool stamp = mv.wait_timeline && threadIdx.x == 0 && blockIdx.x == 0 &&
+                       blockIdx.y == 0;
+    if (stamp) mv.wait_timeline[2 * (need & (NB_TIMELINE_CAP - 1))] = global_timer_ns();
     unsigned long long v, t0 = 0;
     unsigned spins = 0;
     for (;;) {
@@ -78,6 +81,7 @@ __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv) {
         else if (now - t0 > NB_WATCHDOG_NS) __trap();  // a peer never arrived
       }
     }
+    if (stamp) mv.wait_timeline[2 * (need & (NB_TIMELINE_CAP - 1)) + 1] = global_timer_ns();
   }
   __syncthreads();
 }
@@ -540,6 +544,8 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
   const int t_step = ka.has_mv ? *ka.mv.step : 0;  // before anybody can increment it
+  if (ka.has_peers && ka.peers.timeline && blockIdx.x == 0 && threadIdx.x == 0)
+    ka.peers.timeline[4 * (*ka.peers.gen & (NB_TIMELINE_CAP - 1))] = global_timer_ns();
   // the accept step's operands do not depend on the model: fetch them up front so that
   // their (cold) latency overlaps the component loads
   int sidx = 0;
@@ -682,23 +688,34 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   }
   if (ka.has_peers) {
     // replicated state: the accept step above already wrote every rank's copy; the last CTA
-    // to finish raises this rank's flag on every peer
+    // to finish raises this rank's flag on every peer.  Ordering (PTX memory model, release
+    // pattern with cumulativity): each CTA's stores -> bar.sync -> fence.gpu + ticket (thread
+    // 0) -> the last CTA observes all tickets -> fence.gpu -> ONE release.sys store of the
+    // flag, which makes every store that happens-before it visible to the acquiring peer.
+    // The system-scope round trip is paid once per half-step, not once per thread and again
+    // by the last CTA.
     const nb_peers& pr = ka.peers;
     const unsigned long long epoch = *pr.gen + 1ull;
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence();
       int ticket = atomicAdd(pr.ticket, 1);
       if (ticket == (int)gridDim.x - 1) {
         *pr.ticket = 0;
-        __threadfence_system();
+        __threadfence();
+        if (pr.timeline) pr.timeline[4 * ((epoch - 1ull) & (NB_TIMELINE_CAP - 1)) + 1] = global_timer_ns();
         if (pr.mc_flags) {
           asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(pr.mc_flags + pr.rank),
                        "l"(epoch)
                        : "memory");
         } else {
-          for (int p = 0; p < pr.world; ++p) st_release_sys(pr.flags[p] + pr.rank, epoch);
+          __threadfence_system();
+          for (int p = 0; p < pr.world; ++p)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pr.flags[p] + pr.rank),
+                         "l"(epoch)
+                         : "memory");
         }
+        if (pr.timeline) pr.timeline[4 * ((epoch - 1ull) & (NB_TIMELINE_CAP - 1)) + 2] = global_timer_ns();
         *pr.gen = epoch;
       }
     }

@@ -116,8 +116,9 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
     identical to the single-GPU chain (tests/multi/check_sharded.py)."""
 
     def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
-                 use_graph=True, transport="auto", multicast=True):
+                 use_graph=True, transport="auto", multicast=True, timeline=False):
         self.multicast = multicast
+        self._want_timeline = bool(timeline)
         from . import engine as eng
 
         if seed is None:
@@ -126,7 +127,8 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             raise ValueError("transport must be 'auto', 'fused' or 'nccl'")
         self.group = group
         self.rank, self.world = world_info(group)
-        super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=True, use_graph=use_graph)
+        super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=store_blobs,
+                         use_graph=use_graph)
         self.per, self.bounds = shard_bounds(self.Ns, self.world)
         if self.per * self.world != self.Ns:
             raise ValueError("the half-ensemble (%d) must divide evenly over %d ranks"
@@ -148,7 +150,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
                               "the NCCL all-gather" % (e,))
                 for name in ("peers_fused", "_flags_local"):
                     self.__dict__.pop(name, None)
-                super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=True,
+                super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=store_blobs,
                                  use_graph=use_graph)
         if self.transport == "fused":
             self.ex = plan.executable(self.per)
@@ -202,6 +204,12 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             pr.arena_peer[0][r] = int(h_arena.buffer_ptrs[r])
             pr.flags[r] = int(h_flags.buffer_ptrs[r])
         pr.gen, pr.ticket = self.gen.data_ptr(), self.ticket.data_ptr()
+        self._timeline = None
+        if self._want_timeline:
+            from ._lib import NB_TIMELINE_CAP
+            self._timeline = (eng.zeros(NB_TIMELINE_CAP, 4, dtype=torch.int64),
+                              eng.zeros(NB_TIMELINE_CAP, 2, dtype=torch.int64))
+            pr.timeline = self._timeline[0].data_ptr()
         self.peers_fused = pr
         self._flags_local = flags
         self.uses_multicast = bool(mc)
@@ -266,7 +274,19 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             mv.wait_flags = self._flags_local.data_ptr()
             mv.wait_gen = self.gen.data_ptr()
             mv.wait_world = self.world
+            if self._timeline is not None:
+                mv.wait_timeline = self._timeline[1].data_ptr()
         return mv
+
+    def timeline(self):
+        """Diagnostic (timeline=True): per half-step %globaltimer stamps of this rank, ns --
+        columns: wait entered, wait left (first kernel of the half-step, CTA 0), accept kernel
+        entered, last CTA before its release, flag stored.  Rows follow the generation count
+        modulo NB_TIMELINE_CAP."""
+        if self._timeline is None:
+            raise RuntimeError("construct the ensemble with timeline=True")
+        a, w = (t.cpu().numpy() for t in self._timeline)
+        return np.concatenate([w, a[:, :3]], axis=1), int(self.gen.item())
 
     def set_state(self, coords, log_prob=None, rows=None):
         """Evaluate the initial ensemble sharded (unless given), then replicate."""

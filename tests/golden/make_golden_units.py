@@ -168,5 +168,46 @@ def main():
         print("%-22s %s" % (k, np.shape(v)))
 
 
+def save_run_layout():
+    """The HDF5 layout the reference's save_run writes (analysis.py:366-471), read off its
+    source: group, dataset names and attribute names.  h5py is not installable here, so the
+    npz mirror of naima_b200.analysis.save_run is checked against these names."""
+    import json
+
+    tree = _module_ast("src/naima/analysis.py")
+    (fn,) = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "save_run"]
+    groups, datasets, attrs, table_paths = [], [], [], []
+
+    def text(node):
+        if isinstance(node, ast.Constant) and isinstance(node.value, str):
+            return node.value
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) \
+                and node.func.attr == "format" and isinstance(node.func.value, ast.Constant):
+            return node.func.value.value  # "blob{0}".format(idx) -> "blob{0}"
+        return None
+
+    for node in ast.walk(fn):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+            if node.func.attr == "create_group":
+                groups.append(text(node.args[0]))
+            elif node.func.attr == "create_dataset":
+                datasets.append(text(node.args[0]))
+        if isinstance(node, ast.Call) and getattr(node.func, "id", "") == "write_table_hdf5":
+            for kw in node.keywords:
+                if kw.arg == "path":
+                    table_paths.append(text(kw.value))
+        if isinstance(node, ast.Subscript) and isinstance(node.value, ast.Attribute) \
+                and node.value.attr == "attrs" and isinstance(node.ctx, ast.Store):
+            t = text(node.slice)
+            attrs.append(t if t is not None else "<run_info key>")
+    layout = {"group": groups, "datasets": sorted(set(datasets)), "attrs": sorted(set(attrs)),
+              "table_path": table_paths,
+              "cite": "src/naima/analysis.py:366-471 (zblz/naima @ ba20a64)"}
+    with open(os.path.join(HERE, "save_run_layout.json"), "w") as f:
+        json.dump(layout, f, indent=1)
+    print(layout)
+
+
 if __name__ == "__main__":
     main()
+    save_run_layout()

@@ -87,3 +87,47 @@ def test_find_ML_and_model_samples():
     assert E.shape == (20,) and m.shape == (9, 20)
     with pytest.raises(TypeError):
         analysis.model_samples(s, u.Quantity([1.0, 2.0], "cm"))
+
+
+def test_save_run_uses_the_reference_layout_names(tmp_path):
+    """Group, dataset and attribute names of save_run against the layout read off the
+    reference's save_run source (tests/golden/save_run_layout.json, analysis.py:366-471); the
+    data table is the one documented difference."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "save_run_layout.json")) as f:
+        ref = json.load(f)
+    s = FakeSampler()
+    fn = tmp_path / "run.npz"
+    analysis.save_run(fn, s)
+    z = np.load(fn, allow_pickle=False)
+    attrs = json.loads(str(z["__attrs__"]))
+    (group,) = ref["group"]
+    names = [k for k in z.files if k != "__attrs__"]
+    assert all(k.startswith(group + "/") for k in names)
+    for ds in ref["datasets"]:
+        key = "%s/%s" % (group, ds.format(0))
+        assert key in names, key
+    # blob datasets are flattened over steps x walkers, as the reference's loop builds them
+    assert z["mcmc/blob0"].shape == (s.chain.shape[0] * s.chain.shape[1], 7)
+    assert z["mcmc/blob1"].shape == (30, 2, 4)
+    for a in ref["attrs"]:
+        if a == "<run_info key>":
+            for k in s.run_info:
+                assert "%s@%s" % (group, k) in attrs
+        elif a == "unit":
+            assert "mcmc/blob0@unit" in attrs and "mcmc/blob2@unit" in attrs
+        elif a == "unit{0}":
+            assert "mcmc/blob1@unit0" in attrs and "mcmc/blob1@unit1" in attrs
+        else:
+            assert "%s@%s" % (group, a.format(0)) in attrs, a
+    # the data table sits under <group>/<table path>/, one dataset per column
+    (tp,) = ref["table_path"]
+    assert "%s/%s/energy" % (group, tp) in names
+    # a reference-written file (compound mcmc/data) is refused, not misread
+    bad = dict(z)
+    bad["mcmc/data"] = np.zeros(3)
+    np.savez(tmp_path / "foreign.npz", **bad)
+    with pytest.raises(ValueError, match="compound dataset"):
+        analysis.read_run(tmp_path / "foreign.npz")

@@ -1,0 +1,48 @@
+"""Reads the per-rank half-step time stamps bench.py --timeline wrote and prints where a
+sharded half-step's time goes (median over the timed half-steps, microseconds).
+
+columns per row h: wait entered, wait left, accept kernel entered, last CTA before its release,
+flag stored, generation count at the end of the run."""
+import sys
+
+import numpy as np
+
+
+def main(prefix, world, last):
+    tls = [np.load("%s%d.npy" % (prefix, r)) for r in range(world)]
+    gen = int(tls[0][0, 5])
+    cap = tls[0].shape[0]
+    hs = np.arange(max(gen - last, 1), gen - 1)  # half-steps whose successor also exists
+    out = {}
+    for r, t in enumerate(tls):
+        a, b = t[hs % cap].astype(float), t[(hs + 1) % cap].astype(float)
+        seg = {
+            "wait": a[:, 1] - a[:, 0],
+            "evaluate": a[:, 2] - a[:, 1],
+            "accept": a[:, 3] - a[:, 2],
+            "release": a[:, 4] - a[:, 3],
+            "to_next_wait": b[:, 0] - a[:, 4],
+            "half_step": b[:, 0] - a[:, 0],
+        }
+        out[r] = {k: (float(np.median(v)) / 1e3, float(np.percentile(v, 90)) / 1e3)
+                  for k, v in seg.items()}
+        print("rank %d  (median / p90 us over %d half-steps)" % (r, len(hs)))
+        for k, (m, p) in out[r].items():
+            print("   %-13s %7.2f %7.2f" % (k, m, p))
+    if world == 2:
+        # one-way flag latency, clock offset removed NTP-style: the flag rank A stored at
+        # a[4] lets rank B leave its wait at b[1] >= a[4] + latency + offset(B - A)
+        A, B = tls[0], tls[1]
+        d01 = (B[(hs + 1) % cap, 1] - A[hs % cap, 4]).astype(float)
+        d10 = (A[(hs + 1) % cap, 1] - B[hs % cap, 4]).astype(float)
+        print("min over half-steps of (peer leaves wait - flag stored): 0->1 %.2f us, 1->0 %.2f us;"
+              " their mean bounds the one-way latency: %.2f us"
+              % (d01.min() / 1e3, d10.min() / 1e3, (d01.min() + d10.min()) / 2e3))
+        # who was the later rank, and by how much the earlier one waited for it
+        print("median of max(wait) over the two ranks: %.2f us"
+              % (np.median(np.maximum(A[hs % cap, 1] - A[hs % cap, 0],
+                                      B[hs % cap, 1] - B[hs % cap, 0])) / 1e3))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 300)
