@@ -58,8 +58,13 @@ def parse():
     ap.add_argument("--no-check", action="store_true", help="skip the N > 1 bitwise chain check")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostic)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the public-API loop (diagnostic)")
+    ap.add_argument("--steps-per-graph", type=int, default=1,
+                    help="diagnostic: ensemble steps captured into one CUDA graph (a timed "
+                         "'step' is then that many steps; the JSON line still reports per step)")
+    ap.add_argument("--carveout", type=int, default=None,
+                    help="diagnostic: preferred shared-memory carve-out (percent) of all kernels")
     ap.add_argument("--timeline", default=None, metavar="PREFIX",
-                    help="diagnostic (N > 1, implies --no-check): every rank saves its "
+                    help="diagnostic (implies --no-check): every rank saves its "
                          "per-half-step device time stamps to PREFIX<rank>.npy")
     ap.add_argument("--no-blobs", action="store_true",
                     help="device loop without blob records (diagnostic: cost of moving them)")
@@ -155,7 +160,10 @@ def workload_config(args, n_gpus, W):
             "walkers_per_gpu": W // n_gpus,
             "n_photon_energies": int(sum(e.size for e in wk.energies())),
             "parallelism": "walkers sharded over %d GPU(s)" % n_gpus,
-            "l2": "flushed between timed steps (%d MiB memset > 126 MB L2)" % FLUSH_MIB}
+            "l2": ("not flushed (--no-flush diagnostic)" if args.no_flush else
+                   "flushed between timed %s (%d MiB memset > 126 MB L2)"
+                   % ("steps" if args.steps_per_graph <= 1
+                      else "graphs of %d steps" % args.steps_per_graph, FLUSH_MIB))}
 
 
 def run_reference(args):
@@ -455,7 +463,8 @@ def run_native(args):
     # ---- N > 1: the sharded chain must equal the single-GPU chain bit for bit ---------
     check = None
     if world == 1:
-        ens = nb.DeviceEnsemble(plan, W, seed=wl.SEED, store_blobs=not args.no_blobs)
+        ens = nb.DeviceEnsemble(plan, W, seed=wl.SEED, store_blobs=not args.no_blobs,
+                                timeline=bool(args.timeline))
     else:
         if args.no_check or args.timeline:
             ens = parallel.ShardedDeviceEnsemble(plan, W, seed=wl.SEED, transport=args.transport,
@@ -467,6 +476,12 @@ def run_native(args):
             ens._random = np.random.mtrand.RandomState(wl.SEED)
 
     # ---- device-resident loop ---------------------------------------------------
+    spg = max(1, args.steps_per_graph)
+    if args.steps % spg or args.warmup % spg:
+        raise SystemExit("--steps and --warmup must be multiples of --steps-per-graph")
+    ens.steps_per_graph = spg
+    if args.carveout is not None:
+        eng.prefer_carveout(args.carveout)
     ens.set_state(p0)
     ens.load_draws(args.warmup + args.steps)
     ens.run_loaded(args.warmup)
@@ -475,26 +490,27 @@ def run_native(args):
         dist.barrier()
     clocks = ClockSampler(local if rank == 0 else None)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+          for _ in range(args.steps // spg)]
     eng.fallback_counts(reset=True)
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(args.steps // spg):
         flush()
         ev[k][0].record()
-        ens.run_loaded(1)
+        ens.run_loaded(spg)
         ev[k][1].record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
     if world > 1:
         dist.barrier()
-    if args.timeline and world > 1:
-        tl, gen_now = ens.timeline()
+    if args.timeline:
+        tl = ens.timeline()
         np.save("%s%d.npy" % (args.timeline, rank), np.concatenate(
-            [tl, np.full((tl.shape[0], 1), gen_now, dtype=tl.dtype)], axis=1))
+            [tl, np.full((tl.shape[0], 1), 2 * (args.warmup + args.steps), dtype=tl.dtype)],
+            axis=1))
     fb_contract, fb_ssc = eng.fallback_counts()
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = _max_over_ranks(float(step_ms.sum()), world)
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev]) / spg
+    total_ms = _max_over_ranks(float(step_ms.sum()) * spg, world)
     value = W * args.steps / (total_ms * 1e-3)
     gpu_launches = ens.kernel_launches_per_step * args.steps
     lp_final = ens.lp.cpu().numpy()

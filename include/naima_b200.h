@@ -335,6 +335,7 @@ int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const
  * `step` is read at kernel start by all kernels of a step and incremented by the last
  * CTA of the split == 1 combine kernel to finish (ticket in `sync`, an int32 scratch
  * word that must be zero before the first launch). */
+#define NB_TIMELINE_CAP 8192 /* half-steps kept by nb_stretch.timeline (a ring) */
 typedef struct nb_stretch {
   double* coords;      /* [W][P] */
   double* lp;          /* [W] */
@@ -360,9 +361,12 @@ typedef struct nb_stretch {
   const unsigned long long* wait_gen;
   int wait_world;
   int pad2_;
-  /* optional diagnostic: [NB_TIMELINE_CAP][2] %globaltimer stamps (ns) of CTA 0 entering and
-   * leaving the wait of half-step *wait_gen; NULL in production */
-  unsigned long long* wait_timeline;
+  /* optional diagnostic (NULL in production): [NB_TIMELINE_CAP][8] %globaltimer stamps (ns),
+   * row (2 * *step + split) mod NB_TIMELINE_CAP of the half-step: [0] first kernel entered
+   * (CTA 0 of nb_walker_prep_move), [1] its wait for the peers' flags is over, [2] accept
+   * kernel entered (CTA 0), [3] last CTA before it releases this rank's flag (sharded runs),
+   * [4] last CTA of the accept kernel done */
+  unsigned long long* timeline;
 } nb_stretch;
 int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
                         const nb_parmap* map_host, int n_map, double* pm,
@@ -400,7 +404,6 @@ int nb_stretch_update_packed(const nb_stretch* mv_host, const double* pack, int 
  * The ensemble state and the chain live in buffers that every rank has mapped from every
  * peer (symmetric memory).  See nb_combine_lnprob_update_push below. */
 #define NB_MAX_PEERS 16
-#define NB_TIMELINE_CAP 8192 /* half-steps kept by the diagnostic timelines (a ring) */
 typedef struct nb_peers {
   int world, rank;
   int i0;                               /* unused (reserved) */
@@ -409,10 +412,7 @@ typedef struct nb_peers {
   unsigned long long* flags[NB_MAX_PEERS]; /* peer r's flag array [world] */
   unsigned long long* gen;              /* this rank's half-step generation counter */
   int* ticket;                          /* int32 scratch, zero before the first launch */
-  unsigned long long* timeline;         /* optional diagnostic: [NB_TIMELINE_CAP][4] %globaltimer
-                                           stamps (ns) of the accept kernel of half-step *gen:
-                                           entry of CTA 0, last CTA before its release, after
-                                           the flag store; NULL in production */
+  double* mc_pack;                      /* unused (reserved) */
   /* replicated-state mode (nb_combine_lnprob_update_push): up to two symmetric arenas that
    * hold the ensemble state and the chain on every rank; a local pointer inside arena k
    * maps to arena_peer[k][r] + offset on rank r and to arena_mc[k] + offset for a
@@ -497,6 +497,10 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
  * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
 int nb_fallback_counts(unsigned long long* out_host, int reset);
+/* Preferred shared-memory carve-out (percent of the SM's L1/shared array, -1 = driver default)
+ * of every kernel a likelihood evaluation launches: with one common value the SMs never
+ * reconfigure between the kernels of a step. */
+int nb_prefer_carveout(int percent);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

@@ -49,7 +49,7 @@ class nb_stretch(ctypes.Structure):
                 ("s_idx", vp), ("c_idx", vp), ("zz", vp), ("lnu", vp), ("n_accepted", vp),
                 ("chain", vp), ("chain_lp", vp), ("chain_blobs", vp), ("wait_flags", vp),
                 ("wait_gen", vp), ("wait_world", c_int), ("pad2_", c_int),
-                ("wait_timeline", vp)]
+                ("timeline", vp)]
 
 
 NB_MAX_PEERS = 16
@@ -59,7 +59,7 @@ NB_TIMELINE_CAP = 8192
 class nb_peers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("i0", c_int), ("ld", c_int),
                 ("pack", vp * NB_MAX_PEERS), ("flags", vp * NB_MAX_PEERS), ("gen", vp),
-                ("ticket", vp), ("timeline", vp), ("arena_local", vp * 2), ("arena_mc", vp * 2),
+                ("ticket", vp), ("mc_pack", vp), ("arena_local", vp * 2), ("arena_mc", vp * 2),
                 ("arena_peer", (vp * NB_MAX_PEERS) * 2), ("arena_bytes", ctypes.c_ulonglong * 2),
                 ("mc_flags", vp)]
 
@@ -126,6 +126,7 @@ PROTOTYPES = {
     "nb_peer_wait": [ctypes.POINTER(nb_stretch), vp],
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
     "nb_fallback_counts": [ctypes.POINTER(ctypes.c_ulonglong), c_int],
+    "nb_prefer_carveout": [c_int],
     "nb_kelner_table": [vp, vp, c_int, c_int, c_dbl, vp, vp, vp],
     "nb_kelner_rows": [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp],
 }

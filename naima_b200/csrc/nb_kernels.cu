@@ -60,30 +60,36 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // Replicated ensemble state (walker sharding with peer pushes): spin until every rank's
 // flag has reached this rank's generation count, i.e. all pushes of the previous
 // half-step have landed in our copy.  Called by whole CTAs before they read coords.
-__device__ __forceinline__ void wait_for_peers(const nb_stretch& mv) {
-  if (mv.wait_flags == nullptr) return;
-  if ((int)threadIdx.x < mv.wait_world) {
-    const unsigned long long need = *mv.wait_gen;
-    const bool stamp = mv.wait_timeline && threadIdx.x == 0 && blockIdx.x == 0 &&
-                       blockIdx.y == 0;
-    if (stamp) mv.wait_timeline[2 * (need & (NB_TIMELINE_CAP - 1))] = global_timer_ns();
-    unsigned long long v, t0 = 0;
-    unsigned spins = 0;
-    for (;;) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
-                   : "=l"(v)
-                   : "l"(mv.wait_flags + threadIdx.x)
-                   : "memory");
-      if (v >= need) break;
-      if ((++spins & 1023u) == 0u) {  // look at the clock every 1024 polls
-        const unsigned long long now = global_timer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > NB_WATCHDOG_NS) __trap();  // a peer never arrived
+__device__ __forceinline__ unsigned long long* timeline_row(const nb_stretch& mv) {
+  return mv.timeline +
+         8 * ((size_t)(2 * *mv.step + mv.split) & (size_t)(NB_TIMELINE_CAP - 1));
+}
+
+__device__ __forceinline__ void wait_for_peers(const nb_stretch& mv, bool first_kernel = false) {
+  const bool stamp = first_kernel && mv.timeline && threadIdx.x == 0 && blockIdx.x == 0 &&
+                     blockIdx.y == 0;
+  if (stamp) timeline_row(mv)[0] = global_timer_ns();
+  if (mv.wait_flags != nullptr) {
+    if ((int)threadIdx.x < mv.wait_world) {
+      const unsigned long long need = *mv.wait_gen;
+      unsigned long long v, t0 = 0;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];"
+                     : "=l"(v)
+                     : "l"(mv.wait_flags + threadIdx.x)
+                     : "memory");
+        if (v >= need) break;
+        if ((++spins & 1023u) == 0u) {  // look at the clock every 1024 polls
+          const unsigned long long now = global_timer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > NB_WATCHDOG_NS) __trap();  // a peer never arrived
+        }
       }
     }
-    if (stamp) mv.wait_timeline[2 * (need & (NB_TIMELINE_CAP - 1)) + 1] = global_timer_ns();
+    __syncthreads();
   }
-  __syncthreads();
+  if (stamp) timeline_row(mv)[1] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------
@@ -544,8 +550,13 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * COMBINE_WARPS + warp;
   const int t_step = ka.has_mv ? *ka.mv.step : 0;  // before anybody can increment it
-  if (ka.has_peers && ka.peers.timeline && blockIdx.x == 0 && threadIdx.x == 0)
-    ka.peers.timeline[4 * (*ka.peers.gen & (NB_TIMELINE_CAP - 1))] = global_timer_ns();
+  // diagnostic time stamps (see nb_stretch.timeline); the row is fixed before the last CTA
+  // can advance the step counter
+  unsigned long long* tl_row = (ka.has_mv && ka.mv.timeline && threadIdx.x == 0)
+                                   ? ka.mv.timeline + 8 * ((size_t)(2 * t_step + ka.mv.split) &
+                                                           (size_t)(NB_TIMELINE_CAP - 1))
+                                   : nullptr;
+  if (tl_row && blockIdx.x == 0) tl_row[2] = global_timer_ns();
   // the accept step's operands do not depend on the model: fetch them up front so that
   // their (cold) latency overlaps the component loads
   int sidx = 0;
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
       if (ticket == (int)gridDim.x - 1) {
         *pr.ticket = 0;
         __threadfence();
-        if (pr.timeline) pr.timeline[4 * ((epoch - 1ull) & (NB_TIMELINE_CAP - 1)) + 1] = global_timer_ns();
+        if (tl_row) tl_row[3] = global_timer_ns();
         if (pr.mc_flags) {
           asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(pr.mc_flags + pr.rank),
                        "l"(epoch)
@@ -715,7 +726,6 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
                          "l"(epoch)
                          : "memory");
         }
-        if (pr.timeline) pr.timeline[4 * ((epoch - 1ull) & (NB_TIMELINE_CAP - 1)) + 2] = global_timer_ns();
         *pr.gen = epoch;
       }
     }
@@ -732,6 +742,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
       }
     }
   }
+  if (tl_row) atomicMax(&tl_row[4], global_timer_ns());
 }
 
 // ---------------------------------------------------------------------------
@@ -784,7 +795,7 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   const double* p = a.pm.pars + (size_t)w * a.pm.P;
   __shared__ double s_q[NB_MAX_MOVE_PAR];
   if (a.has_mv) {
-    wait_for_peers(a.mv);
+    wait_for_peers(a.mv, true);
     // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
     if (tid < a.pm.P) {
       const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + a.mv.i0 + w;
@@ -2180,6 +2191,28 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
   dim3 grid(R, W);
   kelner_rows_kernel<<<grid, 256, smem, as_stream(stream)>>>(kind, pd_params, Ep, Kk, R, N, out);
   NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_prefer_carveout(int percent) {
+  // one shared-memory carve-out for every kernel of a likelihood evaluation: an SM changes
+  // its L1/shared split only when idle, so kernels that prefer different splits cannot
+  // overlap on an SM and pay a drain at every kernel boundary
+  if (percent < -1 || percent > 100) return NB_EINVAL;
+  const void* fns[] = {(const void*)walker_prep_kernel,
+                       (const void*)contract_kernel<8, 0>, (const void*)contract_kernel<4, 0>,
+                       (const void*)contract_kernel<2, 0>, (const void*)contract_kernel<8, 1>,
+                       (const void*)contract_kernel<4, 1>, (const void*)contract_kernel<2, 1>,
+                       (const void*)contract_kernel<8, 2>, (const void*)contract_kernel<4, 2>,
+                       (const void*)contract_kernel<2, 2>, (const void*)synchrotron_kernel,
+                       (const void*)synchrotron_fused_kernel, (const void*)combine_lnprob_kernel,
+                       (const void*)stretch_update_packed_kernel, (const void*)ssc_seed_kernel,
+                       (const void*)ssc_inner_kernel<8>, (const void*)ssc_inner_kernel<16>,
+                       (const void*)ssc_outer_kernel, (const void*)peer_wait_kernel};
+  for (const void* f : fns) {
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
 }
 

@@ -118,7 +118,6 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
     def __init__(self, plan, nwalkers, a=2.0, seed=0, store_blobs=True, group=None,
                  use_graph=True, transport="auto", multicast=True, timeline=False):
         self.multicast = multicast
-        self._want_timeline = bool(timeline)
         from . import engine as eng
 
         if seed is None:
@@ -128,7 +127,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
         self.group = group
         self.rank, self.world = world_info(group)
         super().__init__(plan, nwalkers, a=a, seed=seed, store_blobs=store_blobs,
-                         use_graph=use_graph)
+                         use_graph=use_graph, timeline=timeline)
         self.per, self.bounds = shard_bounds(self.Ns, self.world)
         if self.per * self.world != self.Ns:
             raise ValueError("the half-ensemble (%d) must divide evenly over %d ranks"
@@ -204,12 +203,6 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             pr.arena_peer[0][r] = int(h_arena.buffer_ptrs[r])
             pr.flags[r] = int(h_flags.buffer_ptrs[r])
         pr.gen, pr.ticket = self.gen.data_ptr(), self.ticket.data_ptr()
-        self._timeline = None
-        if self._want_timeline:
-            from ._lib import NB_TIMELINE_CAP
-            self._timeline = (eng.zeros(NB_TIMELINE_CAP, 4, dtype=torch.int64),
-                              eng.zeros(NB_TIMELINE_CAP, 2, dtype=torch.int64))
-            pr.timeline = self._timeline[0].data_ptr()
         self.peers_fused = pr
         self._flags_local = flags
         self.uses_multicast = bool(mc)
@@ -274,19 +267,7 @@ class ShardedDeviceEnsemble(DeviceEnsemble):
             mv.wait_flags = self._flags_local.data_ptr()
             mv.wait_gen = self.gen.data_ptr()
             mv.wait_world = self.world
-            if self._timeline is not None:
-                mv.wait_timeline = self._timeline[1].data_ptr()
         return mv
-
-    def timeline(self):
-        """Diagnostic (timeline=True): per half-step %globaltimer stamps of this rank, ns --
-        columns: wait entered, wait left (first kernel of the half-step, CTA 0), accept kernel
-        entered, last CTA before its release, flag stored.  Rows follow the generation count
-        modulo NB_TIMELINE_CAP."""
-        if self._timeline is None:
-            raise RuntimeError("construct the ensemble with timeline=True")
-        a, w = (t.cpu().numpy() for t in self._timeline)
-        return np.concatenate([w, a[:, :3]], axis=1), int(self.gen.item())
 
     def set_state(self, coords, log_prob=None, rows=None):
         """Evaluate the initial ensemble sharded (unless given), then replicate."""

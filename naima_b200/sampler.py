@@ -369,7 +369,8 @@ class DeviceEnsemble:
 
     use_host_lib = True  # C helper for the random draws (NumPy calls when it is absent)
 
-    def __init__(self, plan, nwalkers, a=2.0, seed=None, store_blobs=True, use_graph=True):
+    def __init__(self, plan, nwalkers, a=2.0, seed=None, store_blobs=True, use_graph=True,
+                 timeline=False):
         import torch
 
         from . import engine as eng
@@ -391,10 +392,15 @@ class DeviceEnsemble:
         self.n_acc = eng.zeros(self.W, dtype=torch.int32)
         self.step = eng.zeros(1, dtype=torch.int32)
         self.sync = eng.zeros(1, dtype=torch.int32)
+        self._timeline = None
+        if timeline:  # diagnostic: device time stamps per half-step (nb_stretch.timeline)
+            from ._lib import NB_TIMELINE_CAP
+            self._timeline = eng.zeros(NB_TIMELINE_CAP, 8, dtype=torch.int64)
         self.before_step = None
         self.read_rows = True
         self.min_block = 0
         self.use_graph = use_graph
+        self.steps_per_graph = 1  # steps captured into one graph (set before the first run)
         self._graph = None
         self._block = 0
         self.kernel_launches_per_step = 2 * plan.launches_per_eval
@@ -516,7 +522,18 @@ class DeviceEnsemble:
                         ("chain_blobs", self.chain_blobs if self.nb else None)):
             setattr(mv, name, t.data_ptr() if t is not None else None)
         mv.nb, mv.W, mv.P, mv.Ns, mv.split = self.nb, self.W, self.P, self.Ns, split
+        if self._timeline is not None:
+            mv.timeline = self._timeline.data_ptr()
         return mv
+
+    def timeline(self):
+        """Diagnostic (timeline=True): %globaltimer stamps of this rank, ns, one row per
+        half-step (row (2 t + split) mod NB_TIMELINE_CAP): first kernel entered, its wait for
+        the peers over, accept kernel entered, last CTA before its release (sharded runs),
+        accept kernel done."""
+        if self._timeline is None:
+            raise RuntimeError("construct the ensemble with timeline=True")
+        return self._timeline.cpu().numpy()[:, :5]
 
     def _enqueue_step(self):
         """One ensemble step: per half, set-up (+ proposal) -> components -> combine
@@ -553,7 +570,8 @@ class DeviceEnsemble:
             from . import engine as eng
 
             with eng.capture_graph() as g:
-                self._enqueue_step()
+                for _ in range(self.steps_per_graph):
+                    self._enqueue_step()
             self._graph = g
             self.coords.copy_(c0)
             self.lp.copy_(l0)
@@ -562,13 +580,16 @@ class DeviceEnsemble:
             self.step.copy_(s0)
             torch.cuda.synchronize()
             self._sync_ranks()  # every copy is restored before anybody steps again
-        for _ in range(nsteps):
+        k = 0
+        while k < nsteps:
             if self.before_step is not None:
                 self.before_step()  # measurement hook (bench.py flushes L2 here)
-            if self._graph is not None:
+            if self._graph is not None and nsteps - k >= self.steps_per_graph:
                 self._graph.replay()
+                k += self.steps_per_graph
             else:
                 self._enqueue_step()
+                k += 1
 
     # -- pipelined execution for the host-facing sampler ------------------------------
     def begin_chunk(self, n):

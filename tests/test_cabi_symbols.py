@@ -100,7 +100,8 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         "nb_prep_job": ["kind", "N", "pd_off", "x", "invdlx", "e_mul1", "xn", "wpitch",
                         "x_to_energy", "energy_out", "energy_stride"],
         "nb_stretch": ["coords", "nb", "split", "i0", "pars_ld", "step", "sync", "s_idx",
-                       "n_accepted", "chain_blobs", "wait_flags", "wait_gen", "wait_world"],
+                       "n_accepted", "chain_blobs", "wait_flags", "wait_gen", "wait_world",
+                       "timeline"],
         "nb_peers": ["world", "rank", "i0", "ld", "pack", "flags", "gen", "ticket", "mc_pack",
                      "arena_local", "arena_mc", "arena_peer", "arena_bytes", "mc_flags"],
         "nb_walker_src": ["pars", "P", "n_map", "map_host", "mv_host"],

@@ -783,6 +783,17 @@ def test_get_sampler_run_sampler(nb):
     pars = res.get_chain(flat=True)[np.random.RandomState(2).randint(30, size=12)]
     one = ElectronIC(pars[5], {"energy": E, "flux": hess["flux"][:1]})[0]
     assert_allclose(m.value[5], one.to(m.unit).value, rtol=1e-10)
+    # ... and against the oracle: the reference evaluates sampler.modelfn(p, bogus data) per
+    # sample on the new grid (plot.py:372-391); the same with the oracle's model function
+    omodel, _ = oracle_IC()
+    E_eV = E.to("eV").value
+    od = {"E_eV": E_eV, "unit_fac": u.Quantity(1.0, "1/(s cm2 eV)").to(m.unit).value}
+    want = np.array([omodel(p_, od) for p_ in pars])
+    assert_allclose(m.value, want, rtol=1e-6)
+    # find_ML's model (plot.py:396-430 / analysis.py find_ML) is the maximum-likelihood
+    # walker's blob: the oracle on the data energies
+    od2 = oracle_data(nb.validate_data_table(hess))
+    assert_allclose(my.to(hess["flux"].unit).value, omodel(MLp, od2), rtol=1e-6)
     # continue the run; non-traceable callbacks; per-walker mode; prefit
     sampler, pos = nb.run_sampler(nrun=2, sampler=sampler, pos=pos)
     assert sampler.get_chain().shape == (2, 10, 3)

@@ -1,8 +1,8 @@
 """Reads the per-rank half-step time stamps bench.py --timeline wrote and prints where a
 sharded half-step's time goes (median over the timed half-steps, microseconds).
 
-columns per row h: wait entered, wait left, accept kernel entered, last CTA before its release,
-flag stored, generation count at the end of the run."""
+columns per row h: first kernel entered, its wait over, accept kernel entered, last CTA before
+its release (0 on one GPU), accept kernel done, number of half-steps run."""
 import sys
 
 import numpy as np
@@ -12,24 +12,28 @@ def main(prefix, world, last):
     tls = [np.load("%s%d.npy" % (prefix, r)) for r in range(world)]
     gen = int(tls[0][0, 5])
     cap = tls[0].shape[0]
-    hs = np.arange(max(gen - last, 1), gen - 1)  # half-steps whose successor also exists
+    hs = np.arange(max(gen - last, 1), gen - 1)  # rows are 2 t + split  # half-steps whose successor also exists
     out = {}
     for r, t in enumerate(tls):
         a, b = t[hs % cap].astype(float), t[(hs + 1) % cap].astype(float)
         seg = {
             "wait": a[:, 1] - a[:, 0],
             "evaluate": a[:, 2] - a[:, 1],
-            "accept": a[:, 3] - a[:, 2],
-            "release": a[:, 4] - a[:, 3],
+            "accept": a[:, 4] - a[:, 2],
+            "release": np.where(a[:, 3] > 0, a[:, 4] - a[:, 3], 0.0),
             "to_next_wait": b[:, 0] - a[:, 4],
             "half_step": b[:, 0] - a[:, 0],
         }
+        for par in (0, 1):
+            m = (hs % 2) == par
+            for k in ("evaluate", "to_next_wait", "half_step"):
+                seg["%s[split %d]" % (k, par)] = seg[k][m]
         out[r] = {k: (float(np.median(v)) / 1e3, float(np.percentile(v, 90)) / 1e3)
                   for k, v in seg.items()}
         print("rank %d  (median / p90 us over %d half-steps)" % (r, len(hs)))
         for k, (m, p) in out[r].items():
-            print("   %-13s %7.2f %7.2f" % (k, m, p))
-    if world == 2:
+            print("   %-22s %7.2f %7.2f" % (k, m, p))
+    if world == 2 and tls[0][:, 3].any():
         # one-way flag latency, clock offset removed NTP-style: the flag rank A stored at
         # a[4] lets rank B leave its wait at b[1] >= a[4] + latency + offset(B - A)
         A, B = tls[0], tls[1]
