@@ -497,31 +497,6 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
  * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
 int nb_fallback_counts(unsigned long long* out_host, int reset);
-/* --- one-launch evaluation ---------------------------------------------------------
- * Between nb_program_begin() and nb_program_launch() (same thread) the calls
- *   nb_walker_prep / nb_walker_prep_move (at most two: operands, total-energy blobs),
- *   nb_synchrotron / nb_synchrotron_fused (at most two), nb_contract_ex with mode 0 or 2 (at
- *   most eight tables), and exactly one nb_combine_lnprob* call
- * -- all on the same number of walkers W -- launch nothing: they record their arguments.
- * nb_program_launch then runs the whole evaluation as ONE kernel whose CTAs take the
- * recorded launches' CTAs as work items in ticket order (set-up first, combine last) and
- * wait on per-walker completion counters where a recorded launch followed another in stream
- * order.  Results are bit-identical to the separate launches.
- *   sched: device int32 [2 + 2 W], zero before the first launch; the kernel leaves it zero.
- *          Not to be shared by launches that may run concurrently.
- *   order: ticket order of the components after the set-up items, 0: blobs, synchrotron,
- *          tables; 1: tables, synchrotron, blobs; 2: synchrotron, tables, blobs.
- *   trace: NULL, or device uint64 [trace_len >= 4 * items]: per work item (ticket order) its
- *          %globaltimer start and end (ns), 16 * kind + index, and the SM it ran on --
- *          a measurement aid (tools/program_trace.py).
- * Any other nb_* call between begin and launch runs as usual (it is not part of the program).
- * A recording call that cannot be part of a program (exact mode, too many tables, another
- * W) returns NB_EINVAL and nb_program_launch then fails; nb_program_abort() drops a
- * recording. */
-int nb_program_begin(void);
-int nb_program_launch(int* sched, int sched_len, int order, unsigned long long* trace,
-                      long long trace_len, void* stream);
-void nb_program_abort(void);
 /* Preferred shared-memory carve-out (percent of the SM's L1/shared array, -1 = driver default)
  * of every kernel a likelihood evaluation launches: with one common value the SMs never
  * reconfigure between the kernels of a step. */

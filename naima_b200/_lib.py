@@ -127,8 +127,6 @@ PROTOTYPES = {
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
     "nb_fallback_counts": [ctypes.POINTER(ctypes.c_ulonglong), c_int],
     "nb_prefer_carveout": [c_int],
-    "nb_program_begin": [],
-    "nb_program_launch": [vp, c_int, c_int, vp, c_ll, vp],
     "nb_kelner_table": [vp, vp, c_int, c_int, c_dbl, vp, vp, vp],
     "nb_kelner_rows": [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp],
 }
@@ -150,8 +148,6 @@ def lib():
             fn.argtypes = args
             fn.restype = c_int
         L.nb_version.restype = c_int
-        L.nb_program_abort.argtypes = []
-        L.nb_program_abort.restype = None
         L.nb_strerror.restype = ctypes.c_char_p
         L.nb_strerror.argtypes = [c_int]
         _lib = L

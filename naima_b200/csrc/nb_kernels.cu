@@ -16,7 +16,6 @@
 //                             -- the replicated state written to every rank over NVLink)
 // captured with the device-resident ensemble state in one CUDA graph per ensemble step.
 // All arithmetic is IEEE fp64; no tensor cores (there is no dense contraction).
-#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -67,7 +66,8 @@ __device__ __forceinline__ unsigned long long* timeline_row(const nb_stretch& mv
 }
 
 __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv, bool first_kernel = false) {
-  const bool stamp = first_kernel && mv.timeline && threadIdx.x == 0;
+  const bool stamp = first_kernel && mv.timeline && threadIdx.x == 0 && blockIdx.x == 0 &&
+                     blockIdx.y == 0;
   if (stamp) timeline_row(mv)[0] = global_timer_ns();
   if (mv.wait_flags != nullptr) {
     if ((int)threadIdx.x < mv.wait_world) {
@@ -90,35 +90,6 @@ __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv, bool first_
     __syncthreads();
   }
   if (stamp) timeline_row(mv)[1] = global_timer_ns();
-}
-
-// In-kernel dependencies of a one-launch evaluation (halfstep_kernel below): work items are
-// handed out in ticket order, producers first, so an item only ever waits for items that
-// already run.  prep_cnt[w] counts the finished items of walker w's set-up (operand arrays,
-// published parameters), out_cnt[w] everything the combine step of walker w reads.
-struct HsDeps {
-  int* prep_cnt;
-  int* out_cnt;
-  int prep_target, out_target;
-};
-// by ONE thread, after a barrier that orders the CTA's (or warp's) stores before it
-__device__ __forceinline__ void hs_signal(int* cnt) {
-  __threadfence();
-  atomicAdd(cnt, 1);
-}
-__device__ __forceinline__ void hs_wait(const int* cnt, int target) {
-  int v;
-  unsigned long long t0 = 0;
-  unsigned spins = 0;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-    if (v >= target) break;
-    if ((++spins & 1023u) == 0u) {
-      const unsigned long long now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > NB_WATCHDOG_NS) __trap();  // a producer never finished
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -411,14 +382,14 @@ struct ContractArgs {
 
 
 template <int RT, int MODE>
-__device__ __forceinline__ void contract_body(const ContractArgs& a, const int bx, const int by,
-                                              unsigned char* smem_raw, const HsDeps* dp) {
+__global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(ContractArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool EXACT = MODE == 1;
   double* sK = reinterpret_cast<double*>(smem_raw);
   double* sL = sK + (size_t)RT * a.pitch;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sL + (EXACT ? 0 : (size_t)RT * a.pitch));
 
-  const int row0 = bx * RT;
+  const int row0 = blockIdx.x * RT;
   const int nrows = min(RT, a.R - row0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nint = a.N - 1;
@@ -430,15 +401,11 @@ __device__ __forceinline__ void contract_body(const ContractArgs& a, const int b
     for (int r = 0; r < nrows; ++r) jt = min(jt, a.row_j0[row0 + r]);
     jt = max(jt - 1, 0) & ~1;  // the interval left of the first non-zero node is zero anyway
   }
-  const int wbeg = by * a.w_per_cta;
+  const int wbeg = blockIdx.y * a.w_per_cta;
   const int wend = min(wbeg + a.w_per_cta, a.W);
   if (jt >= nint) {  // all-zero tile
     for (int k = threadIdx.x; k < (wend - wbeg) * nrows; k += blockDim.x)
       a.out[(size_t)(wbeg + k / nrows) * a.R + row0 + k % nrows] = 0.0;
-    if (dp) {
-      __syncthreads();
-      if ((int)threadIdx.x < wend - wbeg) hs_signal(&dp->out_cnt[wbeg + threadIdx.x]);
-    }
     return;
   }
 
@@ -465,11 +432,6 @@ __device__ __forceinline__ void contract_body(const ContractArgs& a, const int b
       sK[(size_t)nrows * a.pitch + k] = 0.0;
       if (!EXACT) sL[(size_t)nrows * a.pitch + k] = NB_BIG_SLOPE;
     }
-    __syncthreads();
-  }
-  if (dp) {  // the walkers' operand arrays (the tile's bulk copies are in flight meanwhile)
-    if ((int)threadIdx.x < wend - wbeg)
-      hs_wait(&dp->prep_cnt[wbeg + threadIdx.x], dp->prep_target);
     __syncthreads();
   }
   {  // a bulk copy that never completes (bad pointer, lost transaction): fail loudly
@@ -524,14 +486,7 @@ __device__ __forceinline__ void contract_body(const ContractArgs& a, const int b
         a.out[(size_t)w * a.R + row] = v;
       }
     }
-    if (dp && lane == 0) hs_signal(&dp->out_cnt[w]);  // lane 0 stored this walker's rows
   }
-}
-
-template <int RT, int MODE>
-__global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(ContractArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  contract_body<RT, MODE>(a, blockIdx.x, blockIdx.y, smem_raw, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -588,15 +543,12 @@ __device__ __forceinline__ void bcast_store(const nb_peers& pr, int* local, int 
   }
 }
 
-// WARPS walkers per CTA; cta / ncta: this CTA's index among the CTAs that combine the launch's
-// walkers (the last of them to finish raises the flags / advances the step counter)
-template <int WARPS>
-__device__ __forceinline__ void combine_body(const CombineKernelArgs& ka, const int cta,
-                                             const int ncta, unsigned char* smem_raw,
-                                             const HsDeps* dp) {
+__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
+    const __grid_constant__ CombineKernelArgs ka) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const CombineArgs& a = ka.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = cta * WARPS + warp;
+  const int w = blockIdx.x * COMBINE_WARPS + warp;
   const int t_step = ka.has_mv ? *ka.mv.step : 0;  // before anybody can increment it
   // diagnostic time stamps (see nb_stretch.timeline); the row is fixed before the last CTA
   // can advance the step counter
@@ -604,7 +556,7 @@ __device__ __forceinline__ void combine_body(const CombineKernelArgs& ka, const 
                                    ? ka.mv.timeline + 8 * ((size_t)(2 * t_step + ka.mv.split) &
                                                            (size_t)(NB_TIMELINE_CAP - 1))
                                    : nullptr;
-  if (tl_row && cta == 0) tl_row[2] = global_timer_ns();
+  if (tl_row && blockIdx.x == 0) tl_row[2] = global_timer_ns();
   // the accept step's operands do not depend on the model: fetch them up front so that
   // their (cold) latency overlaps the component loads
   int sidx = 0;
@@ -616,10 +568,6 @@ __device__ __forceinline__ void combine_body(const CombineKernelArgs& ka, const 
     mv_zz = ka.mv.zz[mv_base];
     mv_lnu = ka.mv.lnu[mv_base];
     lp_old = ka.mv.lp[sidx];
-  }
-  if (dp && w < a.W) {  // everything this walker's combine step reads has been produced
-    if (lane == 0) hs_wait(&dp->out_cnt[w], dp->out_target);
-    __syncwarp();
   }
   if (w < a.W) {
     // s_t[k]: Gaussian term of the k-th non-upper-limit point (k ascending with e)
@@ -763,7 +711,7 @@ __device__ __forceinline__ void combine_body(const CombineKernelArgs& ka, const 
     if (threadIdx.x == 0) {
       __threadfence();
       int ticket = atomicAdd(pr.ticket, 1);
-      if (ticket == ncta - 1) {
+      if (ticket == (int)gridDim.x - 1) {
         *pr.ticket = 0;
         __threadfence();
         if (tl_row) tl_row[3] = global_timer_ns();
@@ -788,23 +736,13 @@ __device__ __forceinline__ void combine_body(const CombineKernelArgs& ka, const 
     if (threadIdx.x == 0) {
       __threadfence();
       int ticket = atomicAdd(ka.mv.sync, 1);
-      if (ticket == ncta - 1) {
+      if (ticket == (int)gridDim.x - 1) {
         *ka.mv.sync = 0;
         *ka.mv.step = t_step + 1;
       }
     }
   }
-  if (dp && w < a.W && lane == 0) {  // consumed: the counters are zero again for the next launch
-    dp->out_cnt[w] = 0;
-    dp->prep_cnt[w] = 0;
-  }
   if (tl_row) atomicMax(&tl_row[4], global_timer_ns());
-}
-
-__global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
-    const __grid_constant__ CombineKernelArgs ka) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  combine_body<COMBINE_WARPS>(ka, blockIdx.x, gridDim.x, smem_raw, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -844,23 +782,20 @@ struct WalkerPrepArgs {
   double* pars_out;  // where CTA y == 0 publishes the proposals
 };
 
-constexpr int PREP_SN_BYTES = ((PREP_CHUNK + 1) * 8 + 127) & ~127;
-constexpr int PREP_FIXED_SMEM =
-    PREP_SN_BYTES + (((PREP_CHUNK + 1) * (int)sizeof(PdNode) + 127) & ~127);
-__device__ __forceinline__ void walker_prep_body(const WalkerPrepArgs& a, const int w,
-                                                 const int item, unsigned char* smem_raw) {
-  // dynamic shared memory: chunk scratch (fixed size), then the energy items' n at every node
-  double* s_n = reinterpret_cast<double*>(smem_raw);                       // [PREP_CHUNK + 1]
-  PdNode* s_nd = reinterpret_cast<PdNode*>(smem_raw + PREP_SN_BYTES);      // [PREP_CHUNK + 1]
-  double* s_node = reinterpret_cast<double*>(smem_raw + PREP_FIXED_SMEM);
+__global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant__ WalkerPrepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_node = reinterpret_cast<double*>(smem_raw);  // energy items: n at every node
   __shared__ double s_pm[NB_MAX_MAP];
+  __shared__ double s_n[PREP_CHUNK + 1];
+  __shared__ PdNode s_nd[PREP_CHUNK + 1];
   __shared__ double s_red[256];
+  const int w = blockIdx.x;
   const int tid = threadIdx.x;
-  const bool publish = item == 0;
+  const bool publish = blockIdx.y == 0;
   const double* p = a.pm.pars + (size_t)w * a.pm.P;
   __shared__ double s_q[NB_MAX_MOVE_PAR];
   if (a.has_mv) {
-    wait_for_peers(a.mv, w == 0 && item == 0);
+    wait_for_peers(a.mv, true);
     // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
     if (tid < a.pm.P) {
       const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + a.mv.i0 + w;
@@ -891,9 +826,9 @@ __device__ __forceinline__ void walker_prep_body(const WalkerPrepArgs& a, const 
       lp += prior_eval(a.pm.pri[k].kind, p[a.pm.pri[k].par], a.pm.pri[k].a, a.pm.pri[k].b);
     a.pm.prior_out[w] = lp;
   }
-  if (item >= a.n_items) return;
+  if ((int)blockIdx.y >= a.n_items) return;
   __syncthreads();
-  const PrepItem it = a.items[item];
+  const PrepItem it = a.items[blockIdx.y];
   const nb_prep_job& J = a.jobs[it.job];
   // this item's distribution parameters: lane q < 8 of warp 0 finds parameter q among the
   // mapped entries, thread 0 derives the log-space constants once for the whole CTA
@@ -934,11 +869,6 @@ __device__ __forceinline__ void walker_prep_body(const WalkerPrepArgs& a, const 
     }
     if (tid == 0) J.energy_out[(size_t)w * (J.energy_stride > 0 ? J.energy_stride : 1)] = s_red[0];
   }
-}
-
-__global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant__ WalkerPrepArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  walker_prep_body(a, blockIdx.x, blockIdx.y, smem_raw);
 }
 
 // ---------------------------------------------------------------------------
@@ -1040,11 +970,9 @@ struct SynFusedArgs {
 // FUSED: warp 0 derives the walker's parameters (proposal -> parameter map -> log-space
 // constants) and the CTA evaluates the particle distribution at the nodes itself; else the
 // operands come from nb_pd_prep's arrays.
-// w: walker; ys / nsl: this CTA's slice of the photon energies and the number of slices
 template <bool FUSED>
-__device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFusedArgs* fa,
-                                                const int w, const int ys, const int nsl,
-                                                unsigned char* smem_raw, const HsDeps* dp) {
+__device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFusedArgs* fa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   // per node: 1/Ec, cbrt(1/Ec), x*n, ds1, invdlx, dlx; per photon energy: first live node
   double* s_iec = reinterpret_cast<double*>(smem_raw);
   double* s_cb = s_iec + a.N;
@@ -1057,15 +985,13 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
   __shared__ double s_B;
   __shared__ PdLog s_S;
 
+  const int w = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nint = a.N - 1;
-  // this CTA's photon energies: e = ys + k * nsl, k < ne (strided, so that every slice gets
-  // the same mix of cheap and expensive energies)
-  const int ne = (a.N_E - ys + nsl - 1) / nsl;
-  if (!FUSED && dp) {  // operand arrays and the field strength come from the set-up items
-    if (threadIdx.x == 0) hs_wait(&dp->prep_cnt[w], dp->prep_target);
-    __syncthreads();
-  }
+  // this CTA's photon energies: e = blockIdx.y + k * gridDim.y, k < ne (strided, so that
+  // every slice gets the same mix of cheap and expensive energies)
+  const int nsl = gridDim.y;
+  const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
   if (FUSED) {
     if (fa->src.has_mv) wait_for_peers(fa->src.mv);
     if (warp == 0) {
@@ -1089,7 +1015,7 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
   // energy, the first node that can be non-zero, and only set up nodes from the
   // smallest of them on
   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[ys + k * nsl]);
+    int js = syn_first_node(a.gam, a.N, Bw, a.E_erg[blockIdx.y + k * nsl]);
     s_js[k] = js;
     atomicMin(&s_jmin, js);
   }
@@ -1132,12 +1058,12 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
   double* s_part = reinterpret_cast<double*>(s_js + a.e_per_cta + (a.e_per_cta & 1));  // [epc][2]
   const int pair = warp >> 1, half = warp & 1;
   for (int k = pair; k < ne; k += 4) {
-    const double E = a.E_erg[ys + k * nsl];
+    const double E = a.E_erg[blockIdx.y + k * nsl];
     const int js = s_js[k];
     const int len = nint - js;
     double acc = 0.0;
     if (len > 0) {
-      const double cbE = a.cbrtE ? a.cbrtE[ys + k * nsl] : cbrt(E);
+      const double cbE = a.cbrtE ? a.cbrtE[blockIdx.y + k * nsl] : cbrt(E);
       const int m = odd_chunk2(len);
       const int i0 = js + (half * 32 + lane) * m;
       const int i1 = min(i0 + m, nint);
@@ -1148,25 +1074,19 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
   }
   __syncthreads();
   for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-    const int e = ys + k * nsl;
+    const int e = blockIdx.y + k * nsl;
     const double acc = s_part[2 * k] + s_part[2 * k + 1];
     a.out[(size_t)w * a.out_ld + e] = syn_finish(Bw, a.E_erg[e], acc);
-  }
-  if (dp) {
-    __syncthreads();
-    if (threadIdx.x == 0) hs_signal(&dp->out_cnt[w]);
   }
 }
 
 __global__ void __launch_bounds__(256) synchrotron_kernel(const __grid_constant__ SynArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  synchrotron_cta<false>(a, nullptr, blockIdx.x, blockIdx.y, gridDim.y, smem_raw, nullptr);
+  synchrotron_cta<false>(a, nullptr);
 }
 
 __global__ void __launch_bounds__(256) synchrotron_fused_kernel(
     const __grid_constant__ SynFusedArgs fa) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  synchrotron_cta<true>(fa.a, &fa, blockIdx.x, blockIdx.y, gridDim.y, smem_raw, nullptr);
+  synchrotron_cta<true>(fa.a, &fa);
 }
 
 // ---------------------------------------------------------------------------
@@ -1563,157 +1483,6 @@ __global__ void trapz_loglog_kernel(const double* __restrict__ y, int R, int N, 
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
-
-// ---------------------------------------------------------------------------
-// A whole likelihood evaluation (+ stretch move + accept step) as ONE launch
-// ---------------------------------------------------------------------------
-// The launches of an evaluation -- set-up, total-energy blobs, synchrotron, one contraction per
-// emissivity table, combine -- become work items of a single grid.  A CTA draws a ticket and
-// runs the item with that number; items are numbered producers first (set-up < components <
-// combine), and an item that needs another's output spins on the per-walker counters of HsDeps,
-// so it only ever waits for items whose CTAs already run (no deadlock whatever the residency).
-// What this buys over the five-kernel graph: no kernel boundaries inside the evaluation (their
-// drain / ramp-up and the cross-branch joins of the graph cost more than the kernels' work at
-// these sizes), contraction CTAs stage their table tiles while the set-up still runs, and the
-// combine step of a walker starts the moment its last component row is stored.
-constexpr int HS_MAX_TAB = 8;
-constexpr int HS_MAX_SYN = 2;
-constexpr int HS_MAX_SEG = 16;
-#ifndef HS_CTAS_PER_SM
-#define HS_CTAS_PER_SM 4
-#endif
-constexpr int HS_MAX_PD = 4;
-constexpr int HS_COMBINE_WARPS = 8;
-enum { HS_PREP = 0, HS_SYN = 1, HS_TAB = 2, HS_COMB = 3, HS_PD = 4 };
-struct PdEvalArgs {  // a particle-distribution blob: n(e) of every walker on N energies
-  int kind, N, out_ld;
-  const double* params;
-  const double* e;
-  double* out;
-};
-struct HsSeg {
-  int kind, idx;
-  int n;   // items of this segment
-  int ny;  // items per walker (set-up, synchrotron) / row tiles (contraction)
-};
-struct HalfStepArgs {
-  HsSeg seg[HS_MAX_SEG];
-  int n_seg, n_items;
-  int* sched;  // [0] next ticket, [1] retired items; both zero between launches
-  unsigned long long* trace;  // optional [n_items][4]: start ns, end ns, kind, SM id
-  HsDeps deps;
-  int syn_fused[HS_MAX_SYN];
-  WalkerPrepArgs prep[2];
-  SynFusedArgs syn[HS_MAX_SYN];
-  ContractArgs tab[HS_MAX_TAB];
-  PdEvalArgs pdv[HS_MAX_PD];
-  CombineKernelArgs comb;
-};
-
-template <int RT, int MODE>
-__global__ void __launch_bounds__(256, HS_CTAS_PER_SM) halfstep_kernel(const __grid_constant__ HalfStepArgs h) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_ticket;
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&h.sched[0], 1);
-  __syncthreads();
-  int t = s_ticket;
-  unsigned long long* tr = (h.trace && threadIdx.x == 0) ? h.trace + 4 * (size_t)t : nullptr;
-  if (tr) tr[0] = global_timer_ns();
-  int k = 0;
-  while (k < h.n_seg - 1 && t >= h.seg[k].n) {
-    t -= h.seg[k].n;
-    ++k;
-  }
-  const int kind = h.seg[k].kind, idx = h.seg[k].idx, ny = h.seg[k].ny;
-  if (kind == HS_PREP) {
-    const int w = t / ny;
-    walker_prep_body(h.prep[idx], w, t - w * ny, smem_raw);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (idx == 0) atomicAdd(&h.deps.prep_cnt[w], 1);
-      atomicAdd(&h.deps.out_cnt[w], 1);
-    }
-  } else if (kind == HS_SYN) {
-    const int w = t / ny;
-    if (h.syn_fused[idx])
-      synchrotron_cta<true>(h.syn[idx].a, &h.syn[idx], w, t - w * ny, ny, smem_raw, &h.deps);
-    else
-      synchrotron_cta<false>(h.syn[idx].a, nullptr, w, t - w * ny, ny, smem_raw, &h.deps);
-  } else if (kind == HS_TAB) {
-    const int by = t / ny;
-    contract_body<RT, MODE>(h.tab[idx], t - by * ny, by, smem_raw, &h.deps);
-  } else if (kind == HS_PD) {
-    const int w = t / ny;
-    const PdEvalArgs& pa = h.pdv[idx];
-    if (threadIdx.x == 0) hs_wait(&h.deps.prep_cnt[w], h.deps.prep_target);  // its parameters
-    __syncthreads();
-    const int i = (t - w * ny) * 256 + threadIdx.x;
-    if (i < pa.N) {
-      double pp[PD_MAXPAR];
-#pragma unroll
-      for (int q = 0; q < PD_MAXPAR; ++q) pp[q] = pa.params[w * PD_MAXPAR + q];
-      pa.out[(size_t)w * pa.out_ld + i] = pd_eval(pa.kind, pp, pa.e[i]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) hs_signal(&h.deps.out_cnt[w]);
-  } else {
-    combine_body<HS_COMBINE_WARPS>(h.comb, t, h.seg[k].n, smem_raw, &h.deps);
-  }
-  __syncthreads();
-  if (tr) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    tr[1] = global_timer_ns();
-    tr[2] = (unsigned long long)kind * 16ull + (unsigned long long)idx;
-    tr[3] = smid;
-  }
-  if (threadIdx.x == 0) {
-    const int f = atomicAdd(&h.sched[1], 1);
-    if (f == h.n_items - 1) {  // every ticket is taken and every other CTA has retired
-      h.sched[0] = 0;
-      h.sched[1] = 0;
-    }
-  }
-}
-
-// Host side: between nb_program_begin and nb_program_launch (same thread) the launch functions
-// below record their kernel arguments instead of launching.
-struct HsRecorder {
-  int n_prep = 0, n_syn = 0, n_tab = 0, n_comb = 0, n_pd = 0;
-  PdEvalArgs pdv[HS_MAX_PD];
-  bool bad = false;
-  WalkerPrepArgs prep[2];
-  int prep_ny[2];
-  size_t prep_smem[2];
-  SynFusedArgs syn[HS_MAX_SYN];
-  int syn_fused[HS_MAX_SYN], syn_ny[HS_MAX_SYN];
-  size_t syn_smem[HS_MAX_SYN];
-  ContractArgs tab[HS_MAX_TAB];
-  int tab_mode[HS_MAX_TAB], tab_RT[HS_MAX_TAB];
-  CombineKernelArgs comb;
-  int W = -1;
-  bool walkers(int w) {
-    if (W < 0) W = w;
-    return W == w;
-  }
-};
-static thread_local HsRecorder* g_rec = nullptr;
-
-template <int RT, int MODE>
-static int launch_halfstep(const HalfStepArgs& h, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(halfstep_kernel<RT, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  halfstep_kernel<RT, MODE><<<h.n_items, 256, smem, st>>>(h);
-  NB_CHECK_LAUNCH();
-  return 0;
-}
-
 extern "C" {
 
 int nb_version(void) { return 100; }
@@ -1739,13 +1508,6 @@ int nb_pdist_eval_ld(int kind, const double* pd_params, int W, const double* e_e
       out_ld < N)
     return NB_EINVAL;
   if (W == 0 || N == 0) return 0;
-  if (g_rec) {
-    HsRecorder& r = *g_rec;
-    if (r.n_pd == HS_MAX_PD || !r.walkers(W)) { r.bad = true; return NB_EINVAL; }
-    PdEvalArgs& pa = r.pdv[r.n_pd++];
-    pa.kind = kind; pa.N = N; pa.out_ld = out_ld; pa.params = pd_params; pa.e = e_eV; pa.out = out;
-    return 0;
-  }
   dim3 grid((N + 255) / 256, W);
   pdist_eval_kernel<<<grid, 256, 0, as_stream(stream)>>>(kind, pd_params, W, e_eV, N, out,
                                                          out_ld);
@@ -1918,14 +1680,6 @@ int nb_contract_ex(const double* K, const double* lrs, int R, int N, int pitch,
   int RT = 8;
   while (RT > 2 && RT * row_bytes > 96 * 1024) RT >>= 1;
   if (RT * row_bytes + 16 > 227 * 1024) return NB_ETOOLARGE;
-  if (g_rec) {  // geometry is fixed at nb_program_launch (one row-tile height for all tables)
-    HsRecorder& r = *g_rec;
-    if (r.n_tab == HS_MAX_TAB || exact || !r.walkers(W)) { r.bad = true; return NB_EINVAL; }
-    r.tab[r.n_tab] = a;
-    r.tab_mode[r.n_tab] = mode;
-    r.tab_RT[r.n_tab++] = RT;
-    return 0;
-  }
   int smem = (int)(RT * row_bytes + 16);
   // walkers per CTA (multiple of the 8 warps): as few as keeps the whole grid resident in
   // one wave (148 SMs x CTAs that fit by shared memory, at most 3 by registers) -- a second
@@ -1979,15 +1733,6 @@ int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g2
   long long smem;
   int rc = syn_geometry(a, N, W, N_E, &smem);
   if (rc) return rc;
-  if (g_rec) {
-    HsRecorder& r = *g_rec;
-    if (r.n_syn == HS_MAX_SYN || !r.walkers(W)) { r.bad = true; return NB_EINVAL; }
-    r.syn[r.n_syn].a = a;
-    r.syn_fused[r.n_syn] = 0;
-    r.syn_ny[r.n_syn] = (N_E + a.e_per_cta - 1) / a.e_per_cta;
-    r.syn_smem[r.n_syn++] = (size_t)smem;
-    return 0;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synchrotron_kernel,
@@ -2065,15 +1810,6 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
   long long smem;
   rc = syn_geometry(a, N, W, N_E, &smem);
   if (rc) return rc;
-  if (g_rec) {
-    HsRecorder& r = *g_rec;
-    if (r.n_syn == HS_MAX_SYN || !r.walkers(W)) { r.bad = true; return NB_EINVAL; }
-    r.syn[r.n_syn] = fa;
-    r.syn_fused[r.n_syn] = 1;
-    r.syn_ny[r.n_syn] = (N_E + a.e_per_cta - 1) / a.e_per_cta;
-    r.syn_smem[r.n_syn++] = (size_t)smem;
-    return 0;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(synchrotron_fused_kernel,
@@ -2138,17 +1874,6 @@ static int launch_combine(const nb_peers* peers, const nb_stretch* mv, const dou
     if (ka.mv.pars_ld == 0) ka.mv.pars_ld = mv->P;
   }
   if (W == 0) return 0;
-  if (g_rec) {
-    HsRecorder& r = *g_rec;
-    if (r.n_comb == 1 || !r.walkers(W) ||
-        (size_t)HS_COMBINE_WARPS * N_E * sizeof(double) > 48 * 1024) {
-      r.bad = true;
-      return NB_EINVAL;
-    }
-    r.comb = ka;
-    r.n_comb = 1;
-    return 0;
-  }
   size_t smem = (size_t)COMBINE_WARPS * N_E * sizeof(double);
   if (smem > 48 * 1024) return NB_ETOOLARGE;
   combine_lnprob_kernel<<<(W + COMBINE_WARPS - 1) / COMBINE_WARPS, COMBINE_WARPS * 32, smem,
@@ -2270,20 +1995,12 @@ static int launch_walker_prep(const nb_stretch* mv, double* pars_out, const doub
     }
   }
   if (W == 0) return 0;
-  size_t smem = PREP_FIXED_SMEM + (size_t)max_energy_N * sizeof(double);
+  size_t smem = (size_t)max_energy_N * sizeof(double);
   if (smem > 200 * 1024) return NB_ETOOLARGE;
   if (smem > 32 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(walker_prep_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-  }
-  if (g_rec) {
-    HsRecorder& r = *g_rec;
-    if (r.n_prep == 2 || !r.walkers(W)) { r.bad = true; return NB_EINVAL; }
-    r.prep[r.n_prep] = a;
-    r.prep_ny[r.n_prep] = a.n_items > 0 ? a.n_items : 1;
-    r.prep_smem[r.n_prep++] = smem;
-    return 0;
   }
   dim3 grid(W, a.n_items > 0 ? a.n_items : 1);
   walker_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
@@ -2475,122 +2192,6 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
   kelner_rows_kernel<<<grid, 256, smem, as_stream(stream)>>>(kind, pd_params, Ep, Kk, R, N, out);
   NB_CHECK_LAUNCH();
   return 0;
-}
-
-int nb_program_begin(void) {
-  if (g_rec) return NB_EINVAL;  // already recording on this thread
-  g_rec = new HsRecorder();
-  return 0;
-}
-
-void nb_program_abort(void) {
-  delete g_rec;
-  g_rec = nullptr;
-}
-
-int nb_program_launch(int* sched, int sched_len, int order, unsigned long long* trace,
-                      long long trace_len, void* stream) {
-  if (!g_rec) return NB_EINVAL;
-  HsRecorder* rp = g_rec;
-  g_rec = nullptr;  // whatever happens below, the recording is over
-  struct Guard { HsRecorder* p; ~Guard() { delete p; } } guard{rp};
-  HsRecorder& r = *rp;
-  const int W = r.W;
-  if (r.bad || r.n_prep < 1 || r.n_comb != 1 || W < 1 || !sched || sched_len < 2 + 2 * W ||
-      order < 0 || order > 3)
-    return NB_EINVAL;
-  static thread_local HalfStepArgs h;  // ~13 KB: not on the stack of a ctypes call
-  h.sched = sched;
-  h.deps.prep_cnt = sched + 2;
-  h.deps.out_cnt = sched + 2 + W;
-  // one row-tile height and one cell mode for all tables of the launch
-  int RT = 8, mode = 2;
-  for (int k = 0; k < r.n_tab; ++k) {
-    if (r.tab_RT[k] < RT) RT = r.tab_RT[k];
-    if (r.tab_mode[k] != 2) mode = 0;
-  }
-  // four rows per tile: the 8-row contraction needs 80 registers and would spill under the
-  // 64 that four resident CTAs per SM allow (measured: 8 rows 0.129 ms/step, 4 rows 0.104)
-  if (RT > 4) RT = 4;
-  if (const char* cap = getenv("NB_PROGRAM_RT")) {  // measurement knob
-    const int c = atoi(cap);
-    if (c == 2 || c == 4 || c == 8) RT = c < RT || c == 8 ? c : RT;
-  }
-  size_t smem = (size_t)HS_COMBINE_WARPS * r.comb.c.N_E * sizeof(double);
-  for (int k = 0; k < r.n_prep; ++k) if (r.prep_smem[k] > smem) smem = r.prep_smem[k];
-  for (int k = 0; k < r.n_syn; ++k) if (r.syn_smem[k] > smem) smem = r.syn_smem[k];
-  int tab_nx[HS_MAX_TAB], tab_n[HS_MAX_TAB];
-  long long tiles = 0;
-  for (int k = 0; k < r.n_tab; ++k) {
-    const size_t sm = (size_t)RT * 2 * r.tab[k].pitch * 8 + 16;
-    if (sm > smem) smem = sm;
-    tab_nx[k] = (r.tab[k].R + RT - 1) / RT;
-    tiles += tab_nx[k];
-  }
-  if (smem > 200 * 1024) return NB_ETOOLARGE;
-  // walkers per contraction CTA: all tables' CTAs together about one residency of the GPU
-  // (3 CTAs per SM by registers, fewer when the tiles are large)
-  int resident = (int)((227LL * 1024) / (long long)(smem + 2048));
-  if (resident > HS_CTAS_PER_SM) resident = HS_CTAS_PER_SM;
-  if (resident < 1) resident = 1;
-  // short contraction items (few walkers per CTA) keep the tail of the launch short; more
-  // than ~4 residencies of items only re-stages the tiles more often
-  int wpc = 8;
-  while (wpc < 64 && tiles * ((W + wpc - 1) / wpc) > 4 * 148LL * resident) wpc <<= 1;
-  if (const char* cap = getenv("NB_PROGRAM_WPC")) {  // measurement knob
-    const int c = atoi(cap);
-    if (c == 8 || c == 16 || c == 32 || c == 64) wpc = c;
-  }
-  for (int k = 0; k < r.n_tab; ++k) {
-    r.tab[k].w_per_cta = wpc;
-    tab_n[k] = tab_nx[k] * ((W + wpc - 1) / wpc);
-  }
-  // ticket order: producers first
-  int ns = 0;
-  auto add = [&](int kind, int idx, int n, int ny) {
-    h.seg[ns].kind = kind; h.seg[ns].idx = idx; h.seg[ns].n = n; h.seg[ns].ny = ny;
-    ++ns;
-  };
-  auto add_syn = [&]() { for (int k = 0; k < r.n_syn; ++k) add(HS_SYN, k, W * r.syn_ny[k], r.syn_ny[k]); };
-  auto add_tab = [&]() { for (int k = 0; k < r.n_tab; ++k) add(HS_TAB, k, tab_n[k], tab_nx[k]); };
-  auto add_blob = [&]() {
-    if (r.n_prep == 2) add(HS_PREP, 1, W * r.prep_ny[1], r.prep_ny[1]);
-    for (int k = 0; k < r.n_pd; ++k) add(HS_PD, k, W * ((r.pdv[k].N + 255) / 256), (r.pdv[k].N + 255) / 256);
-  };
-  add(HS_PREP, 0, W * r.prep_ny[0], r.prep_ny[0]);
-  if (order == 0) { add_blob(); add_syn(); add_tab(); }
-  else if (order == 1) { add_tab(); add_syn(); add_blob(); }
-  else if (order == 3) { add_syn(); add_blob(); add_tab(); }
-  else { add_syn(); add_tab(); add_blob(); }
-  add(HS_COMB, 0, (W + HS_COMBINE_WARPS - 1) / HS_COMBINE_WARPS, 1);
-  h.n_seg = ns;
-  h.n_items = 0;
-  for (int k = 0; k < ns; ++k) h.n_items += h.seg[k].n;
-  if (trace && trace_len < 4LL * h.n_items) return NB_EINVAL;
-  h.trace = trace;
-  // what a walker's combine step waits for: every set-up item, every synchrotron CTA and
-  // every (table, row tile) warp of that walker
-  h.deps.prep_target = r.prep_ny[0];
-  h.deps.out_target = r.prep_ny[0] + (r.n_prep == 2 ? r.prep_ny[1] : 0);
-  for (int k = 0; k < r.n_syn; ++k) h.deps.out_target += r.syn_ny[k];
-  for (int k = 0; k < r.n_pd; ++k) {
-    h.deps.out_target += (r.pdv[k].N + 255) / 256;
-    h.pdv[k] = r.pdv[k];
-  }
-  h.deps.out_target += (int)tiles;
-  for (int k = 0; k < 2; ++k) if (k < r.n_prep) h.prep[k] = r.prep[k];
-  for (int k = 0; k < r.n_syn; ++k) { h.syn[k] = r.syn[k]; h.syn_fused[k] = r.syn_fused[k]; }
-  for (int k = 0; k < r.n_tab; ++k) h.tab[k] = r.tab[k];
-  h.comb = r.comb;
-  cudaStream_t st = as_stream(stream);
-  if (mode == 2) {
-    if (RT == 8) return launch_halfstep<8, 2>(h, smem, st);
-    if (RT == 4) return launch_halfstep<4, 2>(h, smem, st);
-    return launch_halfstep<2, 2>(h, smem, st);
-  }
-  if (RT == 8) return launch_halfstep<8, 0>(h, smem, st);
-  if (RT == 4) return launch_halfstep<4, 0>(h, smem, st);
-  return launch_halfstep<2, 0>(h, smem, st);
 }
 
 int nb_prefer_carveout(int percent) {

@@ -27,14 +27,7 @@ from ._lib import (NB_PD_MAXPAR, PD_KIND, check, lib, nb_parmap, nb_pd_desc, nb_
                    nb_walker_src)
 from .units import Quantity, Unit
 
-import os
-
 FN_ID, FN_POW10, FN_EXP = 0, 1, 2
-# One kernel per likelihood evaluation (nb_program_*) where the plan allows it; NB_ONE_LAUNCH=0
-# keeps the separate launches on graph branches (the path of plans with self-Compton, Kelner06
-# or particle-distribution blobs).  PROGRAM_ORDER: ticket order of the components.
-ONE_LAUNCH = os.environ.get("NB_ONE_LAUNCH", "1") != "0"
-PROGRAM_ORDER = int(os.environ.get("NB_PROGRAM_ORDER", "0"))
 PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_LOGUNIFORM = 0, 1, 2
 
 
@@ -849,25 +842,6 @@ class LikelihoodPlan:
         if mv is None and ex.pack is not None:
             raise ValueError("a packed executable is driven by device-side proposals only")
         nodes = self._nodes(ex, mv)
-        if self._one_launch_ok(ex):
-            # every launch of the evaluation becomes work items of ONE kernel
-            # (nb_program_*): the calls below record their arguments instead of launching
-            L = lib()
-            check(L.nb_program_begin(), "nb_program_begin")
-            try:
-                for name, fn, deps in nodes:
-                    fn()
-                self._launch_combine(ex, mv, fuse_update, peers)
-            except Exception:
-                L.nb_program_abort()
-                raise
-            tr = getattr(ex, "trace", None)  # measurement aid: tools/program_trace.py
-            check(L.nb_program_launch(eng.ptr(ex.sched), ex.sched.numel(), PROGRAM_ORDER,
-                                      eng.ptr(tr) if tr is not None else None,
-                                      tr.numel() if tr is not None else 0, eng.stream()),
-                  "nb_program_launch")
-            self.launches_per_eval = 1
-            return 1
         main = torch.cuda.current_stream()
         streams, tails = [main], [None]  # stream k, name of the last node launched on it
         where, done = {}, {}
@@ -906,24 +880,6 @@ class LikelihoodPlan:
         n = len(nodes) + self._launch_combine(ex, mv, fuse_update, peers)
         self.launches_per_eval = n
         return n
-
-    def _one_launch_ok(self, ex):
-        """True when the evaluation consists of launches a program can hold: set-up, blobs,
-        synchrotron, table contractions in the lean / careful mode, combine."""
-        if not ONE_LAUNCH or eng.EXACT or self.aux:
-            return False
-        kinds = [c["kind"] for c in self.comps]
-        if any(k not in ("syn", "table") for k in kinds):
-            return False
-        if kinds.count("syn") > 2 or kinds.count("table") > 8:
-            return False
-        if sum(spec["kind"] == "pdist" for spec in self._flat_blob_specs()) > 4:
-            return False
-        if 8 * 8 * self.N_E > 48 * 1024:
-            return False
-        if getattr(ex, "sched", None) is None:
-            ex.sched = eng.zeros(2 + 2 * ex.W, dtype=torch.int32)
-        return True
 
     def stages(self, ex):
         """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
