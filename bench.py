@@ -61,8 +61,6 @@ def parse():
     ap.add_argument("--steps-per-graph", type=int, default=1,
                     help="diagnostic: ensemble steps captured into one CUDA graph (a timed "
                          "'step' is then that many steps; the JSON line still reports per step)")
-    ap.add_argument("--carveout", type=int, default=None,
-                    help="diagnostic: preferred shared-memory carve-out (percent) of all kernels")
     ap.add_argument("--timeline", default=None, metavar="PREFIX",
                     help="diagnostic (implies --no-check): every rank saves its "
                          "per-half-step device time stamps to PREFIX<rank>.npy")
@@ -480,8 +478,6 @@ def run_native(args):
     if args.steps % spg or args.warmup % spg:
         raise SystemExit("--steps and --warmup must be multiples of --steps-per-graph")
     ens.steps_per_graph = spg
-    if args.carveout is not None:
-        eng.prefer_carveout(args.carveout)
     ens.set_state(p0)
     ens.load_draws(args.warmup + args.steps)
     ens.run_loaded(args.warmup)

@@ -497,10 +497,6 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
  * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
 int nb_fallback_counts(unsigned long long* out_host, int reset);
-/* Preferred shared-memory carve-out (percent of the SM's L1/shared array, -1 = driver default)
- * of every kernel a likelihood evaluation launches: with one common value the SMs never
- * reconfigure between the kernels of a step. */
-int nb_prefer_carveout(int percent);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

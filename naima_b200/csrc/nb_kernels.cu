@@ -2194,28 +2194,6 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
   return 0;
 }
 
-int nb_prefer_carveout(int percent) {
-  // one shared-memory carve-out for every kernel of a likelihood evaluation: an SM changes
-  // its L1/shared split only when idle, so kernels that prefer different splits cannot
-  // overlap on an SM and pay a drain at every kernel boundary
-  if (percent < -1 || percent > 100) return NB_EINVAL;
-  const void* fns[] = {(const void*)walker_prep_kernel,
-                       (const void*)contract_kernel<8, 0>, (const void*)contract_kernel<4, 0>,
-                       (const void*)contract_kernel<2, 0>, (const void*)contract_kernel<8, 1>,
-                       (const void*)contract_kernel<4, 1>, (const void*)contract_kernel<2, 1>,
-                       (const void*)contract_kernel<8, 2>, (const void*)contract_kernel<4, 2>,
-                       (const void*)contract_kernel<2, 2>, (const void*)synchrotron_kernel,
-                       (const void*)synchrotron_fused_kernel, (const void*)combine_lnprob_kernel,
-                       (const void*)stretch_update_packed_kernel, (const void*)ssc_seed_kernel,
-                       (const void*)ssc_inner_kernel<8>, (const void*)ssc_inner_kernel<16>,
-                       (const void*)ssc_outer_kernel, (const void*)peer_wait_kernel};
-  for (const void* f : fns) {
-    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    if (e != cudaSuccess) return (int)e;
-  }
-  return 0;
-}
-
 int nb_fallback_counts(unsigned long long* out_host, int reset) {
   if (!out_host) return NB_EINVAL;
   cudaError_t e = cudaMemcpyFromSymbol(out_host, g_fallbacks, sizeof(g_fallbacks));

@@ -594,12 +594,6 @@ class DeviceData:
         self.cl = to_dev(np.broadcast_to(np.asarray(cl, dtype=float), (self.N_E,)))
 
 
-def prefer_carveout(percent):
-    """One preferred shared-memory carve-out for every kernel of a likelihood evaluation
-    (nb_prefer_carveout); -1 restores the driver's per-kernel default."""
-    check(lib().nb_prefer_carveout(int(percent)), "nb_prefer_carveout")
-
-
 def fallback_counts(reset=False):
     """(contraction (walker, row tile) pairs, self-Compton rows) that the lean cell handed to
     the careful cell since the last reset."""
