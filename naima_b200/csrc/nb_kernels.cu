@@ -46,6 +46,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// RT sums at once: on return lane (32 / RT) * r holds the sum over the 32 lanes of acc[r], with
+// the pairing tree of warp_sum (offsets 16, 8, 4, 2, 1), hence bit-identical to it.  While more
+// than one row is left, the two halves of every lane pair split the rows between them (each
+// keeps half and hands the other half over), so the tree costs RT - 1 + log2(32 / RT) shuffles
+// instead of 5 RT: 9 instead of 40 for eight rows.
+template <int RT>
+__device__ __forceinline__ double warp_sum_rows(double (&acc)[RT], const int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = RT; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int r = 0; r < n / 2; ++r) {
+      const double send = upper ? acc[r] : acc[r + n / 2];
+      const double keep = upper ? acc[r + n / 2] : acc[r];
+      acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  double v = acc[0];
+  for (; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
 // Spin loops on flags that another GPU (or a bulk copy) raises carry a watchdog: after
 // NB_WATCHDOG_NS of waiting the kernel traps -- a dead peer then surfaces as a CUDA error on
 // this rank instead of hanging every GPU of the job.
@@ -477,11 +500,11 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(Contra
         contract_lane_fast<RT, 1>(xnw, a.ds1 + (size_t)w * a.wpitch, a.dlx, sK, sL, a.pitch, i0,
                                   i1, acc);
     }
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      double v = warp_sum(acc[r]);
-      if (lane == 0 && r < nrows) {
-        int row = row0 + r;
+    {  // lane (32 / RT) * r ends up with row r's sum
+      double v = warp_sum_rows<RT>(acc, lane);
+      const int r = lane / (32 / RT);
+      if ((lane & (32 / RT - 1)) == 0 && r < nrows) {
+        const int row = row0 + r;
         if (a.coef) v *= a.coef[row];
         a.out[(size_t)w * a.R + row] = v;
       }

@@ -77,6 +77,14 @@ if hi:
             op = s[1] if s[0].startswith("@") else s[0]
             mix[op] += int(r[ix])
 tot = sum(mix.values()) or 1
+# executed fp64 arithmetic of the first launch from the per-instruction counts of the source
+# page (warp-level counts of DFMA / DADD / DMUL x 32 lanes; an upper bound where lanes are
+# predicated off) -- used when this ncu has no sass_thread_inst_executed_op_d* metrics
+fp64_warp = sum(v for k, v in mix.items() if k.split(".")[0] in ("DFMA", "DADD", "DMUL"))
+for rec in summ:
+    if not rec.get("fp64_thread_insts") and fp64_warp:
+        rec["fp64_thread_insts"] = 32.0 * fp64_warp
+        rec["fp64_thread_insts_source"] = "source page of the first launch: 32 x (DFMA + DADD + DMUL)"
 cells = float(sys.argv[3]) if len(sys.argv) > 3 else None  # algorithmic cells per launch
 json.dump({"report": rep, "launches": summ, "cells_per_launch": cells,
            "opcode_mix_first_launch": {k: v for k, v in mix.most_common(16)}},
