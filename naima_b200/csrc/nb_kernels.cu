@@ -1254,7 +1254,7 @@ struct SscInnerArgs {
 // memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell.  The row's
 // table entries stream from L2 two intervals ahead of their use.
 template <int WT>
-__global__ void __launch_bounds__(128, WT >= 16 ? 4 : 6) ssc_inner_kernel(
+__global__ void __launch_bounds__(128, 6) ssc_inner_kernel(
     const __grid_constant__ SscInnerArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_op = reinterpret_cast<double2*>(smem_raw);           // [Ns][WT]
@@ -2143,16 +2143,11 @@ int nb_ssc_inner(const double* KL, const double* F0, const double* coef, long lo
   SscInnerArgs a;
   a.KL = reinterpret_cast<const double2*>(KL); a.F0 = F0; a.coef = coef; a.Rp = Rp; a.Ns = Ns;
   a.sxn = sxn; a.sds = sds; a.spitch = spitch; a.W = W; a.dlx_s = dlx_s; a.inner = inner;
-  // walkers per thread: 8 (6 CTAs = 24 warps per SM; measured 1.4x faster than 16 walkers per
-  // thread at 4 CTAs per SM although it loads the table twice as often: the kernel is bound
-  // by fp64 dependency latency, and more resident warps hide it).  NB_SSC_WT=16 in the
-  // environment selects the other blocking for comparison.
-  static int wt = 0;
-  if (wt == 0) {
-    const char* e = getenv("NB_SSC_WT");
-    wt = (e && atoi(e) == 16) ? 16 : 8;
-  }
-  return wt == 8 ? launch_ssc_inner<8>(a, as_stream(stream)) : launch_ssc_inner<16>(a, as_stream(stream));
+  // eight walkers per thread, 6 CTAs = 24 warps per SM.  Sixteen walkers per thread (4 CTAs per
+  // SM, half the table traffic) measured the same: 820.9 against 809.7 us per launch at C4,
+  // fp64 pipe 57 % against 58 % (profiles/r02_ncu_c4_ssc_inner_wt16.md) -- the kernel is bound
+  // by the fp64 dependency chains of the lean cell, not by the table stream.
+  return launch_ssc_inner<8>(a, as_stream(stream));
 }
 
 int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const double* xn,

@@ -99,7 +99,6 @@ if __name__ == "__main__":
     ncu("ev_c3_combine_lnprob_kernel.ncu-rep", "ncu_c3_combine_lnprob_kernel", 128 * 64)
     # C4: 128 walkers x (100 x 869) rows x 99 seed intervals
     ncu("ev_c4_ssc_inner_wt8.ncu-rep", "ncu_c4_ssc_inner_kernel", 128 * 100 * 869 * 99)
-    ncu("ev_c4_ssc_inner_wt16.ncu-rep", "r02_ncu_c4_ssc_inner_wt16", 128 * 100 * 869 * 99)
     ncu("ev_c4_ssc_rest.ncu-rep", "r02_ncu_c4_ssc_outer_seed", 128 * 100 * 868)
     if os.path.exists(os.path.join(G, "ev_pytest.log")):
         shutil.copy(os.path.join(G, "ev_pytest.log"), os.path.join(P, "r02_pytest_gpu.txt"))

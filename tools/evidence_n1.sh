@@ -7,7 +7,6 @@ python bench.py > gpurun_out/ev_bench_C3.json 2> gpurun_out/ev_bench_C3.err
 for c in C1 C2 C4 C5; do python bench.py --config $c > gpurun_out/ev_bench_$c.json 2> gpurun_out/ev_bench_$c.err; done
 for w in 1024 4096; do python bench.py --walkers-per-gpu $w --no-cpu-baseline > gpurun_out/ev_bench_C3_w$w.json 2> gpurun_out/ev_bench_C3_w$w.err; done
 python bench.py --steps-per-graph 4 --steps 200 --warmup 12 --no-cpu-baseline --no-e2e > gpurun_out/ev_bench_C3_spg4.json 2>/dev/null
-NB_SSC_WT=16 python bench.py --config C4 --no-cpu-baseline --no-e2e > gpurun_out/ev_bench_C4_wt16.json 2>/dev/null
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/ev_bench_C3_reference.json 2>/dev/null
 NQ="--steps 4 --warmup 3 --no-cpu-baseline --no-e2e"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/ev_launches_c3.csv python bench.py $NQ > /dev/null 2>&1
@@ -16,7 +15,6 @@ for k in contract_kernel synchrotron_fused_kernel walker_prep_kernel combine_lnp
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 8 -c 2 -o gpurun_out/ev_c3_$k python bench.py $NQ > gpurun_out/ev_ncu_c3_$k.log 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:ssc_inner --launch-skip 4 -c 1 -o gpurun_out/ev_c4_ssc_inner_wt8 python bench.py --config C4 $NQ > gpurun_out/ev_ncu_c4_wt8.log 2>&1
-NB_SSC_WT=16 ncu --set full --clock-control none --import-source on -k regex:ssc_inner --launch-skip 4 -c 1 -o gpurun_out/ev_c4_ssc_inner_wt16 python bench.py --config C4 $NQ > gpurun_out/ev_ncu_c4_wt16.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"ssc_outer|ssc_seed" --launch-skip 8 -c 2 -o gpurun_out/ev_c4_ssc_rest python bench.py --config C4 $NQ > gpurun_out/ev_ncu_c4_rest.log 2>&1
 ls -la gpurun_out/ev_* | awk '{print $5, $9}'
 for f in gpurun_out/ev_bench_*.json; do python - "$f" <<'PY'

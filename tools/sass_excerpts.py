@@ -13,7 +13,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "naima_b200", "libnaima_b200.so")
 WANT = ["contract_kernelILi8ELi2", "contract_kernelILi8ELi0", "synchrotron_fused_kernel",
-        "walker_prep_kernel", "combine_lnprob_kernel", "ssc_inner_kernelILi8", "ssc_inner_kernelILi16",
+        "walker_prep_kernel", "combine_lnprob_kernel", "ssc_inner_kernelILi8",
         "ssc_outer_kernel"]
 PROOF = ["UBLKCP", "SYNCS", "MUFU.RCP64H", "MUFU.RSQ64H", "DFMA", "DMUL", "DADD", "DSETP", "LDS",
          "LDG", "STG", "STG.E.64.STRONG.SYS", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "REDG", "ATOMG", "MEMBAR", "LDL", "STL", "BAR.SYNC",
