@@ -125,3 +125,22 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         assert ctypes.sizeof(cls) == got[name], name
         for f in fields:
             assert getattr(cls, f).offset == got["%s.%s" % (name, f)], (name, f)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under naima_b200/ may import, load or execute it
+    (the product has no CPU path)."""
+    import re
+
+    pkg = os.path.join(ROOT, "naima_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                continue
+            with open(os.path.join(dirpath, fn)) as f:
+                for k, line in enumerate(f, 1):
+                    if re.search(r"^\s*(from|import)\s+oracle\b|oracle[/.]naima_oracle|oracle/_ref",
+                                 line):
+                        bad.append("%s:%d %s" % (fn, k, line.strip()))
+    assert not bad, bad
