@@ -24,14 +24,17 @@ def last_json(path):
 
 def bench_lines():
     for fn in sorted(os.listdir(G)):
-        if fn.startswith("ev_bench_") and fn.endswith(".json"):
+        if fn.startswith(("ev_bench_", "ev8_bench_")) and fn.endswith(".json"):
             try:
                 d = last_json(os.path.join(G, fn))
             except Exception as e:  # noqa: BLE001
                 print("skip", fn, e)
                 continue
-            tag = fn[len("ev_bench_"):-5]
-            out = "r02_bench_%s_n%d.json" % (tag, d.get("n_gpus", 1))
+            tag = fn.split("_bench_", 1)[1][:-5]
+            n = d.get("n_gpus", 1)
+            if tag.endswith("_n%d" % n):
+                tag = tag[:-len("_n%d" % n)]
+            out = "r02_bench_%s_n%d.json" % (tag, n)
             with open(os.path.join(P, out), "w") as f:
                 json.dump(d, f, indent=1)
             print(out, d.get("ms_per_step"), d.get("value"))
@@ -100,5 +103,7 @@ if __name__ == "__main__":
     # C4: 128 walkers x (100 x 869) rows x 99 seed intervals
     ncu("ev_c4_ssc_inner_wt8.ncu-rep", "ncu_c4_ssc_inner_kernel", 128 * 100 * 869 * 99)
     ncu("ev_c4_ssc_rest.ncu-rep", "r02_ncu_c4_ssc_outer_seed", 128 * 100 * 868)
+    if os.path.exists(os.path.join(G, "ev8_pytest_multi.log")):
+        shutil.copy(os.path.join(G, "ev8_pytest_multi.log"), os.path.join(P, "r02_pytest_multi_gpu.txt"))
     if os.path.exists(os.path.join(G, "ev_pytest.log")):
         shutil.copy(os.path.join(G, "ev_pytest.log"), os.path.join(P, "r02_pytest_gpu.txt"))
