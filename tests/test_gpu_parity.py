@@ -716,8 +716,10 @@ def test_sampler_chain_parity(nb):
     assert_allclose(dchain2, s.get_chain()[nsteps:], rtol=1e-13)
     # the public-API sampler over the device loop (what get_sampler builds): same chain,
     # same blobs, same acceptance counts, for block sizes that do / do not divide nsteps
-    for block in (4, 16):
-        ps = nb.PlanSampler(W, P, plan, seed=seed, block=block, chunk=5)
+    # ... and for several steps per CUDA graph (steps that do not fill a graph are launched
+    # kernel by kernel)
+    for block, spg in ((4, 1), (16, 1), (8, 4), (6, 4)):
+        ps = nb.PlanSampler(W, P, plan, seed=seed, block=block, chunk=5, steps_per_graph=spg)
         st = ps.run_mcmc(p0, nsteps)
         assert_allclose(ps.get_chain(), s.get_chain()[:nsteps], rtol=1e-13)
         assert_allclose(ps.get_log_prob(), s.get_log_prob()[:nsteps], rtol=1e-13)
