@@ -883,7 +883,7 @@ class LikelihoodPlan:
 
     def stages(self, ex):
         """[(name, launch)] of one evaluation on ex.pars, in launch order on the current
-        stream (no forking): measurement aid for bench.py / tools/timeline.py."""
+        stream (no forking): measurement aid for bench.py."""
         nodes = self._nodes(ex, None)
         # the DAG order may put a selfprep root first; any topological order is valid here
         out, seen = [], set()
