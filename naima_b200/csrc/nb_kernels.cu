@@ -1253,12 +1253,26 @@ struct SscInnerArgs {
 // thread = one (e, g) row, WT walkers in registers; the walkers' seed operands sit in shared
 // memory as (x*y at s+1, slope at s) pairs: one 128-bit broadcast load per cell.  The row's
 // table entries stream from L2 two intervals ahead of their use.
+constexpr int SSC_STAGES = 8;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int WT>
 __global__ void __launch_bounds__(128, 6) ssc_inner_kernel(
     const __grid_constant__ SscInnerArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* s_op = reinterpret_cast<double2*>(smem_raw);           // [Ns][WT]
-  double* s_x0 = reinterpret_cast<double*>(s_op + (size_t)WT * a.Ns);  // [WT]
+  double2* s_ring = s_op + (size_t)WT * a.Ns;                     // [SSC_STAGES][128]
+  double* s_x0 = reinterpret_cast<double*>(s_ring + SSC_STAGES * 128);  // [WT]
   const int w0 = blockIdx.x * WT;
   const int Ns = a.Ns;
   for (int k = threadIdx.x; k < WT * Ns; k += blockDim.x) {
@@ -1283,13 +1297,29 @@ __global__ void __launch_bounds__(128, 6) ssc_inner_kernel(
     prev[w] = s_x0[w] * k1;
   }
   const int nint = Ns - 1;
-  double2 kla = KLc[0], klb = KLc[(nint > 1 ? 1 : 0) * a.Rp];
+  // The row's table entries reach the thread through a ring of SSC_STAGES 16-byte slots of its
+  // own in shared memory, filled by cp.async SSC_STAGES - 1 intervals ahead: no registers are
+  // tied up by loads in flight and the L2 latency of the stream is off the dependency chain
+  // (held in registers two intervals ahead, the loads were the kernel's first stall reason).
+  // Every thread reads only the slots it wrote itself: cp.async.wait_group is all the
+  // synchronisation needed.
+  double2* ring = s_ring + threadIdx.x;  // slot of stage g: ring[g * 128]
+#pragma unroll
+  for (int g = 0; g < SSC_STAGES - 1; ++g) {
+    if (g < nint) cp_async16(ring + g * 128, KLc + (long long)g * a.Rp);
+    cp_async_commit();
+  }
   const double2* op_s = s_op;
-#pragma unroll 2
-  for (int s = 0; s < nint; ++s, op_s += WT) {
-    const int sp = (s + 2 < nint) ? s + 2 : nint - 1;  // the last prefetches repeat (unused)
-    const double2 kln = KLc[(long long)sp * a.Rp];
-    const double k2 = kla.x, l = kla.y;
+  const double2* src = KLc + (long long)(SSC_STAGES - 1) * a.Rp;  // next entry to fetch
+  // one interval: wait for its slot, refill the slot of the previous interval, WT cells
+  auto interval = [&](const int s, const int slot) {
+    cp_async_wait<SSC_STAGES - 2>();  // the group of interval s has landed
+    const double2 kl = ring[slot * 128];
+    if (s + SSC_STAGES - 1 < nint)
+      cp_async16(ring + ((slot + SSC_STAGES - 1) % SSC_STAGES) * 128, src);
+    cp_async_commit();
+    src += a.Rp;
+    const double k2 = kl.x, l = kl.y;
 #pragma unroll
     for (int w = 0; w < WT; ++w) {
       const double2 op = op_s[w];
@@ -1297,9 +1327,14 @@ __global__ void __launch_bounds__(128, 6) ssc_inner_kernel(
       cell_lean(prev[w], xy2, op.y + l, acc[w], worst);
       prev[w] = xy2;
     }
-    kla = klb;
-    klb = kln;
+    op_s += WT;
+  };
+  int s = 0;
+  for (; s + SSC_STAGES <= nint; s += SSC_STAGES) {  // slot numbers are compile-time constants
+#pragma unroll
+    for (int g = 0; g < SSC_STAGES; ++g) interval(s + g, g);
   }
+  for (int g = 0; s < nint; ++s, ++g) interval(s, g);  // fewer than SSC_STAGES left
   const double cf = a.coef[r];
   if (worst >= NB_REG_RANGE) {
     // an irregular slope somewhere on this row (sign change in the table, |b+1| <= 1e-10,
@@ -2113,7 +2148,8 @@ int nb_ssc_seed(const nb_ssc_src* src_host, int n_src, int W, int Ns, const doub
 
 template <int WT>
 static int launch_ssc_inner(const SscInnerArgs& a, cudaStream_t st) {
-  size_t smem = (size_t)WT * a.Ns * sizeof(double2) + WT * sizeof(double);
+  size_t smem = (size_t)WT * a.Ns * sizeof(double2) + SSC_STAGES * 128 * sizeof(double2) +
+                WT * sizeof(double);
   if (smem > 200 * 1024) return NB_ETOOLARGE;
   static bool attr_set = false;
   if (!attr_set) {
