@@ -16,8 +16,12 @@ total) is the strong-scaling configuration, the others keep the per-GPU count fi
          graph replay per step); timed with CUDA events around each step, L2
          flushed between steps.
 `e2e`    the public-API loop (`PlanSampler.sample`, what get_sampler()/run_sampler()
-         build): every step's random draws go host->device from pinned memory and its
-         chain row, log-probabilities and blob records come back device->host.
+         build, with its `steps_per_graph=4` option): every step's random draws go
+         host->device from pinned memory and its chain row and log-probabilities come back
+         device->host; the host consumes one State per step.  Blob records stay in HBM
+         until get_blobs() / a State's blobs are looked at (not counted in the bytes).
+         Wall clock; the L2 flush is a node of the step graph in front of EVERY step, so
+         its own device time is inside (`value_excl_flush` subtracts it).
 `--impl reference`  the reference's CPU path: oracle restatement of naima's
          NumPy lnprob mapped over all host cores with multiprocessing.Pool, as
          core.py:446-457 + emcee do (rank 0 only).

@@ -68,6 +68,14 @@ if rank == 0:  # the blob records are read back on rank 0 only
     assert np.array_equal(b[0].value, b1[0].value) and np.array_equal(b[1].value, b1[1].value)
 else:
     assert ps.get_blobs() is None
+# several steps per CUDA graph, with steps left over that do not fill a graph
+ps4 = nb.PlanSampler(W, 4, plan, seed=seed, block=8, steps_per_graph=4)
+ps4.run_mcmc(p0, nsteps - 2)
+ps4.run_mcmc(None, 2)
+assert np.array_equal(ps4.get_chain(), ps1.get_chain())
+assert np.array_equal(ps4.get_log_prob(), ps1.get_log_prob())
+if rank == 0:
+    print("sharded PlanSampler, 4 steps per graph: chain bitwise equal", flush=True)
 # all ranks hold the same chain
 t = torch.from_numpy(ps.get_chain().copy()).cuda()
 full = [torch.empty_like(t) for _ in range(world)]
