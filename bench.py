@@ -16,12 +16,12 @@ total) is the strong-scaling configuration, the others keep the per-GPU count fi
          graph replay per step); timed with CUDA events around each step, L2
          flushed between steps.
 `e2e`    the public-API loop (`PlanSampler.sample`, what get_sampler()/run_sampler()
-         build, with its `steps_per_graph=4` option): every step's random draws go
+         build): every step's random draws go
          host->device from pinned memory and its chain row and log-probabilities come back
          device->host; the host consumes one State per step.  Blob records stay in HBM
          until get_blobs() / a State's blobs are looked at (not counted in the bytes).
-         Wall clock; the L2 flush is a node of the step graph in front of EVERY step, so
-         its own device time is inside (`value_excl_flush` subtracts it).
+         Wall clock; the L2 flush before EVERY step is inside the timed region
+         (`value_excl_flush` subtracts its own device time).
 `--impl reference`  the reference's CPU path: oracle restatement of naima's
          NumPy lnprob mapped over all host cores with multiprocessing.Pool, as
          core.py:446-457 + emcee do (rank 0 only).
@@ -540,14 +540,10 @@ def run_native(args):
         torch.cuda.synchronize()
         flush_one_s = 0.0 if args.no_flush else 1e-3 * fe[0].elapsed_time(fe[1]) / 20
 
-        # four steps per CUDA graph (a public PlanSampler option); the L2 flush is a node of
-        # that graph in front of EVERY step, so each step still starts from a cold L2
-        spg_e2e = 4
-        block = int(min(32, max(4, args.steps // 4))) // spg_e2e * spg_e2e
+        block = int(min(32, max(4, args.steps // 4)))
         sampler = nb.PlanSampler(W, wk.P, plan, seed=wl.SEED, block=block,
-                                 transport=args.transport,  # sharded over the ranks when N > 1
-                                 steps_per_graph=spg_e2e)
-        sampler._device().step_prologue = flush
+                                 transport=args.transport)  # sharded over the ranks when N > 1
+        sampler._device().before_step = flush
         # per step and rank: the draws go up, the chain row and the log-probabilities come
         # down; the blob records (model flux + blobs of every walker) stay in HBM until
         # get_blobs() / a State's blobs are looked at
@@ -575,9 +571,8 @@ def run_native(args):
                "d2h_bytes_per_step": int(d2h_step), "ms_per_step": 1e3 * e2e_t / args.steps,
                "value_excl_flush": W * args.steps / max(e2e_t - flush_s, 1e-9),
                "flush_ms_per_step": 1e3 * flush_s / args.steps, "block_steps": block,
-               "steps_per_graph": spg_e2e,
                "l2": "not flushed" if args.no_flush else
-                     "flushed before every step (%d MiB memset node inside the step graph)" % FLUSH_MIB,
+                     "flushed before every step (%d MiB memset, inside the timed region)" % FLUSH_MIB,
                "api": api}
     clk = clocks.stop()
     if rank != 0:
