@@ -336,6 +336,7 @@ int nb_ssc_outer(const double* inner, long long Rp, int N, int N_E, int W, const
  * CTA of the split == 1 combine kernel to finish (ticket in `sync`, an int32 scratch
  * word that must be zero before the first launch). */
 #define NB_TIMELINE_CAP 8192 /* half-steps kept by nb_stretch.timeline (a ring) */
+#define NB_TIMELINE_COLS 16  /* stamps per half-step */
 typedef struct nb_stretch {
   double* coords;      /* [W][P] */
   double* lp;          /* [W] */
@@ -361,11 +362,13 @@ typedef struct nb_stretch {
   const unsigned long long* wait_gen;
   int wait_world;
   int pad2_;
-  /* optional diagnostic (NULL in production): [NB_TIMELINE_CAP][8] %globaltimer stamps (ns),
-   * row (2 * *step + split) mod NB_TIMELINE_CAP of the half-step: [0] first kernel entered
-   * (CTA 0 of nb_walker_prep_move), [1] its wait for the peers' flags is over, [2] accept
-   * kernel entered (CTA 0), [3] last CTA before it releases this rank's flag (sharded runs),
-   * [4] last CTA of the accept kernel done */
+  /* optional diagnostic (NULL in production): [NB_TIMELINE_CAP][NB_TIMELINE_COLS] %globaltimer
+   * stamps (ns), row (2 * *step + split) mod NB_TIMELINE_CAP of the half-step:
+   * [0] first kernel entered (CTA 0 of nb_walker_prep_move), [1] its wait for the peers' flags is
+   * over, [2] accept kernel entered (CTA 0), [3] last CTA before it releases this rank's flag
+   * (sharded runs), [4] last CTA of the accept kernel done, [5] / [6] synchrotron kernel: CTA 0
+   * entered / last CTA done, [7] last CTA of the set-up launch done, [8] / [9] total-energy blob
+   * launch, [10] / [11] contraction kernel(s): first CTA entered / last CTA done */
   unsigned long long* timeline;
 } nb_stretch;
 int nb_walker_prep_move(const nb_stretch* mv_host, double* pars, int W, int P,
@@ -497,6 +500,13 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
  * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
 int nb_fallback_counts(unsigned long long* out_host, int reset);
+/* Preferred shared-memory carve-out (percent of the SM's L1 / shared-memory array; -1: the
+ * driver's choice, the default) that the CALLING THREAD's subsequent launches of the set-up,
+ * contraction, synchrotron and combine kernels carry as a launch attribute (recorded in the
+ * kernel node when a stream is capturing).  Kernels that run on parallel branches of one
+ * evaluation only share an SM if they ask for the same split (an SM reconfigures only when
+ * idle): a plan with a synchrotron and a tabulated component sets 50 around its launches. */
+int nb_launch_carveout(int percent);
 
 /* --- measurement aid: fp64 FMA throughput probe -------------------------------
  * Runs blocks x threads threads doing iters x 16 dependent-chain-free DFMAs each;

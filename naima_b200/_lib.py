@@ -54,6 +54,7 @@ class nb_stretch(ctypes.Structure):
 
 NB_MAX_PEERS = 16
 NB_TIMELINE_CAP = 8192
+NB_TIMELINE_COLS = 16
 
 
 class nb_peers(ctypes.Structure):
@@ -126,6 +127,7 @@ PROTOTYPES = {
     "nb_peer_wait": [ctypes.POINTER(nb_stretch), vp],
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
     "nb_fallback_counts": [ctypes.POINTER(ctypes.c_ulonglong), c_int],
+    "nb_launch_carveout": [c_int],
     "nb_kelner_table": [vp, vp, c_int, c_int, c_dbl, vp, vp, vp],
     "nb_kelner_rows": [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp],
 }

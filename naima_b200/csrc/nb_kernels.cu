@@ -36,9 +36,43 @@ using namespace nb;
 
 static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 
+// Launch with the caller's preferred shared-memory carve-out (nb_launch_carveout): an SM changes
+// its L1 / shared-memory split only when it is idle, so kernels of one evaluation that run on
+// parallel graph branches can only share an SM if they ask for the same split.  Measured on the
+// C3 half-step: without it the contraction's first CTA starts 21 us after the set-up kernel
+// ended (when synchrotron CTAs retire), with a common 50 % split 1.5 us after it.
+static thread_local int g_launch_carveout = -1;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+  if (g_launch_carveout < 0) {
+    kernel<<<grid, block, smem, st>>>(args...);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
+  at[0].val.sharedMemCarveout = (unsigned)g_launch_carveout;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#define NB_LAUNCH(...)                                   \
+  do {                                                   \
+    cudaError_t e__ = launch_k(__VA_ARGS__);             \
+    if (e__ != cudaSuccess) return (int)e__;             \
+  } while (0)
+
 // how often the lean cell had to be redone with the careful cell: [0] contraction (walker,
 // row tile) pairs, [1] self-Compton rows (x walkers per thread).  Read with nb_fallback_counts.
 __device__ unsigned long long g_fallbacks[2];
+// diagnostic timelines (nb_stretch.timeline): the row of the half-step in flight, published by
+// the set-up kernel for the kernels that do not see the stretch descriptor (the contraction)
+__device__ unsigned long long* g_timeline_row;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -85,7 +119,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // half-step have landed in our copy.  Called by whole CTAs before they read coords.
 __device__ __forceinline__ unsigned long long* timeline_row(const nb_stretch& mv) {
   return mv.timeline +
-         8 * ((size_t)(2 * *mv.step + mv.split) & (size_t)(NB_TIMELINE_CAP - 1));
+         NB_TIMELINE_COLS * ((size_t)(2 * *mv.step + mv.split) & (size_t)(NB_TIMELINE_CAP - 1));
 }
 
 __device__ __forceinline__ void wait_for_peers(const nb_stretch& mv, bool first_kernel = false) {
@@ -407,6 +441,8 @@ struct ContractArgs {
 template <int RT, int MODE>
 __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(ContractArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* const tl_row = threadIdx.x == 0 ? g_timeline_row : nullptr;  // diagnostic
+  if (tl_row && blockIdx.x == 0 && blockIdx.y == 0) tl_row[10] = global_timer_ns();
   constexpr bool EXACT = MODE == 1;
   double* sK = reinterpret_cast<double*>(smem_raw);
   double* sL = sK + (size_t)RT * a.pitch;
@@ -510,6 +546,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 1 : 3) contract_kernel(Contra
       }
     }
   }
+  if (tl_row) atomicMax(&tl_row[11], global_timer_ns());
 }
 
 // ---------------------------------------------------------------------------
@@ -576,7 +613,7 @@ __global__ void __launch_bounds__(COMBINE_WARPS * 32) combine_lnprob_kernel(
   // diagnostic time stamps (see nb_stretch.timeline); the row is fixed before the last CTA
   // can advance the step counter
   unsigned long long* tl_row = (ka.has_mv && ka.mv.timeline && threadIdx.x == 0)
-                                   ? ka.mv.timeline + 8 * ((size_t)(2 * t_step + ka.mv.split) &
+                                   ? ka.mv.timeline + NB_TIMELINE_COLS * ((size_t)(2 * t_step + ka.mv.split) &
                                                            (size_t)(NB_TIMELINE_CAP - 1))
                                    : nullptr;
   if (tl_row && blockIdx.x == 0) tl_row[2] = global_timer_ns();
@@ -817,8 +854,14 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
   const bool publish = blockIdx.y == 0;
   const double* p = a.pm.pars + (size_t)w * a.pm.P;
   __shared__ double s_q[NB_MAX_MOVE_PAR];
+  const bool setup_launch = a.pm.prior_out != nullptr;  // else: the total-energy blob launch
+  if (tid == 0 && w == 0 && blockIdx.y == 0) {
+    unsigned long long* row = (a.has_mv && a.mv.timeline) ? timeline_row(a.mv) : nullptr;
+    if (setup_launch) g_timeline_row = row;
+    else if (row) row[8] = global_timer_ns();
+  }
   if (a.has_mv) {
-    wait_for_peers(a.mv, true);
+    wait_for_peers(a.mv, setup_launch);
     // emcee stretch move: q = c - (c - s) zz, numpy's rounding (no FMA contraction)
     if (tid < a.pm.P) {
       const size_t base = ((size_t)(*a.mv.step) * 2 + a.mv.split) * a.mv.Ns + a.mv.i0 + w;
@@ -892,6 +935,8 @@ __global__ void __launch_bounds__(256) walker_prep_kernel(const __grid_constant_
     }
     if (tid == 0) J.energy_out[(size_t)w * (J.energy_stride > 0 ? J.energy_stride : 1)] = s_red[0];
   }
+  if (a.has_mv && a.mv.timeline && tid == 0)
+    atomicMax(&timeline_row(a.mv)[setup_launch ? 7 : 9], global_timer_ns());
 }
 
 // ---------------------------------------------------------------------------
@@ -1015,6 +1060,11 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
   // every slice gets the same mix of cheap and expensive energies)
   const int nsl = gridDim.y;
   const int ne = (a.N_E - (int)blockIdx.y + nsl - 1) / nsl;
+  unsigned long long* tl_row = nullptr;  // diagnostic stamps [5] entry of CTA (0,0), [6] last end
+  if (FUSED && fa->src.has_mv && fa->src.mv.timeline && threadIdx.x == 0) {
+    tl_row = timeline_row(fa->src.mv);
+    if (blockIdx.x == 0 && blockIdx.y == 0) tl_row[5] = global_timer_ns();
+  }
   if (FUSED) {
     if (fa->src.has_mv) wait_for_peers(fa->src.mv);
     if (warp == 0) {
@@ -1101,6 +1151,7 @@ __device__ __forceinline__ void synchrotron_cta(const SynArgs& a, const SynFused
     const double acc = s_part[2 * k] + s_part[2 * k + 1];
     a.out[(size_t)w * a.out_ld + e] = syn_finish(Bw, a.E_erg[e], acc);
   }
+  if (tl_row) atomicMax(&tl_row[6], global_timer_ns());
 }
 
 __global__ void __launch_bounds__(256) synchrotron_kernel(const __grid_constant__ SynArgs a) {
@@ -1693,8 +1744,7 @@ static int launch_contract(const ContractArgs& a, int smem, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((a.R + RT - 1) / RT, (a.W + a.w_per_cta - 1) / a.w_per_cta);
-  contract_kernel<RT, MODE><<<grid, 256, smem, st>>>(a);
-  NB_CHECK_LAUNCH();
+  NB_LAUNCH(contract_kernel<RT, MODE>, grid, dim3(256), (size_t)smem, st, a);
   return 0;
 }
 
@@ -1768,7 +1818,10 @@ static int syn_geometry(SynArgs& a, int N, int W, int N_E, long long* smem) {
   // photon energies per CTA: every CTA repeats the per-walker node set-up, so take as
   // many as still leaves >= 2 CTAs per SM (148 SMs), but at least one per warp
   int epc = (N_E + 7) & ~7;
-  while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 2 * 148) epc = ((epc / 2) + 7) & ~7;
+  // about 1.5 CTAs per SM: the kernel runs beside the contraction, whose CTAs need registers
+  // left over on the SMs (four synchrotron CTAs would take the whole register file: measured,
+  // the contraction then starts only when they retire)
+  while (epc > 8 && (long long)W * ((N_E + epc - 1) / epc) < 200) epc = ((epc / 2) + 7) & ~7;
   a.e_per_cta = epc;
   *smem = 6LL * N * 8 + 4LL * (epc + 1) + 16LL * epc + 8;
   return (*smem > 224 * 1024) ? NB_ETOOLARGE : 0;
@@ -1799,8 +1852,7 @@ int nb_synchrotron(const double* gam, int N, const double* gm2, const double* g2
     attr_set = true;
   }
   dim3 grid(W, (N_E + a.e_per_cta - 1) / a.e_per_cta);
-  synchrotron_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(a);
-  NB_CHECK_LAUNCH();
+  NB_LAUNCH(synchrotron_kernel, grid, dim3(256), (size_t)smem, as_stream(stream), a);
   return 0;
 }
 
@@ -1876,8 +1928,7 @@ int nb_synchrotron_fused(const nb_walker_src* src, const nb_pd_desc* pd, int b_e
     attr_set = true;
   }
   dim3 grid(W, (N_E + a.e_per_cta - 1) / a.e_per_cta);
-  synchrotron_fused_kernel<<<grid, 256, (int)smem, as_stream(stream)>>>(fa);
-  NB_CHECK_LAUNCH();
+  NB_LAUNCH(synchrotron_fused_kernel, grid, dim3(256), (size_t)smem, as_stream(stream), fa);
   return 0;
 }
 
@@ -1934,9 +1985,8 @@ static int launch_combine(const nb_peers* peers, const nb_stretch* mv, const dou
   if (W == 0) return 0;
   size_t smem = (size_t)COMBINE_WARPS * N_E * sizeof(double);
   if (smem > 48 * 1024) return NB_ETOOLARGE;
-  combine_lnprob_kernel<<<(W + COMBINE_WARPS - 1) / COMBINE_WARPS, COMBINE_WARPS * 32, smem,
-                          as_stream(stream)>>>(ka);
-  NB_CHECK_LAUNCH();
+  NB_LAUNCH(combine_lnprob_kernel, dim3((W + COMBINE_WARPS - 1) / COMBINE_WARPS),
+            dim3(COMBINE_WARPS * 32), smem, as_stream(stream), ka);
   return 0;
 }
 
@@ -2061,8 +2111,7 @@ static int launch_walker_prep(const nb_stretch* mv, double* pars_out, const doub
     if (e != cudaSuccess) return (int)e;
   }
   dim3 grid(W, a.n_items > 0 ? a.n_items : 1);
-  walker_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
-  NB_CHECK_LAUNCH();
+  NB_LAUNCH(walker_prep_kernel, grid, dim3(256), smem, as_stream(stream), a);
   return 0;
 }
 
@@ -2245,6 +2294,12 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
   dim3 grid(R, W);
   kelner_rows_kernel<<<grid, 256, smem, as_stream(stream)>>>(kind, pd_params, Ep, Kk, R, N, out);
   NB_CHECK_LAUNCH();
+  return 0;
+}
+
+int nb_launch_carveout(int percent) {
+  if (percent < -1 || percent > 100) return NB_EINVAL;
+  g_launch_carveout = percent;
   return 0;
 }
 

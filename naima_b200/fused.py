@@ -842,6 +842,19 @@ class LikelihoodPlan:
         if mv is None and ex.pack is not None:
             raise ValueError("a packed executable is driven by device-side proposals only")
         nodes = self._nodes(ex, mv)
+        # kernels of parallel branches only share an SM when they ask for the same L1 /
+        # shared-memory split (nb_launch_carveout): half and half lets contraction CTAs run
+        # beside synchrotron CTAs (C3: 0.1075 -> 0.098 ms per step)
+        kinds = {c["kind"] for c in self.comps}
+        carve = 50 if ("syn" in kinds and "table" in kinds and not self.aux) else -1
+        L = lib()
+        check(L.nb_launch_carveout(carve), "nb_launch_carveout")
+        try:
+            return self._enqueue_nodes(ex, nodes, mv, fuse_update, peers)
+        finally:
+            L.nb_launch_carveout(-1)
+
+    def _enqueue_nodes(self, ex, nodes, mv, fuse_update, peers):
         main = torch.cuda.current_stream()
         streams, tails = [main], [None]  # stream k, name of the last node launched on it
         where, done = {}, {}

@@ -394,8 +394,8 @@ class DeviceEnsemble:
         self.sync = eng.zeros(1, dtype=torch.int32)
         self._timeline = None
         if timeline:  # diagnostic: device time stamps per half-step (nb_stretch.timeline)
-            from ._lib import NB_TIMELINE_CAP
-            self._timeline = eng.zeros(NB_TIMELINE_CAP, 8, dtype=torch.int64)
+            from ._lib import NB_TIMELINE_CAP, NB_TIMELINE_COLS
+            self._timeline = eng.zeros(NB_TIMELINE_CAP, NB_TIMELINE_COLS, dtype=torch.int64)
         self.before_step = None  # host hook before every graph replay (bench.py's L2 flush)
         self.read_rows = True
         self.min_block = 0
@@ -533,7 +533,7 @@ class DeviceEnsemble:
         accept kernel done."""
         if self._timeline is None:
             raise RuntimeError("construct the ensemble with timeline=True")
-        return self._timeline.cpu().numpy()[:, :5]
+        return self._timeline.cpu().numpy()
 
     def _enqueue_step(self):
         """One ensemble step: per half, set-up (+ proposal) -> components -> combine

@@ -1,8 +1,8 @@
 """Reads the per-rank half-step time stamps bench.py --timeline wrote and prints where a
 sharded half-step's time goes (median over the timed half-steps, microseconds).
 
-columns per row h: first kernel entered, its wait over, accept kernel entered, last CTA before
-its release (0 on one GPU), accept kernel done, number of half-steps run."""
+columns per row h: nb_stretch.timeline's stamps (include/naima_b200.h), last column: number of
+half-steps run."""
 import sys
 
 import numpy as np
@@ -10,7 +10,7 @@ import numpy as np
 
 def main(prefix, world, last):
     tls = [np.load("%s%d.npy" % (prefix, r)) for r in range(world)]
-    gen = int(tls[0][0, 5])
+    gen = int(tls[0][0, -1])
     cap = tls[0].shape[0]
     hs = np.arange(max(gen - last, 1), gen - 1)  # rows are 2 t + split  # half-steps whose successor also exists
     out = {}
@@ -24,15 +24,21 @@ def main(prefix, world, last):
             "to_next_wait": b[:, 0] - a[:, 4],
             "half_step": b[:, 0] - a[:, 0],
         }
+        if t.shape[1] > 12 and a[:, 5].any():  # per-kernel stamps, relative to the set-up's start
+            for name, c0, c1 in (("synchrotron", 5, 6), ("set-up", 0, 7), ("energy blobs", 8, 9),
+                                 ("contraction", 10, 11), ("accept", 2, 4)):
+                if a[:, c1].any():
+                    seg["%s starts at" % name] = a[:, c0] - a[:, 0]
+                    seg["%s ends at" % name] = a[:, c1] - a[:, 0]
         for par in (0, 1):
             m = (hs % 2) == par
-            for k in ("evaluate", "to_next_wait", "half_step"):
+            for k in [k for k in seg if "[" not in k and k not in ("wait", "release", "accept")]:
                 seg["%s[split %d]" % (k, par)] = seg[k][m]
         out[r] = {k: (float(np.median(v)) / 1e3, float(np.percentile(v, 90)) / 1e3)
                   for k, v in seg.items()}
         print("rank %d  (median / p90 us over %d half-steps)" % (r, len(hs)))
         for k, (m, p) in out[r].items():
-            print("   %-22s %7.2f %7.2f" % (k, m, p))
+            print("   %-44s %7.2f %7.2f" % (k, m, p))
     if world == 2 and tls[0][:, 3].any():
         # one-way flag latency, clock offset removed NTP-style: the flag rank A stored at
         # a[4] lets rank B leave its wait at b[1] >= a[4] + latency + offset(B - A)
