@@ -1436,7 +1436,9 @@ __global__ void __launch_bounds__(256) ssc_outer_kernel(const __grid_constant__ 
   double acc = 0.0;
   for (int j = lane; j < a.N - 1; j += 32) {
     const double y1 = in[j], y2 = in[j + 1];
-    const double bp1 = ds[j] + log(y2 / y1) * a.invdlx[j];
+    // ln(y2 / y1) of neighbouring nodes by the atanh series (log when they differ by more
+    // than 10 %, or at zero / NaN end points, where interval_fast decides anyway)
+    const double bp1 = ds[j] + log_ratio(y1, y2) * a.invdlx[j];
     acc += interval_fast(xn[j] * y1, xn[j + 1] * y2, bp1, a.dlx[j]);
   }
   acc = warp_sum(acc);
