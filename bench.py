@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-multicast", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the N > 1 bitwise chain check")
+    ap.add_argument("--no-clocks", action="store_true",
+                    help="diagnostic: no nvidia-smi polling during the run")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (diagnostic)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the public-API loop (diagnostic)")
     ap.add_argument("--steps-per-graph", type=int, default=1,
@@ -488,7 +490,7 @@ def run_native(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local if rank == 0 else None)
+    clocks = ClockSampler(local if (rank == 0 and not args.no_clocks) else None)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps // spg)]
     eng.fallback_counts(reset=True)

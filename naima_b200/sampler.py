@@ -746,7 +746,10 @@ class PlanSampler(EnsembleSampler):
         tot = self.iteration + n
         cap = 0 if self._store_t is None else self._store_t[0].shape[0]
         if tot > cap:
-            cap = max(tot, 2 * cap, 64)
+            # at least one chunk (256 steps) from the start: pinning host memory and a fresh
+            # device allocation cost milliseconds -- on a bad day tens of them -- and a
+            # burn-in followed by the run proper should not pay them a second time
+            cap = max(tot, 2 * cap, self.chunk)
             new = (torch.empty(cap, self.nwalkers, self.ndim, dtype=torch.float64,
                                pin_memory=True),
                    torch.empty(cap, self.nwalkers, dtype=torch.float64, pin_memory=True))
