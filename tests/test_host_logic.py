@@ -323,3 +323,48 @@ def test_tablemodel_and_ebl_host_side():
         EblAbsorptionModel(0.3, "Franceschini")
     with pytest.raises(ValueError):
         EblAbsorptionModel(-0.1)
+
+
+def test_transposing_row_sum_tree_has_the_pairing_of_the_plain_tree():
+    """nb_kernels.cu: warp_sum_rows<RT> (RT row sums in one shuffle tree whose lane pairs split
+    the rows between them) against warp_sum (shfl_down by 16, 8, 4, 2, 1 per row), both
+    emulated lane by lane in float64: lane (32 / RT) * r must end up with the bits lane 0 of
+    the plain tree has for row r."""
+    rng = np.random.default_rng(11)
+
+    def plain(v):  # v[32]: value of each lane; returns lane 0's result
+        v = v.copy()
+        for o in (16, 8, 4, 2, 1):
+            nxt = v.copy()
+            for lane in range(32):
+                src = lane + o
+                nxt[lane] = v[lane] + (v[src] if src < 32 else v[lane])  # out of range: own value
+            v = nxt
+        return v[0]
+
+    def transposed(acc, RT):  # acc[32][RT]
+        acc = acc.copy()
+        off, n = 16, RT
+        while n > 1:
+            new = acc.copy()
+            for lane in range(32):
+                upper = (lane & off) != 0
+                for r in range(n // 2):
+                    send_partner = acc[lane ^ off][r] if ((lane ^ off) & off) else acc[lane ^ off][r + n // 2]
+                    keep = acc[lane][r + n // 2] if upper else acc[lane][r]
+                    new[lane][r] = keep + send_partner
+            acc = new
+            n //= 2
+            off //= 2
+        v = acc[:, 0].copy()
+        while off > 0:
+            v = np.array([v[lane] + v[lane ^ off] for lane in range(32)])
+            off //= 2
+        return v
+
+    for RT in (8, 4, 2):
+        acc = rng.normal(size=(32, RT)) * 10.0 ** rng.integers(-8, 8, size=(32, RT))
+        got = transposed(acc, RT)
+        for r in range(RT):
+            want = plain(acc[:, r])
+            assert got[(32 // RT) * r] == want, (RT, r)
