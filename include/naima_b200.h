@@ -500,6 +500,10 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
  * out_host[1]: rows of nb_ssc_inner that were (each for all walkers of its thread), since
  * the library was loaded or the last reset.  Synchronous (cudaMemcpyFromSymbol). */
 int nb_fallback_counts(unsigned long long* out_host, int reset);
+/* Diagnostic timelines (nb_stretch.timeline): call before freeing a timeline buffer -- the
+ * contraction kernel reaches the current row through a device-global pointer that the set-up
+ * kernel publishes. */
+int nb_timeline_reset(void);
 /* Preferred shared-memory carve-out (percent of the SM's L1 / shared-memory array; -1: the
  * driver's choice, the default) that the CALLING THREAD's subsequent launches of the set-up,
  * contraction, synchrotron and combine kernels carry as a launch attribute (recorded in the

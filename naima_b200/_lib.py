@@ -128,6 +128,7 @@ PROTOTYPES = {
     "nb_fp64_peak_probe": [vp, c_int, c_int, c_int, vp],
     "nb_fallback_counts": [ctypes.POINTER(ctypes.c_ulonglong), c_int],
     "nb_launch_carveout": [c_int],
+    "nb_timeline_reset": [],
     "nb_kelner_table": [vp, vp, c_int, c_int, c_dbl, vp, vp, vp],
     "nb_kelner_rows": [c_int, vp, c_int, vp, vp, c_int, c_int, vp, vp],
 }

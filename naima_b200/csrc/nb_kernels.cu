@@ -2299,6 +2299,14 @@ int nb_kelner_rows(int kind, const double* pd_params, int W, const double* Ep, c
   return 0;
 }
 
+int nb_timeline_reset(void) {
+  // the contraction kernel stamps through g_timeline_row: forget a row of a timeline buffer
+  // that is about to be freed
+  unsigned long long* null_row = nullptr;
+  cudaError_t e = cudaMemcpyToSymbol(g_timeline_row, &null_row, sizeof(null_row));
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 int nb_launch_carveout(int percent) {
   if (percent < -1 || percent > 100) return NB_EINVAL;
   g_launch_carveout = percent;

@@ -396,6 +396,18 @@ class DeviceEnsemble:
         if timeline:  # diagnostic: device time stamps per half-step (nb_stretch.timeline)
             from ._lib import NB_TIMELINE_CAP, NB_TIMELINE_COLS
             self._timeline = eng.zeros(NB_TIMELINE_CAP, NB_TIMELINE_COLS, dtype=torch.int64)
+            import weakref
+
+            from ._lib import lib
+
+            def _forget(L=lib()):  # before the buffer goes: no kernel may stamp into it
+                try:
+                    torch.cuda.synchronize()
+                    L.nb_timeline_reset()
+                except Exception:  # interpreter / CUDA context shutting down
+                    pass
+
+            weakref.finalize(self, _forget)
         self.before_step = None  # host hook before every graph replay (bench.py's L2 flush)
         self.read_rows = True
         self.min_block = 0
