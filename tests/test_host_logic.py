@@ -368,3 +368,58 @@ def test_transposing_row_sum_tree_has_the_pairing_of_the_plain_tree():
         for r in range(RT):
             want = plain(acc[:, r])
             assert got[(32 // RT) * r] == want, (RT, r)
+
+
+def test_ssc_ring_schedule_never_reads_a_stale_or_overwritten_slot():
+    """ssc_inner_kernel's cp.async ring (nb_kernels.cu): SSC_STAGES slots per thread, filled
+    SSC_STAGES - 1 intervals ahead, one commit group per interval, wait_group<SSC_STAGES - 2>
+    before interval s is read.  Emulated here with the group semantics of cp.async: when interval
+    s is read, the copy of interval s must have completed and its slot must not have been
+    refilled; a refill may only target a slot whose interval has been consumed."""
+    STAGES = 8
+    for nint in list(range(1, 40)) + [99, 128]:
+        slot_holds = [None] * STAGES     # interval whose data the slot holds (once landed)
+        groups = []                      # per committed group: list of (slot, interval)
+        landed = 0                       # groups [0, landed) have completed
+
+        def commit(copies):
+            groups.append(copies)
+
+        def wait_group(n):               # at most n most-recent groups may still be pending
+            nonlocal landed
+            upto = max(landed, len(groups) - n)
+            for g in groups[landed:upto]:
+                for slot, itv in g:
+                    slot_holds[slot] = itv
+            landed = upto
+
+        consumed = -1
+        for g in range(STAGES - 1):      # prologue
+            commit([(g, g)] if g < nint else [])
+        s = 0
+
+        def interval(s, slot):
+            nonlocal consumed
+            wait_group(STAGES - 2)
+            assert slot_holds[slot] == s, (nint, s, slot, slot_holds)
+            consumed = s
+            sn = s + STAGES - 1
+            tgt = (slot + STAGES - 1) % STAGES
+            if sn < nint:
+                # the slot being refilled held interval s - 1 (or nothing): already consumed
+                assert slot_holds[tgt] is None or slot_holds[tgt] <= consumed - 1 or \
+                    slot_holds[tgt] == s - 1, (nint, s, tgt, slot_holds)
+                commit([(tgt, sn)])
+            else:
+                commit([])
+
+        while s + STAGES <= nint:        # unrolled rounds: slot numbers are compile-time
+            for g in range(STAGES):
+                interval(s + g, g)
+            s += STAGES
+        g = 0
+        while s < nint:                  # fewer than STAGES left
+            interval(s, g)
+            s += 1
+            g += 1
+        assert consumed == nint - 1
